@@ -1,0 +1,215 @@
+/*
+ * lightgrad_b200 -- C-ABI of the sm_100a tensor backend.
+ *
+ * This is the drop-in boundary: everything lightgrad's Python backend layer
+ * needs from a device (what the reference's OpenCL backend gets from pyopencl
+ * + its JIT-built kernels) is one of the plain-C entry points below.  Host code
+ * (lightgrad_b200/autograd/cuda/*.py) reaches them with ctypes; nothing here
+ * mentions torch, numpy or Python.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from lg_last_error() (thread-local, valid until the next call);
+ *   - device pointers are void* obtained from lg_alloc (or any cudaMalloc);
+ *   - sizes, shapes and strides are int64_t, strides are in ELEMENTS;
+ *   - all work is enqueued on the library's compute stream and the call returns
+ *     immediately; only lg_sync, lg_memcpy_d2h and lg_event_sync block;
+ *   - not thread-safe by contract (the reference is single-threaded), one
+ *     device per process (data parallelism = one process per GPU).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   runtime      lightgrad/autograd/opencl/device.py:51-115 (context, queue, MemoryPool)
+ *                lightgrad/autograd/opencl/tensor.py:58-93  (allocate, enqueue_copy)
+ *   elementwise  lightgrad/autograd/opencl/kernels.py:24-195 (atom)  /  cpu/ops.py:52-229
+ *   reductions   lightgrad/autograd/opencl/kernels.py:344-501 (reduce) / cpu/ops.py:260-293
+ *   matmul       lightgrad/autograd/opencl/kernels.py:201-337 (matmul) / cpu/ops.py:107-116
+ *   indexing     lightgrad/autograd/cpu/ops.py:234-255 (getitem / setitem)
+ *   fused        lightgrad/autograd/ops.py:62-66 (softmax), lightgrad/nn.py:109-124 (LayerNorm),
+ *                lightgrad/loss.py:14-24 (cross_entropy), examples/bert.py:12 (gelu)
+ *   optimizers   lightgrad/optim.py:3-52
+ *   collectives  (none in the reference -- new: NCCL gradient all-reduce)
+ */
+#ifndef LIGHTGRAD_B200_H
+#define LIGHTGRAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_MAX_DIMS 8
+
+/* element types */
+enum LgDType {
+    LG_F32 = 0,
+    LG_F64 = 1,
+    LG_I32 = 2,
+    LG_I64 = 3,
+    LG_I16 = 4,
+    LG_U8  = 5,
+    LG_I8  = 6,
+    LG_BF16 = 7   /* internal: operand staging for the BF16 tensor-core GEMM */
+};
+
+/* elementwise operator codes (out = f(a[,b[,c]]; alpha)) */
+enum LgEwOp {
+    /* one input */
+    LG_EW_COPY = 0, LG_EW_NEG = 1, LG_EW_SIN = 2, LG_EW_COS = 3, LG_EW_EXP = 4, LG_EW_LOG = 5,
+    LG_EW_SIGMOID = 6, LG_EW_TANH = 7, LG_EW_RELU = 8, LG_EW_GELU = 9,
+    LG_EW_ADD_S = 10,   /* a + alpha          */
+    LG_EW_MUL_S = 11,   /* a * alpha          */
+    LG_EW_RSUB_S = 12,  /* alpha - a          */
+    LG_EW_RDIV_S = 13,  /* alpha / a          */
+    LG_EW_POW_S = 14,   /* a ** alpha         */
+    LG_EW_RPOW_S = 15,  /* alpha ** a         */
+    LG_EW_SQRT = 16,
+    LG_EW_DIV_S = 17,   /* a / alpha          */
+    LG_EW_FILL = 18,    /* alpha (a ignored)  */
+    /* two inputs */
+    LG_EW_ADD = 32, LG_EW_SUB = 33, LG_EW_MUL = 34, LG_EW_DIV = 35, LG_EW_POW = 36,
+    LG_EW_SIN_BWD = 40,      /* cos(a) * b                         (a = x, b = g)   */
+    LG_EW_COS_BWD = 41,      /* -sin(a) * b                                         */
+    LG_EW_LOG_BWD = 42,      /* (1 / a) * b                                         */
+    LG_EW_SIGMOID_BWD = 43,  /* a * (1 - a) * b                    (a = y)          */
+    LG_EW_TANH_BWD = 44,     /* (1 - a*a) * b                      (a = y)          */
+    LG_EW_RELU_BWD = 45,     /* b * (a >= 0)                                        */
+    LG_EW_GELU_BWD = 46,     /* gelu'(a) * b                                        */
+    LG_EW_POW_S_BWD = 47,    /* alpha * a**(alpha-1) * b                            */
+    LG_EW_RPOW_S_BWD = 48,   /* b * a * ln(alpha)                  (a = y)          */
+    LG_EW_RDIV_S_BWD = 49,   /* -alpha / a**2 * b                                   */
+    LG_EW_AXPY = 50,         /* a + alpha * b                                       */
+    /* three inputs */
+    LG_EW_DIV_BWD_B = 64,    /* -a / b**2 * c                      (c = g)          */
+    LG_EW_POW_BWD_A = 65,    /* b * a**(b-1) * c                                    */
+    LG_EW_POW_BWD_B = 66,    /* c * b * ln(a)                      (b = y)          */
+    LG_EW_EQ_MASK_MUL = 67   /* c * (a == b)                       (max/min bwd)    */
+};
+
+enum LgReduceOp { LG_RED_SUM = 0, LG_RED_MAX = 1, LG_RED_MIN = 2 };
+
+/* matmul arithmetic modes */
+enum LgGemmMode {
+    LG_GEMM_FP32_SIMT = 0,  /* exact fp32 FFMA (also the only mode for f64)       */
+    LG_GEMM_TF32_TC = 1,    /* tcgen05 kind::tf32, fp32 operands read by TMA       */
+    LG_GEMM_BF16_TC = 2     /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate  */
+};
+
+/* ---- runtime (replaces opencl/device.py + pyopencl.tools.MemoryPool) ---------------------- */
+const char* lg_last_error(void);
+int lg_device_count(int* count);
+int lg_init(int device);                 /* idempotent; binds the process to one GPU       */
+int lg_device(int* device);
+int lg_device_props(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+int lg_sync(void);                        /* drain compute + comm streams                   */
+int lg_alloc(size_t nbytes, void** ptr);  /* caching, stream-ordered; 256-byte aligned      */
+int lg_free(void* ptr);                   /* returns the block to the cache                 */
+int lg_empty_cache(void);
+int lg_mem_stats(size_t* in_use, size_t* reserved, size_t* peak_in_use);
+int lg_memcpy_h2d(void* dst, const void* src, size_t nbytes);   /* async wrt host when src is pinned */
+int lg_memcpy_d2h(void* dst, const void* src, size_t nbytes);   /* blocks until the bytes landed      */
+int lg_memcpy_d2d(void* dst, const void* src, size_t nbytes);
+int lg_memset(void* dst, int byte, size_t nbytes);
+int lg_host_alloc(size_t nbytes, void** ptr);                   /* pinned host memory */
+int lg_host_free(void* ptr);
+int lg_event_create(void** ev);
+int lg_event_record(void* ev);            /* on the compute stream */
+int lg_event_sync(void* ev);
+int lg_event_elapsed_ms(void* start, void* stop, float* ms);
+int lg_event_destroy(void* ev);
+int lg_launch_count(uint64_t* n);         /* kernels launched by this library so far */
+void* lg_stream_handle(void);             /* cudaStream_t of the compute stream, for profilers */
+
+/* ---- elementwise (replaces kernels.atom) --------------------------------------------------- */
+/* all operands contiguous, n elements, same dtype; b/c may be NULL for 1/2-input ops */
+int lg_ew_flat(int op, int dtype, const void* a, const void* b, const void* c, void* out,
+               int64_t n, double alpha);
+/* broadcast / strided form: every operand described over one common shape; a stride of 0
+ * broadcasts; s? == NULL means "contiguous over shape"; out may alias an input (in-place ops) */
+int lg_ew(int op, int dtype, int ndim, const int64_t* shape,
+          const void* a, const int64_t* sa, const void* b, const int64_t* sb,
+          const void* c, const int64_t* sc, void* out, const int64_t* so, double alpha);
+/* fused two-output backward of mul/div (kernels.atom with two outputs, opencl/ops.py:78-98):
+ * contiguous operands; kind 0: da = g*b, db = a*g;  kind 1: da = g/b, db = -a/b^2*g */
+int lg_ew_bwd2_flat(int kind, int dtype, const void* a, const void* b, const void* g,
+                    void* da, void* db, int64_t n);
+/* dtype conversion / strided gather-copy (replaces OpenCLTensor.contiguous + astype) */
+int lg_cast(int src_dtype, int dst_dtype, int ndim, const int64_t* shape,
+            const void* src, const int64_t* ssrc, void* dst, const int64_t* sdst);
+
+/* ---- reductions (replaces kernels.reduce) -------------------------------------------------- */
+/* x is a contiguous (outer, reduce, inner) block; out is (outer, inner); out = scale * reduce(x) */
+int lg_reduce(int op, int dtype, const void* x, void* out,
+              int64_t outer, int64_t reduce, int64_t inner, double scale);
+
+/* ---- matmul (replaces kernels.dot) ---------------------------------------------------------- */
+/* C[b0,b1] (M x N) = A[b0,b1] (M x K) * B[b0,b1] (K x N) (+ bias[N] if bias != NULL)
+ * element strides: A(m,k) at a + b0*sa_b0 + b1*sa_b1 + m*sa_m + k*sa_k, likewise B(k,n), C(m,n).
+ * Transposed operands are expressed through the strides -- no copies are made.
+ * accumulate != 0: C += A*B. */
+typedef struct LgGemmDesc {
+    int64_t M, N, K;
+    int64_t batch0, batch1;
+    int64_t sa_b0, sa_b1, sa_m, sa_k;
+    int64_t sb_b0, sb_b1, sb_k, sb_n;
+    int64_t sc_b0, sc_b1, sc_m, sc_n;
+} LgGemmDesc;
+int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c,
+            const void* bias, int accumulate);
+/* 1 if the tensor-core kernel can take this problem in `mode` without a fallback */
+int lg_gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d);
+
+/* ---- indexing (replaces cpu getitem/setitem with integer-array indices) -------------------- */
+/* rows: out[i, :] = src[idx[i], :]; src rows `row_stride` elements apart, row_len contiguous */
+int lg_gather_rows(int dtype, int idx_dtype, const void* src, int64_t n_src_rows, int64_t row_stride,
+                   const void* idx, int64_t n_idx, int64_t row_len, void* out);
+/* dst[idx[i], :] += src[i, :]  (scatter-add; duplicates accumulate) */
+int lg_scatter_add_rows(int dtype, int idx_dtype, void* dst, int64_t n_dst_rows, int64_t row_stride,
+                        const void* idx, int64_t n_idx, int64_t row_len, const void* src);
+/* dst[idx[i], :] = src[i, :] or = value when src == NULL  (setitem; last writer wins) */
+int lg_scatter_set_rows(int dtype, int idx_dtype, void* dst, int64_t n_dst_rows, int64_t row_stride,
+                        const void* idx, int64_t n_idx, int64_t row_len, const void* src, double value);
+/* lin[i] = sum_k wrap(idx_k[i]) * stride_k : folds up to 4 index arrays into row numbers */
+int lg_index_linearize(int n_arrays, const void* const* idx, const int* idx_dtypes,
+                       const int64_t* dim_sizes, const int64_t* dim_strides, int64_t n, int64_t* lin);
+
+/* ---- fused layers ---------------------------------------------------------------------------- */
+/* softmax over the last axis of a contiguous (rows, cols) block; x is pre-multiplied by `scale` */
+int lg_softmax_fwd(int dtype, const void* x, void* y, int64_t rows, int64_t cols, double scale);
+/* dx = scale * y * (g - sum(g*y)) */
+int lg_softmax_bwd(int dtype, const void* y, const void* g, void* dx, int64_t rows, int64_t cols, double scale);
+/* loss_rows[i] = logsumexp(x[i,:]) - x[i,label[i]];  lse[i] saved for backward */
+int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, const void* labels,
+                         void* loss_rows, void* lse, int64_t rows, int64_t cols);
+/* dlogits[i,j] = (exp(x[i,j]-lse[i]) - [j==label[i]]) * gscale[0] / rows ; may run in place on logits */
+int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, const void* labels, const void* lse,
+                         const void* gscale, void* dlogits, int64_t rows, int64_t cols);
+/* layer norm over the last axis (nn.py:109-124): y = (x-mean)/sqrt(var+eps)*gamma+beta */
+int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y,
+                     void* mean, void* rstd, int64_t rows, int64_t cols, double eps);
+int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd,
+                     const void* g, void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols);
+
+/* ---- optimizers (replaces the per-parameter python loops of optim.py) ----------------------- */
+/* all tensors of one optimizer live in flat fp32 arenas; `seg_end_dev[i]` (device, int64) is the
+ * exclusive end offset of tensor i.  Tensor i uses step count t = t0 + i + 1 in its bias
+ * corrections 1 - beta^t (the reference advances t once per parameter, optim.py:36-37).        */
+int lg_sgd_step(void* param, const void* grad, void* delta, int64_t n, double lr, double momentum);
+int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, int64_t n,
+                 int n_seg, const int64_t* seg_end_dev, int64_t t0,
+                 double lr, double beta1, double beta2, double eps);
+
+/* ---- collectives (new; NCCL over NVLink, one process per GPU) ------------------------------- */
+int lg_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId */
+int lg_nccl_init(const void* id128, int world, int rank);
+int lg_nccl_allreduce_f32(void* buf, int64_t n, int average, int on_comm_stream);
+int lg_nccl_broadcast(void* buf, int64_t nbytes, int root);
+int lg_nccl_wait(void);                                   /* compute stream waits for comm stream */
+int lg_nccl_fork(void);                                   /* comm stream waits for compute stream */
+int lg_nccl_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTGRAD_B200_H */

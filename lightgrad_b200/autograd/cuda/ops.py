@@ -1,0 +1,1136 @@
+"""Operators of the CUDA backend, registered on CudaTensor.
+
+Same op names, argument meaning and gradient conventions as the reference's CPU backend
+(lightgrad/autograd/cpu/ops.py) and the union with its OpenCL backend (opencl/ops.py); every
+Function below cites the reference op it stands in for.  Conventions kept on purpose
+(SURVEY.md F4): every result has requires_grad=True, relu' is 1 at 0, max/min send the full
+gradient to every tie.  Divergence kept on purpose: getitem backward is scatter-ADD.
+
+Host side only: shape/stride bookkeeping and kernel selection.  All arithmetic happens in
+liblightgrad_b200.so.
+"""
+import os
+import ctypes as C
+import numpy as np
+from ..func import Function
+from ..tensor import AbstractTensor
+from .tensor import CudaTensor, i64arr, contiguous_strides, _prod
+from . import runtime as rt
+
+EW, RED = rt.EW, rt.RED
+_SCALARS = (int, float, np.integer, np.floating, bool, np.bool_)
+
+# ---------------------------------------------------------------------------------------------------
+# matmul arithmetic mode: 'fp32' (exact FFMA, default), 'tf32' or 'bf16' (tcgen05 tensor cores)
+_MODES = {'fp32': rt.GEMM_FP32_SIMT, 'tf32': rt.GEMM_TF32_TC, 'bf16': rt.GEMM_BF16_TC}
+_matmul_mode = _MODES[os.environ.get('LG_MATMUL_MODE', 'fp32').lower()]
+
+
+def set_matmul_mode(name):
+    """Select how float32 matmuls are computed: 'fp32' | 'tf32' | 'bf16'.  Returns the previous mode name."""
+    global _matmul_mode
+    prev = get_matmul_mode()
+    _matmul_mode = _MODES[name.lower()]
+    return prev
+
+
+def get_matmul_mode():
+    return [k for k, v in _MODES.items() if v == _matmul_mode][0]
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+def _is_scalar(v):
+    return isinstance(v, _SCALARS) or (isinstance(v, np.ndarray) and v.ndim == 0)
+
+
+def _as_tensor(v, like):
+    """Promote array-likes that reach an op (ndarray, list) to a CudaTensor."""
+    if isinstance(v, CudaTensor):
+        return v
+    if isinstance(v, AbstractTensor):
+        raise AssertionError("All Tensors must be of the same type!")
+    a = np.asarray(v)
+    if a.dtype == np.float64 and not isinstance(v, np.ndarray):
+        a = a.astype(like.dtype)
+    return CudaTensor.from_numpy(a, requires_grad=False)
+
+
+def _float_like(t):
+    """Arithmetic kernels are float32/float64; integer operands are promoted like numpy's true division."""
+    if t._code in (rt.F32, rt.F64):
+        return t
+    return t.astype(np.float64 if t._code == rt.I64 else np.float32)
+
+
+def _promote(a, b):
+    a, b = _float_like(a), _float_like(b)
+    if a._code != b._code:
+        a, b = a.astype(np.float64), b.astype(np.float64)
+    return a, b
+
+
+def _bshape(sa, sb):
+    if sa == sb:
+        return sa
+    n = max(len(sa), len(sb))
+    pa, pb = (1,) * (n - len(sa)) + sa, (1,) * (n - len(sb)) + sb
+    out = []
+    for x, y in zip(pa, pb):
+        if x != y and x != 1 and y != 1:
+            raise ValueError("operands could not be broadcast together with shapes %s %s" % (sa, sb))
+        out.append(y if x == 1 else x)
+    return tuple(out)
+
+
+def _bstrides(t, shape):
+    """Strides of ``t`` viewed over the broadcast ``shape`` (0 where t is expanded)."""
+    lead = len(shape) - len(t._shape)
+    st = [0] * lead
+    for s, have, stride in zip(shape[lead:], t._shape, t._strides):
+        st.append(stride if have == s and s != 1 else 0)
+    return st
+
+
+def _ew1(op, a, alpha=0.0, out=None):
+    if out is None:
+        out = CudaTensor._new(a._shape, a._dtype)
+    if a._numel == 0:
+        return out
+    if a._contig and out._contig:
+        rt.api.ew_flat(op, a._code, a.ptr, None, None, out.ptr, a._numel, alpha)
+    else:
+        rt.api.ew(op, a._code, len(a._shape), i64arr(a._shape), a.ptr, i64arr(a._strides), None, None, None, None,
+                  out.ptr, i64arr(out._strides), alpha)
+    return out
+
+
+def _ewn(op, operands, alpha=0.0, out=None):
+    """out = op(*operands) with numpy broadcasting; operands are CudaTensors of one float dtype."""
+    shape = operands[0]._shape
+    same = True
+    for t in operands[1:]:
+        if t._shape != shape:
+            same = False
+            shape = _bshape(shape, t._shape)
+    if out is None:
+        out = CudaTensor._new(shape, operands[0]._dtype)
+    elif out._shape != shape:
+        raise ValueError("non-broadcastable output operand with shape %s doesn't match the broadcast shape %s"
+                         % (out._shape, shape))
+    n = out._numel
+    if n == 0:
+        return out
+    code = operands[0]._code
+    if same and out._contig and all(t._contig for t in operands):
+        p = [t.ptr for t in operands] + [None, None]
+        rt.api.ew_flat(op, code, p[0], p[1], p[2], out.ptr, n, alpha)
+        return out
+    args = []
+    for t in operands:
+        args += [t.ptr, i64arr(_bstrides(t, shape))]
+    while len(args) < 6:
+        args += [None, None]
+    rt.api.ew(op, code, len(shape), i64arr(shape), *args, out.ptr, i64arr(out._strides), alpha)
+    return out
+
+
+def _assign(dst, val):
+    """dst[...] = val with numpy broadcasting of ``val``; ``dst`` may be any strided view."""
+    if val._code != dst._code:
+        val = val.astype(dst._dtype)
+    shp = dst._shape
+    if _bshape(shp, val._shape) != shp:
+        raise ValueError("could not broadcast input from shape %s into shape %s" % (val._shape, shp))
+    if dst._numel:
+        rt.api.cast(dst._code, dst._code, len(shp), i64arr(shp), val.ptr, i64arr(_bstrides(val, shp)),
+                    dst.ptr, i64arr(dst._strides))
+
+
+def _unbroadcast(g, shape):
+    """Sum ``g`` down to ``shape`` (what Function._deliver would do later, done eagerly where it is cheaper)."""
+    if g._shape == shape:
+        return g
+    lead = len(g._shape) - len(shape)
+    axes = tuple(range(lead)) + tuple(lead + i for i, (x, y) in enumerate(zip(shape, g._shape[lead:])) if x != y)
+    return _reduce(RED['SUM'], g, axes, True).reshape(*shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+# transformations (cpu/ops.py:25-47, opencl/ops.py:9-36)
+@CudaTensor.register_op()
+@CudaTensor.register_op("T")
+class transpose(Function):
+    def forward(ctx, a, *axes):
+        nd = len(a._shape)
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            axes = tuple(axes[0])
+        if len(axes) == 0:
+            axes = tuple(reversed(range(nd)))
+        axes = tuple(ax % nd for ax in axes)
+        assert sorted(axes) == list(range(nd)), "axes don't match tensor"
+        ctx.save_for_backward(axes)
+        return a._view(tuple(a._shape[i] for i in axes), tuple(a._strides[i] for i in axes))
+
+    def backward(ctx, out_grad):
+        axes, = ctx.get_saved_tensors()
+        inv = [0] * len(axes)
+        for i, j in enumerate(axes):
+            inv[j] = i
+        return out_grad.transpose(*inv)
+
+
+def _reshape_strides(shape, strides, new_shape):
+    """Strides that express ``new_shape`` over the same memory, or None if a copy is needed."""
+    old = [(s, st) for s, st in zip(shape, strides) if s != 1]
+    new_strides, oi = [], 0
+    ni, n_new = 0, len(new_shape)
+    if _prod(shape) == 0:
+        return contiguous_strides(new_shape)
+    while ni < n_new:
+        if new_shape[ni] == 1:
+            new_strides.append(1)
+            ni += 1
+            continue
+        if oi >= len(old):
+            return None
+        # grow a group of old dims and a group of new dims until their sizes agree
+        osz, ost_last = old[oi][0], old[oi][1]
+        oj = oi + 1
+        nsz, nj = new_shape[ni], ni + 1
+        while osz != nsz:
+            if osz < nsz:
+                if oj >= len(old):
+                    return None
+                # old dims in one group must be mutually contiguous
+                if old[oj - 1][1] != old[oj][0] * old[oj][1]:
+                    return None
+                osz *= old[oj][0]
+                ost_last = old[oj][1]
+                oj += 1
+            else:
+                if nj >= n_new:
+                    return None
+                nsz *= new_shape[nj]
+                nj += 1
+        # check contiguity inside the old group when it spans several dims
+        for k in range(oi, oj - 1):
+            if old[k][1] != old[k + 1][0] * old[k + 1][1]:
+                return None
+        # lay the new group's strides down from the innermost old stride
+        acc = old[oj - 1][1]
+        grp = []
+        for k in range(nj - 1, ni - 1, -1):
+            grp.append(acc)
+            acc *= new_shape[k]
+        new_strides.extend(reversed(grp))
+        oi, ni = oj, nj
+    return tuple(new_strides)
+
+
+@CudaTensor.register_op()
+class reshape(Function):
+    def forward(ctx, a, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        shape = tuple(int(s) for s in shape)
+        if -1 in shape:
+            known = -_prod(shape)
+            shape = tuple(s if s != -1 else (a._numel // known if known else 0) for s in shape)
+        assert _prod(shape) == a._numel, "cannot reshape tensor of size %d into shape %s" % (a._numel, shape)
+        ctx.save_for_backward(a._shape)
+        st = contiguous_strides(shape) if a._contig else _reshape_strides(a._shape, a._strides, shape)
+        if st is None:
+            a = a.copy()
+            a._temp = False
+            st = contiguous_strides(shape)
+        out = a._view(shape, st)
+        return out
+
+    def backward(ctx, out_grad):
+        shape, = ctx.get_saved_tensors()
+        return out_grad.reshape(*shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+# elementwise arithmetic (cpu/ops.py:52-105, opencl/ops.py:40-114)
+@CudaTensor.register_op()
+class neg(Function):
+    def forward(ctx, a):
+        return _ew1(EW['NEG'], _float_like(a))
+
+    def backward(ctx, out_grad):
+        return _ew1(EW['NEG'], out_grad)
+
+
+def _binary_forward(ctx, a, b, op, s_op, rs_op):
+    """Common forward for add/sub/mul/div/pow: tensor-tensor, tensor-scalar and scalar-tensor."""
+    if not isinstance(a, CudaTensor):
+        if _is_scalar(a):
+            b = _float_like(b)
+            ctx.kind = ('rs', float(a))
+            return _ew1(rs_op, b, float(a)) if rs_op is not None else None
+        a = _as_tensor(a, b)
+    if not isinstance(b, CudaTensor):
+        if _is_scalar(b):
+            a = _float_like(a)
+            ctx.kind = ('s', float(b))
+            return _ew1(s_op, a, float(b)) if s_op is not None else None
+        b = _as_tensor(b, a)
+    a, b = _promote(a, b)
+    ctx.kind = ('tt', None)
+    ctx.operands = (a, b)
+    return _ewn(op, (a, b))
+
+
+@CudaTensor.register_op()
+class add(Function):
+    def forward(ctx, a, b):
+        return _binary_forward(ctx, a, b, EW['ADD'], EW['ADD_S'], EW['ADD_S'])
+
+    def backward(ctx, out_grad):
+        return out_grad, out_grad
+
+
+@CudaTensor.register_op(overwrite=True)
+@CudaTensor.register_op("__sub__", overwrite=True)
+class sub(Function):
+    def forward(ctx, a, b):
+        if _is_scalar(b) and isinstance(a, CudaTensor):
+            ctx.kind = ('s', float(b))
+            return _ew1(EW['ADD_S'], _float_like(a), -float(b))
+        return _binary_forward(ctx, a, b, EW['SUB'], None, EW['RSUB_S'])
+
+    def backward(ctx, out_grad):
+        return out_grad, _ew1(EW['NEG'], out_grad)
+
+
+@CudaTensor.register_op("__rsub__", overwrite=True)
+class rsub(Function):
+    """a - b with b the tensor (ops.py:38-42 of the reference)."""
+    def forward(ctx, b, a):
+        if _is_scalar(a):
+            return _ew1(EW['RSUB_S'], _float_like(b), float(a))
+        a = _as_tensor(a, b)
+        a, b = _promote(a, b)
+        return _ewn(EW['SUB'], (a, b))
+
+    def backward(ctx, out_grad):
+        return _ew1(EW['NEG'], out_grad), out_grad
+
+
+@CudaTensor.register_op()
+class mul(Function):
+    def forward(ctx, a, b):
+        out = _binary_forward(ctx, a, b, EW['MUL'], EW['MUL_S'], EW['MUL_S'])
+        if ctx.kind[0] == 'tt':
+            for t in ctx.operands:
+                t._mark_shared()
+        return out
+
+    def backward(ctx, out_grad):
+        kind, s = ctx.kind
+        if kind != 'tt':
+            g = _ew1(EW['MUL_S'], out_grad, s)
+            return g, g
+        a, b = ctx.operands
+        g = out_grad if out_grad._code == a._code else out_grad.astype(a._dtype)
+        if a._shape == b._shape == g._shape and a._contig and b._contig and g._contig:
+            da, db = CudaTensor._new(a._shape, a._dtype), CudaTensor._new(a._shape, a._dtype)
+            if a._numel:
+                rt.api.ew_bwd2_flat(0, a._code, a.ptr, b.ptr, g.ptr, da.ptr, db.ptr, a._numel)
+            return da, db
+        # broadcast operands: reduce eagerly so the big temporaries die here
+        return _unbroadcast(_ewn(EW['MUL'], (g, b)), a._shape), _unbroadcast(_ewn(EW['MUL'], (a, g)), b._shape)
+
+
+@CudaTensor.register_op(overwrite=True)
+@CudaTensor.register_op("__truediv__", overwrite=True)
+class div(Function):
+    def forward(ctx, a, b):
+        out = _binary_forward(ctx, a, b, EW['DIV'], EW['DIV_S'], EW['RDIV_S'])
+        if ctx.kind[0] == 'tt':
+            for t in ctx.operands:
+                t._mark_shared()
+        elif ctx.kind[0] == 'rs':
+            ctx.operands = (_float_like(b),)
+        return out
+
+    def backward(ctx, out_grad):
+        kind, s = ctx.kind
+        if kind == 's':
+            g = _ew1(EW['DIV_S'], out_grad, s)
+            return g, g
+        if kind == 'rs':
+            g = _ewn(EW['RDIV_S_BWD'], (ctx.operands[0], out_grad), s)
+            return g, g
+        a, b = ctx.operands
+        g = out_grad if out_grad._code == a._code else out_grad.astype(a._dtype)
+        if a._shape == b._shape == g._shape and a._contig and b._contig and g._contig:
+            da, db = CudaTensor._new(a._shape, a._dtype), CudaTensor._new(a._shape, a._dtype)
+            if a._numel:
+                rt.api.ew_bwd2_flat(1, a._code, a.ptr, b.ptr, g.ptr, da.ptr, db.ptr, a._numel)
+            return da, db
+        return (_unbroadcast(_ewn(EW['DIV'], (g, b)), a._shape),
+                _unbroadcast(_ewn(EW['DIV_BWD_B'], (a, b, g)), b._shape))
+
+
+@CudaTensor.register_op("__rtruediv__", overwrite=True)
+class rdiv(Function):
+    """a / b with b the tensor (ops.py:43-47 of the reference)."""
+    def forward(ctx, b, a):
+        b = _float_like(b)
+        if _is_scalar(a):
+            ctx.s, ctx.b = float(a), b
+            b._mark_shared()
+            return _ew1(EW['RDIV_S'], b, float(a))
+        a = _as_tensor(a, b)
+        a, b = _promote(a, b)
+        ctx.s, ctx.a, ctx.b = None, a, b
+        return _ewn(EW['DIV'], (a, b))
+
+    def backward(ctx, out_grad):
+        if ctx.s is not None:
+            g = _ewn(EW['RDIV_S_BWD'], (ctx.b, out_grad), ctx.s)
+            return g, g
+        return (_unbroadcast(_ewn(EW['DIV_BWD_B'], (ctx.a, ctx.b, out_grad)), ctx.b._shape),
+                _unbroadcast(_ewn(EW['DIV'], (out_grad, ctx.b)), ctx.a._shape))
+
+
+@CudaTensor.register_op()
+class pow(Function):
+    def forward(ctx, a, b):
+        if isinstance(a, CudaTensor) and _is_scalar(b):
+            a = _float_like(a)
+            e = float(b)
+            ctx.kind = ('s', e)
+            ctx.operands = (a,)
+            a._mark_shared()
+            # numpy evaluates these exponents with exact kernels (square / sqrt / reciprocal)
+            if e == 2.0:
+                return _ewn(EW['MUL'], (a, a))
+            if e == 0.5:
+                return _ew1(EW['SQRT'], a)
+            if e == -1.0:
+                return _ew1(EW['RDIV_S'], a, 1.0)
+            if e == 1.0:
+                return _ew1(EW['COPY'], a)
+            return _ew1(EW['POW_S'], a, e)
+        if _is_scalar(a):
+            b = _float_like(b)
+            y = _ew1(EW['RPOW_S'], b, float(a))
+            ctx.kind = ('rs', float(a))
+            ctx.operands = (y,)
+            y._mark_shared()
+            return y
+        out = _binary_forward(ctx, a, b, EW['POW'], None, None)
+        out._mark_shared()
+        ctx.operands = ctx.operands + (out,)
+        return out
+
+    def backward(ctx, out_grad):
+        kind, s = ctx.kind
+        if kind == 's':
+            # the reference also evaluates ln(a) for the (non-tensor) exponent and discards it
+            g = _ewn(EW['POW_S_BWD'], (ctx.operands[0], out_grad), s)
+            return g, g
+        if kind == 'rs':
+            g = _ewn(EW['RPOW_S_BWD'], (ctx.operands[0], out_grad), s)
+            return g, g
+        a, b, y = ctx.operands
+        g = out_grad if out_grad._code == a._code else out_grad.astype(a._dtype)
+        return (_unbroadcast(_ewn(EW['POW_BWD_A'], (a, b, g)), a._shape),
+                _unbroadcast(_ewn(EW['POW_BWD_B'], (a, y, g)), b._shape))
+
+
+# ---------------------------------------------------------------------------------------------------
+# in-place operators (cpu/ops.py:120-157, opencl/ops.py:136-177): mutate the operand's storage and
+# hand back a new wrapper over the same memory, exactly as the reference adapters do.
+def _inplace(op, s_op, negate=False):
+    class _Op(Function):
+        def forward(ctx, t, other):
+            if _is_scalar(other):
+                v = -float(other) if negate else float(other)
+                if t._code not in (rt.F32, rt.F64):
+                    raise TypeError("in-place arithmetic needs a float tensor")
+                _ew1(s_op, t, v, out=t)
+            else:
+                other = _as_tensor(other, t)
+                if other._code != t._code:
+                    other = other.astype(t._dtype)
+                _ewn(op, (t, other), out=t)
+            return t._view(t._shape, t._strides)
+    return _Op
+
+
+for _name, _op, _sop, _neg in (('__iadd__', EW['ADD'], EW['ADD_S'], False),
+                               ('__isub__', EW['SUB'], EW['ADD_S'], True),
+                               ('__imul__', EW['MUL'], EW['MUL_S'], False),
+                               ('__itruediv__', EW['DIV'], EW['DIV_S'], False)):
+    _cls = _inplace(_op, _sop, _neg)
+    _cls.__name__ = _name.strip('_')
+    CudaTensor.register_op(_name, _cls, overwrite=True)
+
+
+@CudaTensor.register_op()
+class fill(Function):
+    def forward(ctx, t, val):
+        t._fill_value(val)
+        return t._view(t._shape, t._strides)
+
+
+# ---------------------------------------------------------------------------------------------------
+# unary math (cpu/ops.py:158-229, opencl/ops.py:182-288)
+def _unary(name, fwd_op, bwd_op, save_output):
+    class _Op(Function):
+        def forward(ctx, t):
+            t = _float_like(t)
+            y = _ew1(fwd_op, t)
+            ctx.save_for_backward(y if save_output else t)
+            return y
+
+        def backward(ctx, out_grad):
+            s, = ctx.get_saved_tensors()
+            g = out_grad if out_grad._code == s._code else out_grad.astype(s._dtype)
+            return _ewn(bwd_op, (s, g))
+    _Op.__name__ = name
+    return _Op
+
+
+for _name, _f, _b, _so, _ow in (('sin', 'SIN', 'SIN_BWD', False, False), ('cos', 'COS', 'COS_BWD', False, False),
+                                ('exp', 'EXP', 'MUL', True, False), ('log', 'LOG', 'LOG_BWD', False, False),
+                                ('sigmoid', 'SIGMOID', 'SIGMOID_BWD', True, True),
+                                ('tanh', 'TANH', 'TANH_BWD', True, True),
+                                ('relu', 'RELU', 'RELU_BWD', False, False),
+                                ('gelu', 'GELU', 'GELU_BWD', False, False)):
+    CudaTensor.register_op(_name, _unary(_name, EW[_f], EW[_b], _so), overwrite=_ow)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reductions (cpu/ops.py:260-293, opencl/ops.py:335-400)
+def _norm_axes(axis, nd):
+    if axis is None:
+        return tuple(range(nd))
+    if isinstance(axis, (int, np.integer)):
+        axis = (int(axis),)
+    return tuple(sorted(set(int(a) % nd for a in axis))) if nd else ()
+
+
+def _reduce(op, x, axes, keepdims, scale=1.0):
+    """Reduce contiguous runs of axes with one (outer, reduce, inner) kernel each."""
+    x = _float_like(x)
+    nd = len(x._shape)
+    axes = _norm_axes(axes, nd)
+    full_shape = x._shape
+    if x._numel == 0:
+        raise ValueError("zero-size array to reduction operation")
+    cur = x.contiguous()
+    shape = list(full_shape)
+    # group adjacent axes, reduce from the last group to the first so earlier dims keep their place
+    groups, run = [], []
+    for a in axes:
+        if run and a == run[-1] + 1:
+            run.append(a)
+        else:
+            if run:
+                groups.append(run)
+            run = [a]
+    if run:
+        groups.append(run)
+    for gi, grp in enumerate(reversed(groups)):
+        lo, hi = grp[0], grp[-1] + 1
+        outer, red, inner = _prod(shape[:lo]), _prod(shape[lo:hi]), _prod(shape[hi:])
+        for a in grp:
+            shape[a] = 1
+        out = CudaTensor._new(tuple(shape), cur._dtype)
+        last = gi == len(groups) - 1
+        rt.api.reduce(op, cur._code, cur.ptr, out.ptr, outer, red, inner, scale if last else 1.0)
+        cur = out
+    if not groups:
+        cur = x.copy() if scale == 1.0 else _ew1(EW['MUL_S'], x, scale)
+    if not keepdims:
+        final = tuple(s for i, s in enumerate(full_shape) if i not in axes)
+        temp = cur._temp
+        cur = cur._view(final, contiguous_strides(final))
+        cur._temp = temp
+    return cur
+
+
+def _keep_shape(shape, axes):
+    return tuple(1 if i in axes else s for i, s in enumerate(shape))
+
+
+def _extreme(name, red_op):
+    class _Op(Function):
+        def forward(ctx, x, axis=None, keepdims=False):
+            x = _float_like(x)
+            axes = _norm_axes(axis, len(x._shape))
+            val = _reduce(red_op, x, axes, True)
+            val._temp = False
+            ctx.save_for_backward(x, val, axes)
+            if keepdims:
+                return val._view(val._shape, val._strides)
+            final = tuple(s for i, s in enumerate(x._shape) if i not in axes)
+            return val._view(final, contiguous_strides(final))
+
+        def backward(ctx, out_grad):
+            x, val, axes = ctx.get_saved_tensors()
+            g = out_grad._view(val._shape, contiguous_strides(val._shape)) if out_grad._contig \
+                else out_grad.contiguous()._view(val._shape, contiguous_strides(val._shape))
+            if g._code != x._code:
+                g = g.astype(x._dtype)
+            return _ewn(EW['EQ_MASK_MUL'], (x, val, g))
+    _Op.__name__ = name
+    return _Op
+
+
+CudaTensor.register_op('max', _extreme('max', RED['MAX']))
+CudaTensor.register_op('min', _extreme('min', RED['MIN']))
+
+
+@CudaTensor.register_op()
+class sum(Function):
+    def forward(ctx, t, axis=None, keepdims=False):
+        axes = _norm_axes(axis, len(t._shape))
+        ctx.save_for_backward(t._shape, axes)
+        return _reduce(RED['SUM'], t, axes, keepdims)
+
+    def backward(ctx, out_grad):
+        # broadcast back as a zero-stride view (as opencl/ops.py:344-368); materialised on accumulation
+        shape, axes = ctx.get_saved_tensors()
+        kshape = _keep_shape(shape, axes)
+        g = out_grad if out_grad._contig else out_grad.contiguous()
+        kst = contiguous_strides(kshape)
+        st = tuple(0 if (i in axes or kshape[i] == 1) else kst[i] for i in range(len(shape)))
+        return g._view(shape, st)
+
+
+@CudaTensor.register_op(overwrite=True)
+class mean(Function):
+    """sum * (numel_out / numel_in) in one reduction (generic form: ops.py:71-75 of the reference)."""
+    def forward(ctx, t, axis=None, keepdims=False):
+        axes = _norm_axes(axis, len(t._shape))
+        n_red = _prod(tuple(t._shape[a] for a in axes))
+        ctx.save_for_backward(t._shape, axes, 1.0 / n_red)
+        return _reduce(RED['SUM'], t, axes, keepdims, scale=1.0 / n_red)
+
+    def backward(ctx, out_grad):
+        shape, axes, scale = ctx.get_saved_tensors()
+        kshape = _keep_shape(shape, axes)
+        g = _ew1(EW['MUL_S'], out_grad if out_grad._contig else out_grad.contiguous(), scale)
+        kst = contiguous_strides(kshape)
+        st = tuple(0 if (i in axes or kshape[i] == 1) else kst[i] for i in range(len(shape)))
+        return g._view(shape, st)
+
+
+# ---------------------------------------------------------------------------------------------------
+# matmul (cpu/ops.py:107-116, opencl/ops.py:116-132 + kernels.py:201-337)
+def _collapse_batch(shape, strides_list):
+    """Merge batch dims that are jointly mergeable for every operand.  Returns (shape, [strides...])."""
+    dims = [(s, [st[i] for st in strides_list]) for i, s in enumerate(shape) if s != 1]
+    if not dims:
+        return [], [[] for _ in strides_list]
+    out = [dims[0]]
+    for s, sts in dims[1:]:
+        ps, psts = out[-1]
+        if all(p == s * q for p, q in zip(psts, sts)):
+            out[-1] = (ps * s, sts)
+        else:
+            out.append((s, sts))
+    return [d[0] for d in out], [[d[1][k] for d in out] for k in range(len(strides_list))]
+
+
+def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
+    """out[..., M, N] = a[..., M, K] @ b[..., K, N] for float CudaTensors of >= 2 dims (views welcome)."""
+    M, K = a._shape[-2:]
+    K2, N = b._shape[-2:]
+    if K != K2:
+        raise ValueError("matmul: shapes %s and %s are not aligned" % (a._shape, b._shape))
+    ba, bb = a._shape[:-2], b._shape[:-2]
+    bshape = _bshape(ba, bb)
+    if out is None:
+        out = CudaTensor._new(bshape + (M, N), a._dtype)
+    sa = _bstrides(a._view(ba, a._strides[:-2]), bshape) if bshape else []
+    sb = _bstrides(b._view(bb, b._strides[:-2]), bshape) if bshape else []
+    sc = list(out._strides[:-2])
+    cshape, (csa, csb, csc) = _collapse_batch(bshape, [sa, sb, sc])
+    if len(cshape) > 2:
+        # rare: more than two irreducible batch dims -> densify the operands once
+        a2 = a.contiguous() if not a._contig else a
+        b2 = b.contiguous() if not b._contig else b
+        if len(_collapse_batch(bshape, [_bstrides(a2._view(ba, a2._strides[:-2]), bshape),
+                                       _bstrides(b2._view(bb, b2._strides[:-2]), bshape), sc])[0]) > 2:
+            a2 = _ew1(EW['COPY'], a._view(bshape + (M, K), tuple(sa) + a._strides[-2:]))
+            b2 = _ew1(EW['COPY'], b._view(bshape + (K, N), tuple(sb) + b._strides[-2:]))
+        return _gemm(a2, b2, out, bias, accumulate, mode)
+    while len(cshape) < 2:
+        cshape.insert(0, 1)
+        csa.insert(0, 0)
+        csb.insert(0, 0)
+        csc.insert(0, 0)
+    d = rt.GemmDesc(M, N, K, cshape[0], cshape[1],
+                    csa[0], csa[1], a._strides[-2], a._strides[-1],
+                    csb[0], csb[1], b._strides[-2], b._strides[-1],
+                    csc[0], csc[1], out._strides[-2], out._strides[-1])
+    if out._numel:
+        if K == 0:
+            out._fill_value(0)
+        else:
+            rt.api.gemm(_matmul_mode if mode is None else mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr,
+                        bias.ptr if bias is not None else None, 1 if accumulate else 0)
+    return out
+
+
+def _fold_rows(t):
+    """View (..., M, K) as (prod(...)*M, K) without copying when the leading dims are mergeable, else copy."""
+    if len(t._shape) == 2:
+        return t
+    rows = _prod(t._shape[:-1])
+    st = _reshape_strides(t._shape, t._strides, (rows, t._shape[-1]))
+    if st is None:
+        t = t.copy()
+        st = contiguous_strides((rows, t._shape[-1]))
+    return t._view((rows, t._shape[-1]), st)
+
+
+def _swap_last(t):
+    return t._view(t._shape[:-2] + (t._shape[-1], t._shape[-2]), t._strides[:-2] + (t._strides[-1], t._strides[-2]))
+
+
+@CudaTensor.register_op()
+@CudaTensor.register_op("__matmul__")
+class dot(Function):
+    def forward(ctx, a, b):
+        if not isinstance(b, CudaTensor):
+            b = _as_tensor(b, a)
+        a, b = _promote(a, b)
+        ctx.va, ctx.vb = len(a._shape) == 1, len(b._shape) == 1
+        if ctx.va:
+            a = a._view((1,) + a._shape, (0,) + a._strides)
+        if ctx.vb:
+            b = b._view(b._shape + (1,), b._strides + (0,))
+        a._mark_shared()
+        b._mark_shared()
+        ctx.save_for_backward(a, b)
+        if len(b._shape) == 2 and len(a._shape) > 2:
+            # (batch.., M, K) @ (K, N): one GEMM with M' = batch*M
+            a2 = _fold_rows(a)
+            out = _gemm(a2, b)
+            out = out._view(a._shape[:-1] + (b._shape[-1],), None)
+            out._temp = True
+        else:
+            out = _gemm(a, b)
+        if ctx.va or ctx.vb:
+            shp = list(out._shape)
+            if ctx.vb:
+                shp.pop(-1)
+            if ctx.va:
+                shp.pop(-2 if not ctx.vb else -1)
+            out = out._view(tuple(shp), None)
+            out._temp = True
+        return out
+
+    def backward(ctx, out_grad):
+        a, b = ctx.get_saved_tensors()
+        g = out_grad if out_grad._code == a._code else out_grad.astype(a._dtype)
+        if ctx.va or ctx.vb:
+            shp = list(g._shape)
+            if ctx.va:
+                shp.insert(len(shp) - (0 if ctx.vb else 1), 1)
+            if ctx.vb:
+                shp.append(1)
+            g = g.contiguous()._view(tuple(shp), None)
+        if len(b._shape) == 2 and len(a._shape) > 2:
+            # dA = g @ b^T per row; dB = A2d^T @ g2d : the batch sum is folded into the GEMM's K dim
+            g2, a2 = _fold_rows(g), _fold_rows(a)
+            da = _gemm(g2, _swap_last(b))._view(a._shape, None)
+            da._temp = True
+            db = _gemm(_swap_last(a2), g2)
+        else:
+            da = _gemm(g, _swap_last(b))
+            db = _gemm(_swap_last(a), g)
+            da, db = _unbroadcast(da, a._shape), _unbroadcast(db, b._shape)
+        if ctx.va:
+            da = da.reshape(da._shape[-1])
+        if ctx.vb:
+            db = db.reshape(*db._shape[:-1])
+        return da, db
+
+
+@CudaTensor.register_op()
+class linear(Function):
+    """y = x @ W^T (+ b) with W stored (out, in) as nn.Linear keeps it (nn.py:90-96 of the reference).
+
+    One GEMM forward (bias fused into the epilogue) and two backward: dX = dY @ W and
+    dW = dY^T @ X written directly in W's layout, with the batch/sequence dims folded into the
+    reduction (the reference computes a batched dW and then sums it over the batch).
+    """
+    def forward(ctx, x, weight, bias=None):
+        x = _float_like(x)
+        x2 = _fold_rows(x)
+        x2._mark_shared()
+        ctx.save_for_backward(x2, weight, x._shape, bias is not None)
+        out = _gemm(x2, _swap_last(weight), bias=bias)
+        out = out._view(x._shape[:-1] + (weight._shape[0],), None)
+        out._temp = True
+        return out
+
+    def backward(ctx, out_grad):
+        x2, weight, xshape, has_bias = ctx.get_saved_tensors()
+        g2 = _fold_rows(out_grad if out_grad._contig else out_grad.contiguous())
+        dx = _gemm(g2, weight)._view(xshape, None)
+        dx._temp = True
+        dw = _gemm(_swap_last(g2), x2)
+        if has_bias:
+            db = _reduce(RED['SUM'], g2, (0,), False)
+            return dx, dw, db
+        return dx, dw
+
+
+# ---------------------------------------------------------------------------------------------------
+# indexing (cpu/ops.py:234-255, opencl/ops.py:292-331)
+def _is_index_array(v):
+    return isinstance(v, (CudaTensor, np.ndarray, list, range)) and not isinstance(v, (str, bytes))
+
+
+def _parse_index(shape, idx):
+    """Split a numpy-style index into a basic part (view) and integer-array parts.
+
+    Returns (basic, arrays): ``basic`` is a list with one entry per source dim -- int, slice or None
+    (None marks a dim consumed by an index array) -- and ``arrays`` is [(dim, array_like)].
+    """
+    if not isinstance(idx, tuple):
+        idx = (idx,)
+    nd = len(shape)
+    n_specified = builtins_sum(1 for i in idx if i is not Ellipsis and i is not None)
+    out, dim = [], 0
+    for i in idx:
+        if i is Ellipsis:
+            for _ in range(nd - n_specified):
+                out.append(slice(None))
+                dim += 1
+        elif i is None:
+            raise IndexError("newaxis is not supported in CudaTensor indexing")
+        else:
+            out.append(i)
+            dim += 1
+    while len(out) < nd:
+        out.append(slice(None))
+    if len(out) > nd:
+        raise IndexError("too many indices for tensor of shape %s" % (shape,))
+    arrays = [(d, v) for d, v in enumerate(out) if _is_index_array(v)]
+    if arrays:
+        # integer scalars mixed with index arrays broadcast with them, as in numpy
+        arrays = [(d, v) for d, v in enumerate(out) if _is_index_array(v) or isinstance(v, (int, np.integer))]
+    return out, arrays
+
+
+import builtins as _bi  # noqa: E402
+builtins_sum = _bi.sum
+
+
+def _basic_view(t, basic):
+    """Apply ints and slices (entries that are None are left untouched)."""
+    shape, strides, offset = [], [], t._offset
+    for d, i in enumerate(basic):
+        n, st = t._shape[d], t._strides[d]
+        if i is None:
+            shape.append(n)
+            strides.append(st)
+        elif isinstance(i, (int, np.integer)):
+            i = int(i)
+            if i < -n or i >= n:
+                raise IndexError("index %d is out of bounds for axis %d with size %d" % (i, d, n))
+            offset += (i % n) * st
+        elif isinstance(i, slice):
+            lo, hi, step = i.indices(n)
+            cnt = len(range(lo, hi, step))
+            shape.append(cnt)
+            strides.append(st * step)
+            offset += lo * st if cnt else 0
+        else:
+            raise IndexError("unsupported index %r" % (i,))
+    return t._view(tuple(shape), tuple(strides), offset)
+
+
+def _index_plan(t, idx):
+    """Reduce a fancy index to (source rows view, row numbers) -- see _gather."""
+    basic, arrays = _parse_index(t._shape, idx)
+    if not arrays:
+        return _basic_view(t, basic), None
+    idx_dev = list(basic)
+    dims = [d for d, _ in arrays]
+    if dims != list(range(dims[0], dims[0] + len(dims))):
+        raise IndexError("index arrays must address adjacent dims on the cuda backend")
+    if dims[0] != 0:
+        raise IndexError("index arrays must start at dim 0 on the cuda backend (got dim %d)" % dims[0])
+    for d, _ in arrays:
+        basic[d] = None
+    src = _basic_view(t, basic)
+    k = len(arrays)
+    # the trailing dims must be dense rows
+    tail_shape = src._shape[k:]
+    tail_ok = list(src._strides[k:]) == list(contiguous_strides(tail_shape))
+    if not tail_ok:
+        src = src.contiguous()
+    row_len = _prod(tail_shape)
+    # index arrays -> device int tensors broadcast to one shape
+    dev, bshape = [], ()
+    for d, v in arrays:
+        if isinstance(v, CudaTensor):
+            iv = v
+        else:
+            a = np.asarray(list(v) if isinstance(v, range) else v)
+            if a.dtype == np.bool_:
+                raise IndexError("boolean masks are not supported on the cuda backend")
+            if a.dtype.kind not in 'iu':
+                raise IndexError("index arrays must be integers")
+            iv = CudaTensor.from_numpy(a.astype(np.int64) if a.dtype.kind == 'u' and a.dtype.itemsize > 1 else a,
+                                       requires_grad=False)
+        if iv._code not in (rt.I32, rt.I64, rt.I16, rt.U8, rt.I8):
+            raise IndexError("index tensors must be integers, got %s" % iv._dtype)
+        dev.append(iv)
+        idx_dev[d] = iv
+        bshape = _bshape(bshape, iv._shape)
+    n_idx = _prod(bshape)
+    if k == 1 and dev[0]._contig and dev[0]._shape == bshape:
+        rows, row_stride, n_rows = dev[0], src._strides[0], src._shape[0]
+    else:
+        # fold several index arrays (or broadcast ones) into element offsets on the device
+        mats = []
+        for iv in dev:
+            if iv._shape != bshape or not iv._contig:
+                full = CudaTensor._new(bshape, iv._dtype)
+                rt.api.cast(iv._code, iv._code, len(bshape), i64arr(bshape), iv.ptr, i64arr(_bstrides(iv, bshape)),
+                            full.ptr, None)
+                iv = full
+            mats.append(iv)
+        lin = CudaTensor._new(bshape, np.int64)
+        ptrs = (C.c_void_p * k)(*[m.ptr for m in mats])
+        dts = (C.c_int * k)(*[m._code for m in mats])
+        rt.api.index_linearize(k, ptrs, dts, i64arr(src._shape[:k]), i64arr(src._strides[:k]), n_idx, lin.ptr)
+        rows, row_stride, n_rows = lin, 1, 1 << 62
+        dev = mats + [lin]
+    return src, (rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, tuple(idx_dev))
+
+
+@CudaTensor.register_op("__getitem__")
+class getitem(Function):
+    def forward(ctx, a, idx):
+        src, plan = _index_plan(a, idx)
+        if plan is None:
+            ctx.save_for_backward(a._shape, a._dtype, idx)
+            return src
+        rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, idx_dev = plan
+        # keep the uploaded index arrays so backward does not stage them again
+        ctx.save_for_backward(a._shape, a._dtype, idx_dev)
+        out = CudaTensor._new(bshape + tail_shape, a._dtype)
+        rt.api.gather_rows(a._code, rows._code, src.ptr, n_rows, row_stride, rows.ptr, n_idx, row_len, out.ptr)
+        return out
+
+    def backward(ctx, out_grad):
+        shape, dtype, idx = ctx.get_saved_tensors()
+        grad = CudaTensor.zeros(shape, dtype=np.float32 if dtype.kind != 'f' else dtype, requires_grad=False)
+        src, plan = _index_plan(grad, idx)
+        g = out_grad if out_grad._code == grad._code else out_grad.astype(grad._dtype)
+        if plan is None:
+            # basic index: the view does not overlap itself, assignment == accumulation
+            _assign(src, g)
+        else:
+            rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, _keep = plan
+            if src._data is not grad._data:
+                raise IndexError("scatter-add into a non-dense slice is not supported")
+            g = g.contiguous()
+            rt.api.scatter_add_rows(grad._code, rows._code, src.ptr, n_rows, row_stride, rows.ptr, n_idx, row_len,
+                                    g.ptr)
+        grad._temp = True
+        return grad
+
+
+@CudaTensor.register_op("__setitem__")
+class setitem(Function):
+    def forward(ctx, a, idx, val):
+        src, plan = _index_plan(a, idx)
+        if plan is None:
+            if _is_scalar(val):
+                src._fill_value(val)
+            else:
+                _assign(src, _as_tensor(val, a))
+            return a._view(a._shape, a._strides)
+        rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, _keep = plan
+        if src._data is not a._data:
+            raise IndexError("fancy assignment into a non-dense slice is not supported")
+        if _is_scalar(val):
+            rt.api.scatter_set_rows(a._code, rows._code, src.ptr, n_rows, row_stride, rows.ptr, n_idx, row_len,
+                                    None, float(val))
+        else:
+            val = _as_tensor(val, a)
+            if val._code != a._code:
+                val = val.astype(a._dtype)
+            full = bshape + tail_shape
+            if val._shape != full or not val._contig:
+                dense = CudaTensor._new(full, a._dtype)
+                rt.api.cast(a._code, a._code, len(full), i64arr(full), val.ptr, i64arr(_bstrides(val, full)),
+                            dense.ptr, None)
+                val = dense
+            rt.api.scatter_set_rows(a._code, rows._code, src.ptr, n_rows, row_stride, rows.ptr, n_idx, row_len,
+                                    val.ptr, 0.0)
+        return a._view(a._shape, a._strides)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused layers for the BERT path (new op names; nn/loss use them when the tensor class has them)
+@CudaTensor.register_op(overwrite=True)
+class softmax(Function):
+    """exp(t - max) / sum along ``axis`` in one kernel (generic form: ops.py:62-66 of the reference).
+
+    ``scale`` multiplies the input first (fuses attention's 1/sqrt(d), examples/bert.py:79).
+    """
+    def forward(ctx, t, axis=-1, scale=1.0):
+        t = _float_like(t)
+        nd = len(t._shape)
+        axis = axis % nd
+        ctx.axis, ctx.scale, ctx.nd = axis, float(scale), nd
+        x = t if axis == nd - 1 else t.transpose(*[i for i in range(nd) if i != axis], axis)
+        x = x.contiguous()
+        cols = x._shape[-1]
+        y = CudaTensor._new(x._shape, x._dtype)
+        if x._numel:
+            rt.api.softmax_fwd(x._code, x.ptr, y.ptr, x._numel // cols, cols, float(scale))
+        y._temp = False
+        ctx.save_for_backward(y)
+        if axis != nd - 1:
+            inv = list(range(axis)) + [nd - 1] + list(range(axis, nd - 1))
+            return y.transpose(*inv)
+        return y._view(y._shape, y._strides)
+
+    def backward(ctx, out_grad):
+        y, = ctx.get_saved_tensors()
+        axis, nd = ctx.axis, ctx.nd
+        g = out_grad if axis == nd - 1 else out_grad.transpose(*[i for i in range(nd) if i != axis], axis)
+        g = g.contiguous()
+        if g._code != y._code:
+            g = g.astype(y._dtype)
+        cols = y._shape[-1]
+        dx = CudaTensor._new(y._shape, y._dtype)
+        if y._numel:
+            rt.api.softmax_bwd(y._code, y.ptr, g.ptr, dx.ptr, y._numel // cols, cols, ctx.scale)
+        if axis != nd - 1:
+            inv = list(range(axis)) + [nd - 1] + list(range(axis, nd - 1))
+            return dx.transpose(*inv)
+        return dx
+
+
+@CudaTensor.register_op()
+class layernorm(Function):
+    """(x - mean) / sqrt(var + eps) * weight + bias over the last axis (nn.py:109-124 of the reference)."""
+    def forward(ctx, x, weight, bias, eps=1e-5):
+        x = _float_like(x).contiguous()
+        cols = x._shape[-1]
+        assert weight._shape == (cols,) and bias._shape == (cols,)
+        rows = x._numel // cols
+        y = CudaTensor._new(x._shape, x._dtype)
+        mean, rstd = CudaTensor._new((rows,), x._dtype), CudaTensor._new((rows,), x._dtype)
+        w, b = weight.contiguous(), bias.contiguous()
+        rt.api.layernorm_fwd(x._code, x.ptr, w.ptr, b.ptr, y.ptr, mean.ptr, rstd.ptr, rows, cols, float(eps))
+        x._mark_shared()
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    def backward(ctx, out_grad):
+        x, w, mean, rstd = ctx.get_saved_tensors()
+        g = out_grad.contiguous()
+        cols = x._shape[-1]
+        rows = x._numel // cols
+        dx = CudaTensor._new(x._shape, x._dtype)
+        dw, db = CudaTensor._new((cols,), x._dtype), CudaTensor._new((cols,), x._dtype)
+        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols)
+        return dx, dw, db
+
+
+def cross_entropy_forward(logits, labels):
+    """Fused log-softmax + NLL over the last axis.  Returns (mean loss tensor of shape (), saved state)."""
+    x = _float_like(logits).contiguous()
+    rows, cols = x._shape[0], x._shape[-1]
+    assert len(x._shape) == 2, "fused cross entropy expects (rows, classes) logits"
+    lab = labels if isinstance(labels, CudaTensor) else CudaTensor.from_numpy(np.asarray(labels), requires_grad=False)
+    lab = lab.contiguous()
+    if lab._code not in (rt.I32, rt.I64, rt.I16):
+        lab = lab.astype(np.int64)
+    loss_rows, lse = CudaTensor._new((rows,), x._dtype), CudaTensor._new((rows,), x._dtype)
+    rt.api.cross_entropy_fwd(x._code, lab._code, x.ptr, lab.ptr, loss_rows.ptr, lse.ptr, rows, cols)
+    loss = _reduce(RED['SUM'], loss_rows, (0,), False, scale=1.0 / rows)
+    x._mark_shared()
+    return loss, (x, lab, lse)
+
+
+def cross_entropy_backward(saved, out_grad):
+    x, lab, lse = saved
+    rows, cols = x._shape
+    g = out_grad.contiguous()
+    if g._code != x._code:
+        g = g.astype(x._dtype)
+    dx = CudaTensor._new(x._shape, x._dtype)
+    rt.api.cross_entropy_bwd(x._code, lab._code, x.ptr, lab.ptr, lse.ptr, g.ptr, dx.ptr, rows, cols)
+    return dx
+
+
+CudaTensor.fused_cross_entropy = staticmethod(cross_entropy_forward)
+CudaTensor.fused_cross_entropy_backward = staticmethod(cross_entropy_backward)
+
+
+# ---------------------------------------------------------------------------------------------------
+# convolution (cpu/ops.py:298-356): im2col as a strided window view + the GEMM above
+def _window_view(t, kshape, strides):
+    n = len(kshape)
+    shape = t._shape[:-n] + tuple((d - k) // s + 1 for d, k, s in zip(t._shape[-n:], kshape, strides)) + tuple(kshape)
+    st = t._strides[:-n] + tuple(ts * ws for ts, ws in zip(t._strides[-n:], strides)) + t._strides[-n:]
+    return t._view(shape, st)
+
+
+@CudaTensor.register_op()
+class conv(Function):
+    def forward(ctx, t, kernel, strides=1):
+        t, kernel = _promote(t, kernel)
+        n, m = len(kernel._shape) - 1, len(t._shape)
+        strides = ((strides,) * n) if isinstance(strides, int) else \
+            ((1,) + tuple(strides) if len(strides) == n - 1 else tuple(strides))
+        assert m >= n == len(strides)
+        kshape = kernel._shape[1:]
+        win = _window_view(t, kshape, strides)
+        lead = win._shape[:-n]
+        cols = _ew1(EW['COPY'], win)                       # im2col gather (one strided copy)
+        flat_x = cols._view((_prod(lead), _prod(kshape)), None)
+        flat_w = kernel.contiguous()._view((kernel._shape[0], _prod(kshape)), None)
+        y = _gemm(flat_x, _swap_last(flat_w))              # (positions, out_channels)
+        flat_x._mark_shared()
+        ctx.save_for_backward(flat_x, flat_w, t._shape, kernel._shape, strides, lead)
+        y = y._view(lead + (kernel._shape[0],), None)
+        # move the channel axis to where the collapsed input-channel axis was, then drop that axis
+        nd = len(y._shape)
+        perm = list(range(nd))
+        perm[-n - 1], perm[-1] = perm[-1], perm[-n - 1]
+        y = y.transpose(*perm)
+        assert y._shape[-1] == 1
+        return y._view(y._shape[:-1], y._strides[:-1])
+
+    def backward(ctx, out_grad):
+        flat_x, flat_w, in_shape, w_shape, strides, lead = ctx.get_saved_tensors()
+        n = len(w_shape) - 1
+        g = out_grad if out_grad._code == flat_x._code else out_grad.astype(flat_x._dtype)
+        nd = len(g._shape)
+        perm = [i for i in range(nd) if i != nd - n] + [nd - n]
+        flat_g = g.transpose(*perm).contiguous()._view((_prod(g._shape) // w_shape[0], w_shape[0]), None)
+        flat_xg = _gemm(flat_g, flat_w)                     # (positions, in_c*k*k)
+        w_grad = _gemm(_swap_last(flat_g), flat_x)._view(w_shape, None)
+        # col2im: add every kernel-offset plane back into the input gradient (windows overlap)
+        x_grad = CudaTensor.zeros(in_shape, dtype=flat_x._dtype, requires_grad=False)
+        xw = _window_view(x_grad, w_shape[1:], strides)
+        src = flat_xg._view(xw._shape, None)
+        k_nd = len(w_shape[1:])
+        for pos in np.ndindex(*w_shape[1:]):
+            sel = (slice(None),) * (len(xw._shape) - k_nd) + tuple(pos)
+            dst = _basic_view(xw, list(sel))
+            _ewn(EW['ADD'], (dst, _basic_view(src, list(sel))), out=dst)
+        x_grad._temp = True
+        return x_grad, w_grad

@@ -1,0 +1,258 @@
+"""ctypes binding of liblightgrad_b200.so (the C-ABI declared in include/lightgrad_b200.h).
+
+The library is loaded lazily, on the first device operation.  There is no fallback: if the shared
+object has not been built, or no sm_100 GPU is visible, the first tensor operation raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, '..', '..', 'lib', 'liblightgrad_b200.so'))
+
+# ---- enums mirrored from include/lightgrad_b200.h (tests/test_abi.py checks they agree) ----------
+F32, F64, I32, I64, I16, U8, I8, BF16 = range(8)
+DTYPE_CODE = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int32): I32,
+              np.dtype(np.int64): I64, np.dtype(np.int16): I16, np.dtype(np.uint8): U8,
+              np.dtype(np.int8): I8, np.dtype(np.bool_): U8}
+
+EW = dict(COPY=0, NEG=1, SIN=2, COS=3, EXP=4, LOG=5, SIGMOID=6, TANH=7, RELU=8, GELU=9,
+          ADD_S=10, MUL_S=11, RSUB_S=12, RDIV_S=13, POW_S=14, RPOW_S=15, SQRT=16, DIV_S=17, FILL=18,
+          ADD=32, SUB=33, MUL=34, DIV=35, POW=36,
+          SIN_BWD=40, COS_BWD=41, LOG_BWD=42, SIGMOID_BWD=43, TANH_BWD=44, RELU_BWD=45, GELU_BWD=46,
+          POW_S_BWD=47, RPOW_S_BWD=48, RDIV_S_BWD=49, AXPY=50,
+          DIV_BWD_B=64, POW_BWD_A=65, POW_BWD_B=66, EQ_MASK_MUL=67)
+RED = dict(SUM=0, MAX=1, MIN=2)
+GEMM_FP32_SIMT, GEMM_TF32_TC, GEMM_BF16_TC = 0, 1, 2
+MAX_DIMS = 8
+
+_i64p = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        'M', 'N', 'K', 'batch0', 'batch1',
+        'sa_b0', 'sa_b1', 'sa_m', 'sa_k',
+        'sb_b0', 'sb_b1', 'sb_k', 'sb_n',
+        'sc_b0', 'sc_b1', 'sc_m', 'sc_n')]
+
+
+_SIGNATURES = {
+    'lg_device_count': [C.POINTER(C.c_int)],
+    'lg_init': [C.c_int],
+    'lg_device': [C.POINTER(C.c_int)],
+    'lg_device_props': [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)],
+    'lg_sync': [],
+    'lg_alloc': [C.c_size_t, C.POINTER(_vp)],
+    'lg_free': [_vp],
+    'lg_empty_cache': [],
+    'lg_mem_stats': [C.POINTER(C.c_size_t)] * 3,
+    'lg_memcpy_h2d': [_vp, _vp, C.c_size_t],
+    'lg_memcpy_d2h': [_vp, _vp, C.c_size_t],
+    'lg_memcpy_d2d': [_vp, _vp, C.c_size_t],
+    'lg_memset': [_vp, C.c_int, C.c_size_t],
+    'lg_host_alloc': [C.c_size_t, C.POINTER(_vp)],
+    'lg_host_free': [_vp],
+    'lg_event_create': [C.POINTER(_vp)],
+    'lg_event_record': [_vp],
+    'lg_event_sync': [_vp],
+    'lg_event_elapsed_ms': [_vp, _vp, C.POINTER(C.c_float)],
+    'lg_event_destroy': [_vp],
+    'lg_launch_count': [C.POINTER(C.c_uint64)],
+    'lg_ew_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_double],
+    'lg_ew': [C.c_int, C.c_int, C.c_int, _i64p, _vp, _i64p, _vp, _i64p, _vp, _i64p, _vp, _i64p, C.c_double],
+    'lg_ew_bwd2_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64],
+    'lg_cast': [C.c_int, C.c_int, C.c_int, _i64p, _vp, _i64p, _vp, _i64p],
+    'lg_reduce': [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_double],
+    'lg_gemm': [C.c_int, C.c_int, C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, C.c_int],
+    'lg_gemm_tc_supported': [C.c_int, C.c_int, C.POINTER(GemmDesc)],
+    'lg_gather_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp],
+    'lg_scatter_add_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp],
+    'lg_scatter_set_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, C.c_double],
+    'lg_index_linearize': [C.c_int, C.POINTER(_vp), C.POINTER(C.c_int), _i64p, _i64p, C.c_int64, _vp],
+    'lg_softmax_fwd': [C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
+    'lg_softmax_bwd': [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
+    'lg_cross_entropy_fwd': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
+    'lg_cross_entropy_bwd': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
+    'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
+    'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
+    'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
+    'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int64,
+                     C.c_double, C.c_double, C.c_double, C.c_double],
+    'lg_nccl_unique_id': [_vp],
+    'lg_nccl_init': [_vp, C.c_int, C.c_int],
+    'lg_nccl_allreduce_f32': [_vp, C.c_int64, C.c_int, C.c_int],
+    'lg_nccl_broadcast': [_vp, C.c_int64, C.c_int],
+    'lg_nccl_wait': [],
+    'lg_nccl_fork': [],
+    'lg_nccl_destroy': [],
+}
+
+_lib = None
+
+
+class _Checked(object):
+    """Callable wrapper: raises RuntimeError with lg_last_error() on a non-zero status."""
+    __slots__ = ('fn', 'name')
+
+    def __init__(self, fn, name):
+        self.fn, self.name = fn, name
+
+    def __call__(self, *args):
+        if self.fn(*args):
+            raise RuntimeError("%s: %s" % (self.name, _lib.lg_last_error().decode()))
+
+
+class _Api(object):
+    pass
+
+
+api = None
+
+
+def load():
+    """Load the shared object and bind every entry point (idempotent)."""
+    global _lib, api
+    if api is not None:
+        return api
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "lightgrad_b200: %s is missing -- build it with `python -m lightgrad_b200.build` "
+            "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+    _lib = C.CDLL(LIB_PATH)
+    _lib.lg_last_error.restype = C.c_char_p
+    _lib.lg_last_error.argtypes = []
+    _lib.lg_stream_handle.restype = _vp
+    _lib.lg_stream_handle.argtypes = []
+    a = _Api()
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(_lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+        if name == 'lg_gemm_tc_supported':
+            setattr(a, name[3:], fn)
+        else:
+            setattr(a, name[3:], _Checked(fn, name))
+    a.raw = _lib
+    api = a
+    return a
+
+
+_ready = False
+
+
+def ensure_device(device=-1):
+    """Bind this process to a GPU (LOCAL_RANK-th device by default).  Raises without one."""
+    global _ready
+    a = load()
+    if not _ready:
+        a.init(int(device))
+        _ready = True
+        from ..utils.profiler import Profiler
+        Profiler.device_sync = synchronize
+    return a
+
+
+def synchronize():
+    ensure_device().sync()
+
+
+def launch_count():
+    n = C.c_uint64(0)
+    ensure_device().launch_count(C.byref(n))
+    return n.value
+
+
+def mem_stats():
+    a, b, c = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    ensure_device().mem_stats(C.byref(a), C.byref(b), C.byref(c))
+    return {'in_use': a.value, 'reserved': b.value, 'peak_in_use': c.value}
+
+
+def device_props():
+    sm, ma, mi, mem = C.c_int(0), C.c_int(0), C.c_int(0), C.c_size_t(0)
+    ensure_device().device_props(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem))
+    return {'sm_count': sm.value, 'cc': (ma.value, mi.value), 'total_mem': mem.value}
+
+
+class Buffer(object):
+    """Ref-counted device block from the library's caching allocator (analogue of PooledBuffer)."""
+    __slots__ = ('ptr', 'nbytes', '_free', '__weakref__')
+
+    def __init__(self, nbytes):
+        a = ensure_device()
+        p = _vp()
+        a.alloc(int(nbytes), C.byref(p))
+        self.ptr = p.value or 0
+        self.nbytes = int(nbytes)
+        self._free = a.raw.lg_free
+
+    def __del__(self):
+        p = self.ptr
+        if p:
+            self.ptr = 0
+            try:
+                self._free(p)
+            except Exception:
+                pass
+
+
+class ArenaSlice(object):
+    """A window into a parent Buffer (keeps the parent alive); used for flat parameter / gradient arenas."""
+    __slots__ = ('ptr', 'nbytes', 'parent')
+
+    def __init__(self, parent, byte_offset, nbytes):
+        self.parent = parent
+        self.ptr = parent.ptr + int(byte_offset)
+        self.nbytes = int(nbytes)
+
+
+class Event(object):
+    __slots__ = ('h',)
+
+    def __init__(self):
+        h = _vp()
+        ensure_device().event_create(C.byref(h))
+        self.h = h.value
+
+    def record(self):
+        api.event_record(self.h)
+        return self
+
+    def synchronize(self):
+        api.event_sync(self.h)
+
+    def elapsed_ms(self, later):
+        ms = C.c_float(0)
+        api.event_elapsed_ms(self.h, later.h, C.byref(ms))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.h and api is not None:
+                api.raw.lg_event_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PinnedArray(object):
+    """numpy view over page-locked host memory (H2D copies from it are truly asynchronous)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = _vp()
+        ensure_device().host_alloc(max(n, 1), C.byref(p))
+        self.ptr = p.value
+        buf = (C.c_char * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self.ptr and api is not None:
+                api.raw.lg_host_free(self.ptr)
+                self.ptr = 0
+        except Exception:
+            pass

@@ -1,0 +1,70 @@
+// Internal helpers shared by all translation units of liblightgrad_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/lightgrad_b200.h"
+
+namespace lg {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+int set_error(const char* fmt, ...);
+cudaStream_t stream();        // compute stream
+cudaStream_t comm_stream();   // collective stream
+int sm_count();
+void count_launch(int n = 1);
+int ensure_init();
+
+#define LG_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return lg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                                 __FILE__, __LINE__);                                         \
+    } while (0)
+
+#define LG_CHECK_LAUNCH()                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return lg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \
+                                 __FILE__, __LINE__);                                         \
+        lg::count_launch();                                                                   \
+    } while (0)
+
+#define LG_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                      \
+        if (!(cond)) return lg::set_error(__VA_ARGS__);                                       \
+    } while (0)
+
+#define LG_INIT()                                                                             \
+    do {                                                                                      \
+        int _rc = lg::ensure_init();                                                          \
+        if (_rc) return _rc;                                                                  \
+    } while (0)
+
+inline size_t dtype_size(int dt) {
+    switch (dt) {
+        case LG_F32: case LG_I32: return 4;
+        case LG_F64: case LG_I64: return 8;
+        case LG_I16: case LG_BF16: return 2;
+        case LG_U8: case LG_I8: return 1;
+    }
+    return 0;
+}
+
+// internal allocation helpers (same cache as lg_alloc / lg_free)
+void* tmp_alloc(size_t nbytes);
+void tmp_free(void* p);
+
+// grid sizing: persistent-style grids are multiples of the SM count
+inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+    int64_t need = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace lg

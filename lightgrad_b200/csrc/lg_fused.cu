@@ -1,0 +1,398 @@
+// Fused row-wise layers for the BERT path: softmax, log-softmax + NLL (cross entropy), layer norm.
+// The reference composes each from primitive ops, one launch + one blocking wait per primitive:
+//   softmax      lightgrad/autograd/ops.py:62-66   (max, sub, exp, sum, div -> 5 passes + wrappers)
+//   cross_entropy lightgrad/loss.py:14-24          (softmax, gather, log, mean; backward (p-onehot)/N*g)
+//   LayerNorm    lightgrad/nn.py:109-124           (~14 primitives, 2 reductions)
+// Here each is one pass over HBM per direction.  Algorithmic bytes per element (f32):
+//   softmax fwd 8, bwd 12; cross-entropy fwd 4, bwd 8; layernorm fwd 8, bwd 12 (+ per-row/col vectors).
+#include "lg_ew.cuh"
+#include <math.h>
+
+using namespace lg;
+
+namespace {
+
+template <typename T> __device__ __forceinline__ T f_exp(T x);
+template <> __device__ __forceinline__ float f_exp(float x) { return expf(x); }
+template <> __device__ __forceinline__ double f_exp(double x) { return exp(x); }
+template <typename T> __device__ __forceinline__ T f_log(T x);
+template <> __device__ __forceinline__ float f_log(float x) { return logf(x); }
+template <> __device__ __forceinline__ double f_log(double x) { return log(x); }
+template <typename T> __device__ __forceinline__ T f_rsqrt_exact(T x);
+template <> __device__ __forceinline__ float f_rsqrt_exact(float x) { return 1.0f / sqrtf(x); }
+template <> __device__ __forceinline__ double f_rsqrt_exact(double x) { return 1.0 / sqrt(x); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (w > v || w != w) ? w : v;
+    }
+    return v;
+}
+
+// block-wide helpers (256 threads)
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sm) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = sm[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r += sm[i];
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ T block_max(T v, T* sm) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = sm[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = (sm[i] > r || sm[i] != sm[i]) ? sm[i] : r;
+    return r;
+}
+
+// ================================ softmax ==========================================================
+// One warp per row (cols <= 2048 keeps the row in L1 between the three sweeps), else one CTA per row.
+template <typename T, bool BLOCK>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,
+                                                          int64_t cols, T scale) {
+    __shared__ T sm[8];
+    const int lane = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+    const int step = BLOCK ? blockDim.x : 32;
+    int64_t row = BLOCK ? blockIdx.x : (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int64_t row_step = BLOCK ? gridDim.x : (((int64_t)gridDim.x * blockDim.x) >> 5);
+    for (; row < rows; row += row_step) {
+        const T* p = x + row * cols;
+        T* q = y + row * cols;
+        T m = -INFINITY;
+        for (int64_t j = lane; j < cols; j += step) {
+            T v = p[j] * scale;
+            m = (v > m || v != v) ? v : m;
+        }
+        m = BLOCK ? block_max(m, sm) : warp_max(m);
+        T s = T(0);
+        for (int64_t j = lane; j < cols; j += step) s += f_exp(p[j] * scale - m);
+        s = BLOCK ? block_sum(s, sm) : warp_sum(s);
+        for (int64_t j = lane; j < cols; j += step) q[j] = f_exp(p[j] * scale - m) / s;
+    }
+}
+
+template <typename T, bool BLOCK>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ y, const T* __restrict__ g,
+                                                          T* __restrict__ dx, int64_t rows, int64_t cols, T scale) {
+    __shared__ T sm[8];
+    const int lane = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+    const int step = BLOCK ? blockDim.x : 32;
+    int64_t row = BLOCK ? blockIdx.x : (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int64_t row_step = BLOCK ? gridDim.x : (((int64_t)gridDim.x * blockDim.x) >> 5);
+    for (; row < rows; row += row_step) {
+        const T* py = y + row * cols;
+        const T* pg = g + row * cols;
+        T* pd = dx + row * cols;
+        T dot = T(0);
+        for (int64_t j = lane; j < cols; j += step) dot += py[j] * pg[j];
+        dot = BLOCK ? block_sum(dot, sm) : warp_sum(dot);
+        for (int64_t j = lane; j < cols; j += step) pd[j] = scale * (py[j] * (pg[j] - dot));
+    }
+}
+
+// ================================ cross entropy ====================================================
+// One CTA per row; online max/sum in one sweep (logits rows are 122 KB at V = 30522).
+template <typename T, typename L>
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, const L* __restrict__ labels,
+                                                     T* __restrict__ loss_rows, T* __restrict__ lse, int64_t rows,
+                                                     int64_t cols) {
+    __shared__ T sm[8];
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const T* p = x + row * cols;
+        T m = -INFINITY, s = T(0);
+        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+            T v = p[j];
+            if (v > m) {
+                s = s * f_exp(m - v) + T(1);
+                m = v;
+            } else {
+                s += f_exp(v - m);
+            }
+        }
+        T gm = block_max(m, sm);
+        T part = (m == -INFINITY) ? T(0) : s * f_exp(m - gm);
+        T gs = block_sum(part, sm);
+        if (threadIdx.x == 0) {
+            T l = gm + f_log(gs);
+            int64_t lab = (int64_t)labels[row];
+            if (lab < 0) lab += cols;
+            lse[row] = l;
+            loss_rows[row] = l - p[lab];
+        }
+    }
+}
+
+template <typename T, typename L>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, const L* __restrict__ labels,
+                                                     const T* __restrict__ lse, const T* __restrict__ gscale,
+                                                     T* __restrict__ dx, int64_t rows, int64_t cols) {
+    const T gs = gscale[0];
+    const T inv_rows = T(rows);
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const T* p = x + row * cols;
+        T* q = dx + row * cols;
+        const T l = lse[row];
+        int64_t lab = (int64_t)labels[row];
+        if (lab < 0) lab += cols;
+        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+            T pr = f_exp(p[j] - l);
+            if (j == lab) pr -= T(1);
+            q[j] = pr / inv_rows * gs;   // (p - onehot) / N * out_grad, as loss.py:20-24
+        }
+    }
+}
+
+// ================================ layer norm =======================================================
+// One warp per row.  Statistics follow nn.py:117-123: mean, D = x - mean, V = mean(D*D),
+// y = D / sqrt(V + eps) * gamma + beta.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                     const T* __restrict__ beta, T* __restrict__ y,
+                                                     T* __restrict__ mean, T* __restrict__ rstd, int64_t rows,
+                                                     int64_t cols, T eps) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const T inv = T(1) / T(cols);
+    for (; row < rows; row += row_step) {
+        const T* p = x + row * cols;
+        T* q = y + row * cols;
+        T s = T(0);
+        for (int64_t j = lane; j < cols; j += 32) s += p[j];
+        const T mu = warp_sum(s) * inv;
+        T v = T(0);
+        for (int64_t j = lane; j < cols; j += 32) {
+            T dlt = p[j] - mu;
+            v += dlt * dlt;
+        }
+        const T var = warp_sum(v) * inv;
+        const T rs = f_rsqrt_exact(var + eps);
+        for (int64_t j = lane; j < cols; j += 32) q[j] = (p[j] - mu) * rs * gamma[j] + beta[j];
+        if (lane == 0) {
+            mean[row] = mu;
+            rstd[row] = rs;
+        }
+    }
+}
+
+// dx per row (warp per row); dgamma / dbeta partials per CTA -> [gridDim.x, cols], reduced afterwards.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                     const T* __restrict__ mean, const T* __restrict__ rstd,
+                                                     const T* __restrict__ g, T* __restrict__ dx,
+                                                     T* __restrict__ dgamma_part, T* __restrict__ dbeta_part,
+                                                     int64_t rows, int64_t cols) {
+    extern __shared__ unsigned char smem_raw[];
+    T* sg = reinterpret_cast<T*>(smem_raw);  // [cols] dgamma accumulators for this CTA
+    T* sb = sg + cols;                        // [cols] dbeta
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+        sg[j] = T(0);
+        sb[j] = T(0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const T inv = T(1) / T(cols);
+    for (; row < rows; row += row_step) {
+        const T* px = x + row * cols;
+        const T* pg = g + row * cols;
+        T* pd = dx + row * cols;
+        const T mu = mean[row], rs = rstd[row];
+        T s1 = T(0), s2 = T(0);
+        for (int64_t j = lane; j < cols; j += 32) {
+            T xh = (px[j] - mu) * rs;
+            T dxh = pg[j] * gamma[j];
+            s1 += dxh;
+            s2 += dxh * xh;
+        }
+        s1 = warp_sum(s1) * inv;
+        s2 = warp_sum(s2) * inv;
+        for (int64_t j = lane; j < cols; j += 32) {
+            T xh = (px[j] - mu) * rs;
+            T gj = pg[j];
+            pd[j] = rs * (gj * gamma[j] - s1 - xh * s2);
+            atomicAdd(&sg[j], gj * xh);
+            atomicAdd(&sb[j], gj);
+        }
+    }
+    __syncthreads();
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+        dgamma_part[(int64_t)blockIdx.x * cols + j] = sg[j];
+        dbeta_part[(int64_t)blockIdx.x * cols + j] = sb[j];
+    }
+}
+
+template <typename T>
+int softmax_fwd(const void* x, void* y, int64_t rows, int64_t cols, double scale) {
+    if (rows * cols == 0) return 0;
+    if (cols <= 2048) {
+        int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
+        softmax_fwd_kernel<T, false><<<(int)(blocks < cap ? blocks : cap), 256, 0, stream()>>>(
+            (const T*)x, (T*)y, rows, cols, (T)scale);
+    } else {
+        int64_t cap = (int64_t)sm_count() * 8;
+        softmax_fwd_kernel<T, true><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>((const T*)x, (T*)y, rows,
+                                                                                          cols, (T)scale);
+    }
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+template <typename T>
+int softmax_bwd(const void* y, const void* g, void* dx, int64_t rows, int64_t cols, double scale) {
+    if (rows * cols == 0) return 0;
+    if (cols <= 2048) {
+        int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
+        softmax_bwd_kernel<T, false><<<(int)(blocks < cap ? blocks : cap), 256, 0, stream()>>>(
+            (const T*)y, (const T*)g, (T*)dx, rows, cols, (T)scale);
+    } else {
+        int64_t cap = (int64_t)sm_count() * 8;
+        softmax_bwd_kernel<T, true><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>(
+            (const T*)y, (const T*)g, (T*)dx, rows, cols, (T)scale);
+    }
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename T, typename L>
+int ce_fwd(const void* x, const void* labels, void* loss_rows, void* lse, int64_t rows, int64_t cols) {
+    int64_t cap = (int64_t)sm_count() * 8;
+    ce_fwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>((const T*)x, (const L*)labels,
+                                                                              (T*)loss_rows, (T*)lse, rows, cols);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+template <typename T, typename L>
+int ce_bwd(const void* x, const void* labels, const void* lse, const void* gs, void* dx, int64_t rows, int64_t cols) {
+    int64_t cap = (int64_t)sm_count() * 8;
+    ce_bwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>(
+        (const T*)x, (const L*)labels, (const T*)lse, (const T*)gs, (T*)dx, rows, cols);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lg_softmax_fwd(int dtype, const void* x, void* y, int64_t rows, int64_t cols, double scale) {
+    LG_INIT();
+    if (dtype == LG_F32) return softmax_fwd<float>(x, y, rows, cols, scale);
+    if (dtype == LG_F64) return softmax_fwd<double>(x, y, rows, cols, scale);
+    return set_error("lg_softmax_fwd: unsupported dtype %d", dtype);
+}
+
+int lg_softmax_bwd(int dtype, const void* y, const void* g, void* dx, int64_t rows, int64_t cols, double scale) {
+    LG_INIT();
+    if (dtype == LG_F32) return softmax_bwd<float>(y, g, dx, rows, cols, scale);
+    if (dtype == LG_F64) return softmax_bwd<double>(y, g, dx, rows, cols, scale);
+    return set_error("lg_softmax_bwd: unsupported dtype %d", dtype);
+}
+
+int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, const void* labels, void* loss_rows, void* lse,
+                         int64_t rows, int64_t cols) {
+    LG_INIT();
+    if (rows == 0) return 0;
+    LG_REQUIRE(cols > 0, "lg_cross_entropy_fwd: zero classes");
+#define GO(T)                                                                                          \
+    switch (idx_dtype) {                                                                               \
+        case LG_I32: return ce_fwd<T, int32_t>(logits, labels, loss_rows, lse, rows, cols);            \
+        case LG_I64: return ce_fwd<T, int64_t>(logits, labels, loss_rows, lse, rows, cols);            \
+        case LG_I16: return ce_fwd<T, int16_t>(logits, labels, loss_rows, lse, rows, cols);            \
+        default: return set_error("lg_cross_entropy_fwd: label dtype %d unsupported", idx_dtype);      \
+    }
+    if (dtype == LG_F32) { GO(float) }
+    if (dtype == LG_F64) { GO(double) }
+#undef GO
+    return set_error("lg_cross_entropy_fwd: unsupported dtype %d", dtype);
+}
+
+int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, const void* labels, const void* lse,
+                         const void* gscale, void* dlogits, int64_t rows, int64_t cols) {
+    LG_INIT();
+    if (rows == 0) return 0;
+#define GO(T)                                                                                          \
+    switch (idx_dtype) {                                                                               \
+        case LG_I32: return ce_bwd<T, int32_t>(logits, labels, lse, gscale, dlogits, rows, cols);      \
+        case LG_I64: return ce_bwd<T, int64_t>(logits, labels, lse, gscale, dlogits, rows, cols);      \
+        case LG_I16: return ce_bwd<T, int16_t>(logits, labels, lse, gscale, dlogits, rows, cols);      \
+        default: return set_error("lg_cross_entropy_bwd: label dtype %d unsupported", idx_dtype);      \
+    }
+    if (dtype == LG_F32) { GO(float) }
+    if (dtype == LG_F64) { GO(double) }
+#undef GO
+    return set_error("lg_cross_entropy_bwd: unsupported dtype %d", dtype);
+}
+
+int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y, void* mean, void* rstd,
+                     int64_t rows, int64_t cols, double eps) {
+    LG_INIT();
+    if (rows * cols == 0) return 0;
+    int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    if (dtype == LG_F32)
+        ln_fwd_kernel<float><<<grid, 256, 0, stream()>>>((const float*)x, (const float*)gamma, (const float*)beta,
+                                                         (float*)y, (float*)mean, (float*)rstd, rows, cols,
+                                                         (float)eps);
+    else if (dtype == LG_F64)
+        ln_fwd_kernel<double><<<grid, 256, 0, stream()>>>((const double*)x, (const double*)gamma,
+                                                          (const double*)beta, (double*)y, (double*)mean,
+                                                          (double*)rstd, rows, cols, eps);
+    else
+        return set_error("lg_layernorm_fwd: unsupported dtype %d", dtype);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd, const void* g,
+                     void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols) {
+    LG_INIT();
+    if (rows * cols == 0) return 0;
+    size_t es = dtype_size(dtype);
+    LG_REQUIRE(dtype == LG_F32 || dtype == LG_F64, "lg_layernorm_bwd: unsupported dtype %d", dtype);
+    size_t smem = 2 * (size_t)cols * es;
+    LG_REQUIRE(smem <= 48 * 1024, "lg_layernorm_bwd: normalised size %lld too large for the fused kernel",
+               (long long)cols);
+    int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 2;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    void* part = tmp_alloc(2 * (size_t)grid * cols * es);
+    if (!part) return 1;
+    void* pg = part;
+    void* pb = (char*)part + (size_t)grid * cols * es;
+    if (dtype == LG_F32)
+        ln_bwd_kernel<float><<<grid, 256, smem, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean,
+                                                            (const float*)rstd, (const float*)g, (float*)dx,
+                                                            (float*)pg, (float*)pb, rows, cols);
+    else
+        ln_bwd_kernel<double><<<grid, 256, smem, stream()>>>((const double*)x, (const double*)gamma,
+                                                             (const double*)mean, (const double*)rstd,
+                                                             (const double*)g, (double*)dx, (double*)pg, (double*)pb,
+                                                             rows, cols);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        tmp_free(part);
+        return set_error("ln_bwd launch failed: %s", cudaGetErrorString(e));
+    }
+    count_launch();
+    int rc = lg_reduce(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, 1.0);
+    if (!rc) rc = lg_reduce(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, 1.0);
+    tmp_free(part);
+    return rc;
+}
+
+}  // extern "C"

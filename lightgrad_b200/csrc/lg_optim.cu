@@ -1,0 +1,104 @@
+// On-device optimizer updates over flat fp32 arenas (one launch per step instead of the reference's
+// per-parameter Python loop of 3-14 elementwise launches, lightgrad/optim.py:10-52).
+// Arithmetic restates optim.py term by term (python-float coefficients become fp32 scalars, as numpy's
+// weak-scalar promotion does):
+//   SGD       delta = -lr*g + momentum*delta_prev ; p += delta                       (optim.py:23-25)
+//   Adam      m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g^2
+//             p += -lr * (m/(1-b1^t)) / ((v/(1-b2^t))^0.5 + eps)                      (optim.py:35-41)
+//   AdaBelief as Adam with v = b2*v + (1-b2)*(g-m)^2                                  (optim.py:47-52)
+// The reference increments t once per PARAMETER per step (optim.py:36-37), so the
+// bias corrections differ per tensor: they arrive as per-segment scalars.
+// Algorithmic bytes per parameter: SGD 12 (+8 with momentum), Adam 28.
+#include "lg_ew.cuh"
+
+using namespace lg;
+
+namespace {
+
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ delta, int64_t n, float neg_lr, float mom) {
+    const int64_t nv = n / 4;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < nv; i += nt) {
+        float4 pv = reinterpret_cast<float4*>(p)[i], gv = reinterpret_cast<const float4*>(g)[i], dv;
+        if (delta) {
+            float4 pd = reinterpret_cast<float4*>(delta)[i];
+            dv.x = neg_lr * gv.x + mom * pd.x; dv.y = neg_lr * gv.y + mom * pd.y;
+            dv.z = neg_lr * gv.z + mom * pd.z; dv.w = neg_lr * gv.w + mom * pd.w;
+            reinterpret_cast<float4*>(delta)[i] = dv;
+        } else {
+            dv.x = neg_lr * gv.x; dv.y = neg_lr * gv.y; dv.z = neg_lr * gv.z; dv.w = neg_lr * gv.w;
+        }
+        pv.x += dv.x; pv.y += dv.y; pv.z += dv.z; pv.w += dv.w;
+        reinterpret_cast<float4*>(p)[i] = pv;
+    }
+    for (int64_t j = nv * 4 + tid; j < n; j += nt) {
+        float d = neg_lr * g[j] + (delta ? mom * delta[j] : 0.0f);
+        if (delta) delta[j] = d;
+        p[j] += d;
+    }
+}
+
+template <bool BELIEF>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, int n_seg,
+                                                   const int64_t* __restrict__ seg_end, int64_t t0, double b1d,
+                                                   double b2d, float neg_lr, float b1, float b2, float omb1,
+                                                   float omb2, float eps) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n; i += nt) {
+        // segment of element i: first seg with seg_end > i
+        int lo = 0, hi = n_seg - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (seg_end[mid] > i) hi = mid; else lo = mid + 1;
+        }
+        const double t = (double)(t0 + lo + 1);
+        const float d1 = (float)(1.0 - pow(b1d, t)), d2 = (float)(1.0 - pow(b2d, t));
+        float gi = g[i];
+        float mi = b1 * m[i] + omb1 * gi;
+        float r = BELIEF ? (gi - mi) : gi;
+        float vi = b2 * v[i] + omb2 * (r * r);
+        m[i] = mi;
+        v[i] = vi;
+        float mh = mi / d1, vh = vi / d2;
+        p[i] += neg_lr * mh / (sqrtf(vh) + eps);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int lg_sgd_step(void* param, const void* grad, void* delta, int64_t n, double lr, double momentum) {
+    LG_INIT();
+    if (n == 0) return 0;
+    LG_REQUIRE(aligned16(param) && aligned16(grad) && (!delta || aligned16(delta)), "lg_sgd_step: arenas must be 16-byte aligned");
+    sgd_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, stream()>>>((float*)param, (const float*)grad, (float*)delta, n,
+                                                                  (float)(-lr), (float)momentum);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, int64_t n, int n_seg,
+                 const int64_t* seg_end_dev, int64_t t0, double lr, double beta1, double beta2, double eps) {
+    LG_INIT();
+    if (n == 0) return 0;
+    LG_REQUIRE(n_seg >= 1, "lg_adam_step: need at least one segment");
+    int grid = grid_for(n, 256, 8);
+    float b1 = (float)beta1, b2 = (float)beta2;
+    // (1 - beta) is formed in double by python and then rounded to fp32, as numpy does with the scalar
+    float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
+    if (belief)
+        adam_kernel<true><<<grid, 256, 0, stream()>>>((float*)param, (const float*)grad, (float*)m, (float*)v, n,
+                                                      n_seg, seg_end_dev, t0, beta1, beta2, (float)(-lr), b1,
+                                                      b2, omb1, omb2, (float)eps);
+    else
+        adam_kernel<false><<<grid, 256, 0, stream()>>>((float*)param, (const float*)grad, (float*)m, (float*)v, n,
+                                                       n_seg, seg_end_dev, t0, beta1, beta2, (float)(-lr), b1,
+                                                       b2, omb1, omb2, (float)eps);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+// Runtime: device binding, streams, caching allocator, copies, events.
+// Replaces what the reference's OpenCL backend gets from pyopencl: one context + one in-order
+// queue + a MemoryPool per device (opencl/device.py:51-115) and blocking enqueue_copy
+// (opencl/tensor.py:74-93).  Here copies and kernels are stream-ordered and only D2H blocks.
+#include "lg_common.cuh"
+#include <mutex>
+#include <unordered_map>
+#include <map>
+#include <vector>
+#include <atomic>
+#include <string.h>
+
+namespace lg {
+
+static thread_local char g_err[1024] = "";
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr, g_comm = nullptr;
+static int g_sms = 148;
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+cudaStream_t stream() { return g_stream; }
+cudaStream_t comm_stream() { return g_comm; }
+int sm_count() { return g_sms; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- caching allocator ------------------------------------------------------------------------
+// Size-class free lists; a freed block is immediately reusable because every consumer runs on the
+// one compute stream (stream order == program order).  The comm stream only touches long-lived
+// arenas and is joined by events before those could be released.
+struct Cache {
+    std::mutex mu;
+    std::unordered_map<void*, size_t> live;              // ptr -> class size
+    std::map<size_t, std::vector<void*>> free_lists;     // class size -> blocks
+    size_t in_use = 0, reserved = 0, peak = 0;
+
+    static size_t size_class(size_t n) {
+        if (n < 512) return 512;
+        // 8 classes per power of two: waste <= 12.5 %
+        size_t p = 512;
+        while ((p << 1) <= n) p <<= 1;
+        size_t step = p >> 3;
+        if (step < 512) step = 512;
+        return (n + step - 1) / step * step;
+    }
+    void release_all() {
+        for (auto& kv : free_lists) {
+            for (void* p : kv.second) {
+                cudaFree(p);
+                reserved -= kv.first;
+            }
+        }
+        free_lists.clear();
+    }
+    void* get(size_t n) {
+        size_t cls = size_class(n);
+        std::lock_guard<std::mutex> lk(mu);
+        void* p = nullptr;
+        auto it = free_lists.find(cls);
+        if (it != free_lists.end() && !it->second.empty()) {
+            p = it->second.back();
+            it->second.pop_back();
+        } else {
+            cudaError_t e = cudaMalloc(&p, cls);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                cudaStreamSynchronize(g_stream);
+                release_all();
+                e = cudaMalloc(&p, cls);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    set_error("out of device memory allocating %zu bytes (in use %zu, reserved %zu)", cls, in_use,
+                              reserved);
+                    return nullptr;
+                }
+            }
+            reserved += cls;
+        }
+        live[p] = cls;
+        in_use += cls;
+        if (in_use > peak) peak = in_use;
+        return p;
+    }
+    int put(void* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return set_error("lg_free: unknown pointer %p", p);
+        size_t cls = it->second;
+        live.erase(it);
+        in_use -= cls;
+        free_lists[cls].push_back(p);
+        return 0;
+    }
+};
+static Cache* g_cache = nullptr;
+
+void* tmp_alloc(size_t nbytes) { return g_cache->get(nbytes ? nbytes : 1); }
+void tmp_free(void* p) {
+    if (p) g_cache->put(p);
+}
+
+static int do_init(int device) {
+    if (g_device >= 0) {
+        if (device >= 0 && device != g_device)
+            return set_error("lg_init: process already bound to device %d (asked for %d)", g_device, device);
+        return 0;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error("no CUDA device available (%s); lightgrad_b200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0) {
+        const char* lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % n : 0;
+    }
+    if (device >= n) return set_error("lg_init: device %d out of range (%d visible)", device, n);
+    LG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error("lightgrad_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+                         prop.minor);
+    g_sms = prop.multiProcessorCount;
+    LG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    LG_CUDA(cudaStreamCreateWithFlags(&g_comm, cudaStreamNonBlocking));
+    g_cache = new Cache();
+    g_device = device;
+    return 0;
+}
+
+int ensure_init() { return do_init(-1); }
+
+}  // namespace lg
+
+using namespace lg;
+
+extern "C" {
+
+const char* lg_last_error(void) { return g_err; }
+
+int lg_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return 0;
+}
+
+int lg_init(int device) { return do_init(device); }
+
+int lg_device(int* device) {
+    *device = g_device;
+    return g_device >= 0 ? 0 : set_error("not initialised");
+}
+
+int lg_device_props(int* sm_count_, int* cc_major, int* cc_minor, size_t* total_mem) {
+    LG_INIT();
+    cudaDeviceProp prop;
+    LG_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    *sm_count_ = prop.multiProcessorCount;
+    *cc_major = prop.major;
+    *cc_minor = prop.minor;
+    *total_mem = prop.totalGlobalMem;
+    return 0;
+}
+
+int lg_sync(void) {
+    LG_INIT();
+    LG_CUDA(cudaStreamSynchronize(g_stream));
+    LG_CUDA(cudaStreamSynchronize(g_comm));
+    return 0;
+}
+
+int lg_alloc(size_t nbytes, void** ptr) {
+    LG_INIT();
+    void* p = g_cache->get(nbytes ? nbytes : 1);
+    if (!p) return 1;
+    *ptr = p;
+    return 0;
+}
+
+int lg_free(void* ptr) {
+    if (!ptr || !g_cache) return 0;
+    return g_cache->put(ptr);
+}
+
+int lg_empty_cache(void) {
+    LG_INIT();
+    LG_CUDA(cudaStreamSynchronize(g_stream));
+    std::lock_guard<std::mutex> lk(g_cache->mu);
+    g_cache->release_all();
+    return 0;
+}
+
+int lg_mem_stats(size_t* in_use, size_t* reserved, size_t* peak_in_use) {
+    LG_INIT();
+    std::lock_guard<std::mutex> lk(g_cache->mu);
+    *in_use = g_cache->in_use;
+    *reserved = g_cache->reserved;
+    *peak_in_use = g_cache->peak;
+    return 0;
+}
+
+int lg_memcpy_h2d(void* dst, const void* src, size_t nbytes) {
+    LG_INIT();
+    if (nbytes == 0) return 0;
+    LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, g_stream));
+    return 0;
+}
+
+int lg_memcpy_d2h(void* dst, const void* src, size_t nbytes) {
+    LG_INIT();
+    if (nbytes) LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
+    LG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int lg_memcpy_d2d(void* dst, const void* src, size_t nbytes) {
+    LG_INIT();
+    if (nbytes == 0) return 0;
+    LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, g_stream));
+    return 0;
+}
+
+int lg_memset(void* dst, int byte, size_t nbytes) {
+    LG_INIT();
+    if (nbytes == 0) return 0;
+    LG_CUDA(cudaMemsetAsync(dst, byte, nbytes, g_stream));
+    return 0;
+}
+
+int lg_host_alloc(size_t nbytes, void** ptr) {
+    LG_INIT();
+    LG_CUDA(cudaHostAlloc(ptr, nbytes ? nbytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int lg_host_free(void* ptr) {
+    if (ptr) LG_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+int lg_event_create(void** ev) {
+    LG_INIT();
+    cudaEvent_t e;
+    LG_CUDA(cudaEventCreate(&e));
+    *ev = (void*)e;
+    return 0;
+}
+int lg_event_record(void* ev) {
+    LG_CUDA(cudaEventRecord((cudaEvent_t)ev, g_stream));
+    return 0;
+}
+int lg_event_sync(void* ev) {
+    LG_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+    return 0;
+}
+int lg_event_elapsed_ms(void* start, void* stop, float* ms) {
+    LG_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return 0;
+}
+int lg_event_destroy(void* ev) {
+    LG_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+    return 0;
+}
+
+int lg_launch_count(uint64_t* n) {
+    *n = g_launches.load();
+    return 0;
+}
+
+void* lg_stream_handle(void) { return (void*)g_stream; }
+
+}  // extern "C"

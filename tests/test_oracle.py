@@ -1,0 +1,43 @@
+"""Pins the oracle (oracle/, a numpy restatement) and the host-side autograd core / nn / loss / optim /
+example models against vectors produced by the REAL reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+from oracle import CpuTensor
+from tests import replay
+
+# same arithmetic in the same order on the same BLAS: agreement is to rounding of reassociated sums
+RTOL, ATOL = 2e-6, 2e-6
+
+
+def test_oracle_ops_match_reference_golden():
+    n = 0
+    for case, field, got, want in replay.replay_ops(CpuTensor):
+        assert got.shape == want.shape, "%s/%s shape %s != %s" % (case, field, got.shape, want.shape)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL, err_msg="%s/%s" % (case, field))
+        n += 1
+    assert n > 200
+
+
+def test_oracle_bert_tiny_matches_reference_golden():
+    n = 0
+    for name, got, want in replay.replay_bert_tiny(CpuTensor):
+        assert got.shape == want.shape, name
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6, err_msg=name)
+        n += 1
+    assert n > 40
+
+
+def test_duplicate_index_gradient_is_accumulated():
+    # the shipped reference assigns (last write wins); oracle and cuda backend add
+    w = CpuTensor.from_numpy(np.arange(12, dtype=np.float32).reshape(4, 3))
+    w[np.array([1, 1, 2])].sum().backward()
+    np.testing.assert_array_equal(w.grad.numpy(), np.array([[0] * 3, [2] * 3, [1] * 3, [0] * 3], dtype=np.float32))
+
+
+def test_walker_visits_shared_nodes_once():
+    # h feeds two consumers; d/dx [exp(h) + h] with h = tanh(x)
+    x = CpuTensor.from_numpy(np.linspace(-1, 1, 7).astype(np.float32))
+    h = x.tanh()
+    (h.exp() + h).sum().backward()
+    hn = np.tanh(np.linspace(-1, 1, 7))
+    np.testing.assert_allclose(x.grad.numpy(), (np.exp(hn) + 1) * (1 - hn ** 2), rtol=1e-5)
