@@ -181,6 +181,7 @@ class Buffer(object):
     __slots__ = ('ptr', 'nbytes', '_free', '__weakref__')
 
     def __init__(self, nbytes):
+        self.ptr = 0
         a = ensure_device()
         p = _vp()
         a.alloc(int(nbytes), C.byref(p))

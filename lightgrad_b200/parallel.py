@@ -1,0 +1,150 @@
+"""Data-parallel training: one process per GPU, batch sharded across ranks, gradients averaged.
+
+The reference has no multi-device path at all (operands of different tensor classes are rejected,
+lightgrad/autograd/func.py:18-20).  Only the batch axis of examples/mnist.py and
+examples/bert.py shards naturally, so the exchange step is exactly one collective per iteration: an
+averaging all-reduce of the parameter gradients, between ``loss.backward()`` and ``optimizer.step()``.
+
+  * cuda backend: the optimizer keeps all gradients in one flat fp32 arena (optim._Arena), so the
+    exchange is a single in-place ncclAllReduce(avg) over NVLink on that arena (C-ABI lg_nccl_*).
+  * any other backend (the CPU oracle in the gloo tests): gradients are averaged tensor by tensor
+    through ``comm.allreduce_avg_numpy``.
+
+Bootstrap (exchanging the 128-byte NCCL id, barriers, max-over-ranks of timings) is control-plane
+only and uses ``torch.distributed`` with the gloo backend when it is available, as launched by
+``python -m torch.distributed.run`` (RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the env).
+"""
+import os
+import numpy as np
+
+
+class LocalComm(object):
+    """World of one: every collective is the identity."""
+    rank, world = 0, 1
+
+    def barrier(self):
+        pass
+
+    def allreduce_avg_numpy(self, a):
+        return a
+
+    def max_float(self, x):
+        return float(x)
+
+    def broadcast_bytes(self, b, root=0):
+        return b
+
+
+class GlooComm(object):
+    """Control-plane communicator over torch.distributed (gloo).  Host memory only."""
+
+    def __init__(self, rank=None, world=None, init_method=None):
+        import torch.distributed as dist
+        self.dist = dist
+        if not dist.is_initialized():
+            kw = {}
+            if rank is not None:
+                kw = dict(rank=rank, world_size=world)
+            if init_method is not None:
+                kw['init_method'] = init_method
+            dist.init_process_group(backend='gloo', **kw)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def allreduce_avg_numpy(self, a):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a).copy())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return (t.numpy() / self.world).astype(a.dtype)
+
+    def max_float(self, x):
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def broadcast_bytes(self, b, root=0):
+        obj = [b if self.rank == root else None]
+        self.dist.broadcast_object_list(obj, src=root)
+        return obj[0]
+
+
+def default_comm():
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return LocalComm()
+    return GlooComm()
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous, equal slice [lo, hi) of the batch for ``rank``."""
+    assert n_rows % world == 0, "global batch %d is not divisible by %d ranks" % (n_rows, world)
+    per = n_rows // world
+    return rank * per, (rank + 1) * per
+
+
+class DataParallel(object):
+    """Keeps replicas in step: identical initial parameters, averaged gradients.
+
+        dp = DataParallel(model, optimizer)          # broadcasts rank 0's parameters
+        x_local = x_global[slice(*dp.shard(len(x_global)))]
+        loss = step_fn(...); loss.backward()
+        dp.sync_gradients()                          # one averaging all-reduce
+        optimizer.step()
+    """
+
+    def __init__(self, model, optimizer, comm=None, broadcast=True):
+        self.model, self.optimizer = model, optimizer
+        self.comm = comm if comm is not None else default_comm()
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.arena = getattr(optimizer, 'arena', None)
+        self._nccl = False
+        if self.world > 1 and self.arena is not None:
+            rt = self.arena.rt
+            ident = None
+            if self.rank == 0:
+                buf = (np.zeros(128, dtype=np.uint8))
+                rt.api.nccl_unique_id(buf.ctypes.data)
+                ident = buf.tobytes()
+            ident = self.comm.broadcast_bytes(ident, root=0)
+            idbuf = np.frombuffer(ident, dtype=np.uint8).copy()
+            rt.api.nccl_init(idbuf.ctypes.data, self.world, self.rank)
+            self._nccl = True
+        if broadcast and self.world > 1:
+            self.broadcast_parameters()
+
+    def shard(self, n_rows):
+        return shard_rows(n_rows, self.rank, self.world)
+
+    def broadcast_parameters(self, root=0):
+        if self._nccl:
+            a = self.arena
+            a.rt.api.nccl_broadcast(a.param_buf.ptr, a.total * 4, root)
+            return
+        for p in self.optimizer.parameters:
+            data = self.comm.broadcast_bytes(p.numpy().tobytes() if self.rank == root else None, root=root)
+            new = np.frombuffer(data, dtype=p.dtype).reshape(p.shape)
+            p.fill(0.0)
+            p += p.__class__.from_numpy(new.copy(), requires_grad=False)
+
+    def sync_gradients(self):
+        """Average ``.grad`` of every parameter over the ranks (in place)."""
+        if self.world == 1:
+            return
+        if self._nccl:
+            a = self.arena
+            a.adopt_grads(self.optimizer.parameters)
+            a.rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
+            return
+        for p in self.optimizer.parameters:
+            g = p.grad
+            avg = self.comm.allreduce_avg_numpy(g.numpy())
+            g.fill(0.0)
+            g += g.__class__.from_numpy(avg, requires_grad=False)
+
+    def close(self):
+        if self._nccl:
+            self.arena.rt.api.nccl_destroy()
+            self._nccl = False
