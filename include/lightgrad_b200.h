@@ -157,6 +157,11 @@ typedef struct LgGemmDesc {
 } LgGemmDesc;
 int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c,
             const void* bias, int accumulate);
+/* per-launch timing of lg_gemm with CUDA events on the compute stream (off by default):
+ * lg_prof_gemm(1) starts collecting, lg_prof_gemm_read drains the stream and returns the summed
+ * kernel time, the number of launches and their algorithmic flops (2*M*N*K*batch) since the last read */
+int lg_prof_gemm(int enable);
+int lg_prof_gemm_read(double* total_ms, uint64_t* launches, double* total_flops);
 /* 1 if the tensor-core kernel can take this problem in `mode` without a fallback */
 int lg_gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d);
 
@@ -203,7 +208,7 @@ int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, in
 /* ---- collectives (new; NCCL over NVLink, one process per GPU) ------------------------------- */
 int lg_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId */
 int lg_nccl_init(const void* id128, int world, int rank);
-int lg_nccl_allreduce_f32(void* buf, int64_t n, int average, int on_comm_stream);
+int lg_nccl_allreduce_f32(void* buf, int64_t n, int op /* 0 sum, 1 avg, 2 max */, int on_comm_stream);
 int lg_nccl_broadcast(void* buf, int64_t nbytes, int root);
 int lg_nccl_wait(void);                                   /* compute stream waits for comm stream */
 int lg_nccl_fork(void);                                   /* comm stream waits for compute stream */

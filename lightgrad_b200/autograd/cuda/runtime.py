@@ -67,6 +67,8 @@ _SIGNATURES = {
     'lg_reduce': [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_double],
     'lg_gemm': [C.c_int, C.c_int, C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, C.c_int],
     'lg_gemm_tc_supported': [C.c_int, C.c_int, C.POINTER(GemmDesc)],
+    'lg_prof_gemm': [C.c_int],
+    'lg_prof_gemm_read': [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)],
     'lg_gather_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp],
     'lg_scatter_add_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp],
     'lg_scatter_set_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, C.c_double],
@@ -162,6 +164,17 @@ def launch_count():
     n = C.c_uint64(0)
     ensure_device().launch_count(C.byref(n))
     return n.value
+
+
+def gemm_profile(enable):
+    ensure_device().prof_gemm(1 if enable else 0)
+
+
+def gemm_profile_read():
+    """(summed kernel ms, launches, algorithmic flops) of the lg_gemm launches since the last read."""
+    ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
+    ensure_device().prof_gemm_read(C.byref(ms), C.byref(n), C.byref(fl))
+    return ms.value, n.value, fl.value
 
 
 def mem_stats():

@@ -10,7 +10,41 @@ int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, c
 
 using namespace lg;
 
+#include <vector>
+namespace {
+// opt-in per-launch timing of the matmul kernels (bench.py's roofline leg): CUDA events on the
+// compute stream around every lg_gemm launch while enabled
+struct GemmProbe { cudaEvent_t e0, e1; double flops; };
+bool g_prof_on = false;
+std::vector<GemmProbe> g_probes;
+}  // namespace
+
 extern "C" {
+
+int lg_prof_gemm(int enable) {
+    LG_INIT();
+    g_prof_on = enable != 0;
+    return 0;
+}
+
+int lg_prof_gemm_read(double* total_ms, uint64_t* launches, double* total_flops) {
+    LG_INIT();
+    LG_CUDA(cudaStreamSynchronize(stream()));
+    double ms = 0.0, fl = 0.0;
+    for (auto& p : g_probes) {
+        float t = 0.f;
+        LG_CUDA(cudaEventElapsedTime(&t, p.e0, p.e1));
+        ms += t;
+        fl += p.flops;
+        cudaEventDestroy(p.e0);
+        cudaEventDestroy(p.e1);
+    }
+    *total_ms = ms;
+    *launches = g_probes.size();
+    *total_flops = fl;
+    g_probes.clear();
+    return 0;
+}
 
 int lg_gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d) {
     return gemm_tc_supported(mode, dtype, d, nullptr, nullptr, nullptr);
@@ -21,9 +55,23 @@ int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void*
     LG_INIT();
     LG_REQUIRE(d->M >= 0 && d->N >= 0 && d->K >= 0, "lg_gemm: negative dimension");
     LG_REQUIRE(d->batch0 >= 1 && d->batch1 >= 1, "lg_gemm: batch dims must be >= 1");
-    if (mode != LG_GEMM_FP32_SIMT && gemm_tc_supported(mode, dtype, d, a, b, c))
-        return gemm_tc(mode, d, a, b, c, bias, accumulate);
-    return gemm_simt(dtype, d, a, b, c, bias, accumulate);
+    GemmProbe pr;
+    if (g_prof_on) {
+        LG_CUDA(cudaEventCreate(&pr.e0));
+        LG_CUDA(cudaEventCreate(&pr.e1));
+        pr.flops = 2.0 * (double)d->M * (double)d->N * (double)d->K * (double)(d->batch0 * d->batch1);
+        LG_CUDA(cudaEventRecord(pr.e0, stream()));
+    }
+    int rc;
+    if (mode != LG_GEMM_FP32_SIMT && !accumulate && gemm_tc_supported(mode, dtype, d, a, b, c))
+        rc = gemm_tc(mode, d, a, b, c, bias, accumulate);
+    else
+        rc = gemm_simt(dtype, d, a, b, c, bias, accumulate);
+    if (g_prof_on) {
+        LG_CUDA(cudaEventRecord(pr.e1, stream()));
+        g_probes.push_back(pr);
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -1,8 +1,506 @@
-// placeholder until the tcgen05 kernel lands
+// Tensor-core matmul for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators, operands staged
+// by TMA, persistent warp-specialised CTAs.
+//
+// Replaces the reference's OpenCL SGEMM (opencl/kernels.py:201-337) for the "TF32 tensor-core mode".
+// fp32 operands are read straight from HBM by TMA (128-byte swizzled boxes) and consumed by
+// tcgen05.mma.kind::tf32 (the tensor core drops the low mantissa bits; accumulation is fp32 in
+// TMEM) -- there is no conversion pass and no operand copy: transposed operands (x @ W^T,
+// dC @ B^T, A^T @ dC) are expressed through the UMMA "major" bits, row strides through the TMA
+// descriptor, ragged edges through TMA out-of-bounds zero fill / clipped stores.
+//
+//   CTA tile 128 x BN (BN in {64,128,192,256}), K step 32 fp32 = one 128-byte swizzle row
+//   warp 0        TMA producer          (ring of kStages {A,B} stages, full/empty mbarriers)
+//   warp 1        TMEM allocator + MMA issuer (one elected lane; 4 x tcgen05.mma m128nBNk8 per stage;
+//                                       tcgen05.commit releases the stage / publishes the accumulator)
+//   warps 2..5    epilogue: tcgen05.ld 32x32b.x32 -> (+bias) -> swizzled smem -> TMA store
+//                 (cp.reduce.async.bulk.tensor .add when the K range is split across CTAs)
+//   two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// Roofline: tensor pipe (TF32 dense = half the bf16 rate).  Algorithmic flops 2*M*N*K.
 #include "lg_common.cuh"
-namespace lg {
-int gemm_tc_supported(int, int, const LgGemmDesc*, const void*, const void*, const void*) { return 0; }
-int gemm_tc(int, const LgGemmDesc*, const void*, const void*, void*, const void*, int) {
-    return set_error("tensor-core GEMM not built");
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+using namespace lg;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;               // fp32 elements per K step = 128 bytes
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 32 fp32, per warp, double buffered
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LG_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LG_DONE;\n\t"
+        "bra LG_WAIT;\n\t"
+        "LG_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4, [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [46,48) version=1,
+//   [61,64) layout type (2 = SWIZZLE_128B)
+//   fp32/tf32 operands that are MN-major must use layout type 1 (SWIZZLE_128B_BASE32B: 32-byte chunks
+//   permuted over 4-row groups) -- the only MN-major layout the tf32 tensor core accepts
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcParams {
+    int M, N, K;
+    int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
+    const float* bias;
+};
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, TcParams p) {
+    constexpr int B_STAGE_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle atoms
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(epi_base + EPI_WARPS * 2 * EPI_BUF_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int work_items = p.tiles_m * p.tiles_n * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c));
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+                const int tile = w / p.splits, split = w - tile * p.splits;
+                const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+                const int kb0 = split * p.kblocks_per_split;
+                int kb1 = kb0 + p.kblocks_per_split;
+                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = stage_base + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_2d(&map_a, &full[stage], sa, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j)
+                            tma_load_2d(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(&map_b, &full[stage], sb, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_2d(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ========================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int kb0 = split * p.kblocks_per_split;
+                int kb1 = kb0 + p.kblocks_per_split;
+                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        // K-major : SWIZZLE_128B; 32 bytes along the swizzled row per k-step, 8-row groups 1024 B apart
+                        // MN-major: SWIZZLE_128B_BASE32B; 8 k-rows (1024 B) per k-step, 4-row groups 512 B apart,
+                        //           32-element MN chunks BK*128 B apart
+                        const uint64_t da = A_MN ? umma_desc(sa + ks * 1024, BK * 128, 512, 1)
+                                                 : umma_desc(sa + ks * 32, 16, 1024, 2);
+                        const uint64_t db = B_MN ? umma_desc(sb + ks * 1024, BK * 128, 512, 1)
+                                                 : umma_desc(sb + ks * 32, 16, 1024, 2);
+                        const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+                            "}" ::"r"(d_tmem),
+                            "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                            : "memory");
+                    }
+                    // frees the smem stage once the MMAs above have consumed it
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                     smem_u32(&empty[stage]))
+                                 : "memory");
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                // accumulator complete -> epilogue
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                 smem_u32(&tfull[acc]))
+                             : "memory");
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue ==========================================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int ew = warp - 2;                // staging slot
+        uint8_t* buf0 = epi_base + ew * 2 * EPI_BUF_BYTES;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int flip = 0;
+        for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+            const int tile = w / p.splits, split = w - tile * p.splits;
+            const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+            mbar_wait(&tfull[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool rows_live = (m0 + 32 * q) < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (rows_live) {
+                    uint8_t* buf = buf0 + flip * EPI_BUF_BYTES;
+                    // the TMA store that last read this buffer (two chunks ago) must have drained
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const bool add_bias = p.bias != nullptr && split == 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o;
+                        o.x = __uint_as_float(v[4 * j + 0]);
+                        o.y = __uint_as_float(v[4 * j + 1]);
+                        o.z = __uint_as_float(v[4 * j + 2]);
+                        o.w = __uint_as_float(v[4 * j + 3]);
+                        if (add_bias) {
+                            const int cn = col0 + 4 * j;
+                            if (cn + 3 < p.N) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cn);
+                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                            } else {
+                                if (cn + 0 < p.N) o.x += p.bias[cn + 0];
+                                if (cn + 1 < p.N) o.y += p.bias[cn + 1];
+                                if (cn + 2 < p.N) o.z += p.bias[cn + 2];
+                            }
+                        }
+                        // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.splits > 1) tma_reduce_add_2d(&map_c, buf, col0, m0 + 32 * q);
+                        else tma_store_2d(&map_c, buf, col0, m0 + 32 * q);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    flip ^= 1;
+                }
+            }
+            // this warp is done reading the accumulator stage
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&tempty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return set_error("cuTensorMapEncodeTiled is not available from the driver");
+    }
+    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    return 0;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous extent, dim1 = strided extent
+int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t outer_stride_elems,
+             int box_inner, int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)outer_stride_elems * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+template <int BN>
+constexpr int stages_for() { return BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)); }
+
+template <int BN>
+constexpr size_t smem_for() {
+    return (size_t)stages_for<BN>() * (A_STAGE_BYTES + BN * 128) + EPI_WARPS * 2 * EPI_BUF_BYTES +
+           (2 * stages_for<BN>() + 4) * 8 + 16 + 1024;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, int grid) {
+    constexpr int ST = stages_for<BN>();
+    constexpr size_t smem = smem_for<BN>();
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, ST>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    kern<<<grid, 192, smem, stream()>>>(ma, mb, mc, p);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int BN>
+int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+              const TcParams& p, int grid) {
+    if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(ma, mb, mc, p, grid);
+    if (!a_mn && b_mn) return launch_cfg<BN, false, true>(ma, mb, mc, p, grid);
+    if (a_mn && !b_mn) return launch_cfg<BN, true, false>(ma, mb, mc, p, grid);
+    return launch_cfg<BN, true, true>(ma, mb, mc, p, grid);
+}
+
+bool k_major(int64_t s_mn, int64_t s_k, int64_t extent_mn) { return s_k == 1 && (s_mn % 4 == 0 || extent_mn == 1); }
+bool mn_major(int64_t s_mn, int64_t s_k, int64_t extent_k) { return s_mn == 1 && (s_k % 4 == 0 || extent_k == 1); }
+
+struct Plan {
+    int bn, splits, tiles_m, tiles_n, kblocks, kper;
+};
+
+Plan choose_plan(int64_t M, int64_t N, int64_t K) {
+    const int sms = sm_count();
+    const int kblocks = (int)((K + BK - 1) / BK);
+    Plan best{};
+    double best_score = -1.0;
+    const int cands[4] = {256, 192, 128, 64};
+    for (int bn : cands) {
+        if (bn > 64 && N <= bn / 2) continue;            // mostly padding
+        const int tm = (int)((M + BM - 1) / BM), tn = (int)((N + bn - 1) / bn);
+        const int tiles = tm * tn;
+        int splits = 1;
+        if (tiles < sms) {
+            splits = sms / tiles;
+            const int max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;   // >= 8 k-blocks (256 of K) per split
+            if (splits > max_splits) splits = max_splits;
+            if (splits > 16) splits = 16;
+            if (splits < 1) splits = 1;
+        }
+        int kper = (kblocks + splits - 1) / splits;
+        splits = (kblocks + kper - 1) / kper;
+        const int items = tiles * splits;
+        const int waves = (items + sms - 1) / sms;
+        const double util = (double)items / ((double)waves * sms);
+        const double useful = ((double)M * N) / ((double)tm * BM * tn * bn);   // padding waste
+        const double shape = bn == 256 ? 1.0 : (bn == 192 ? 0.95 : (bn == 128 ? 0.85 : 0.6));
+        const double split_cost = splits > 1 ? 0.92 : 1.0;
+        const double score = util * useful * shape * split_cost;
+        if (score > best_score) {
+            best_score = score;
+            best = Plan{bn, splits, tm, tn, kblocks, kper};
+        }
+    }
+    return best;
+}
+
+}  // namespace
+
+namespace lg {
+
+int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c) {
+    if (mode != LG_GEMM_TF32_TC || dtype != LG_F32) return 0;
+    if (d->batch0 * d->batch1 != 1) return 0;
+    if (d->M < 1 || d->N < 1 || d->K < 1) return 0;
+    if (d->M > 0x7fffffff || d->N > 0x7fffffff || d->K > 0x7fffffff) return 0;
+    // tiny problems are launch bound either way; keep them on the exact path
+    if ((double)d->M * d->N * d->K < 64.0 * 64.0 * 64.0 * 8) return 0;
+    const bool a_ok = k_major(d->sa_m, d->sa_k, d->M) || mn_major(d->sa_m, d->sa_k, d->K);
+    const bool b_ok = k_major(d->sb_n, d->sb_k, d->N) || mn_major(d->sb_n, d->sb_k, d->K);
+    const bool c_ok = d->sc_n == 1 && (d->sc_m % 4 == 0 || d->M == 1);
+    if (!a_ok || !b_ok || !c_ok) return 0;
+    if (a && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15)) return 0;
+    return 1;
+}
+
+int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate) {
+    (void)mode;
+    if (load_encode()) return 1;
+    const int64_t M = d->M, N = d->N, K = d->K;
+    const bool a_mn = !k_major(d->sa_m, d->sa_k, M);
+    const bool b_mn = !k_major(d->sb_n, d->sb_k, N);
+    if (accumulate) return set_error("gemm_tc: accumulate is served by the SIMT kernel");
+    Plan pl = choose_plan(M, N, K);
+    CUtensorMap ma, mb, mc;
+    int rc;
+    // operand maps: K-major -> (inner = K, outer = rows); MN-major -> (inner = rows, outer = K)
+    if (!a_mn) rc = make_map(&ma, a, K, M, d->sa_m, BK, BM);
+    else rc = make_map(&ma, a, M, K, d->sa_k, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, BK, pl.bn);
+    else rc = make_map(&mb, b, N, K, d->sb_k, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_map(&mc, c, N, M, d->sc_m, 32, 32);
+    if (rc) return rc;
+    TcParams p;
+    p.M = (int)M;
+    p.N = (int)N;
+    p.K = (int)K;
+    p.tiles_m = pl.tiles_m;
+    p.tiles_n = pl.tiles_n;
+    p.splits = pl.splits;
+    p.kblocks_per_split = pl.kper;
+    p.kblocks_total = pl.kblocks;
+    p.bias = (const float*)bias;
+    if (pl.splits > 1) {
+        // split-K partials are summed by TMA reduce-add into a zeroed C
+        if (d->sc_m == N) {
+            LG_CUDA(cudaMemsetAsync(c, 0, (size_t)M * N * 4, stream()));
+        } else {
+            LG_CUDA(cudaMemset2DAsync(c, (size_t)d->sc_m * 4, 0, (size_t)N * 4, (size_t)M, stream()));
+        }
+    }
+    const int items = pl.tiles_m * pl.tiles_n * pl.splits;
+    const int grid = items < sm_count() ? items : sm_count();
+    switch (pl.bn) {
+        case 256: return launch_bn<256>(a_mn, b_mn, ma, mb, mc, p, grid);
+        case 192: return launch_bn<192>(a_mn, b_mn, ma, mb, mc, p, grid);
+        case 128: return launch_bn<128>(a_mn, b_mn, ma, mb, mc, p, grid);
+        default: return launch_bn<64>(a_mn, b_mn, ma, mb, mc, p, grid);
+    }
+}
+
 }  // namespace lg

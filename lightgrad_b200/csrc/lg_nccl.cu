@@ -94,10 +94,10 @@ int lg_nccl_wait(void) {
     return 0;
 }
 
-int lg_nccl_allreduce_f32(void* buf, int64_t n, int average, int on_comm_stream) {
+int lg_nccl_allreduce_f32(void* buf, int64_t n, int op, int on_comm_stream) {
     LG_REQUIRE(g_comm_nccl, "lg_nccl_allreduce_f32: communicator not initialised");
     if (n == 0) return 0;
-    LG_NCCL(api.AllReduce(buf, buf, (size_t)n, ncclFloat, average ? ncclAvg : ncclSum, g_comm_nccl,
+    LG_NCCL(api.AllReduce(buf, buf, (size_t)n, ncclFloat, op == 1 ? ncclAvg : (op == 2 ? ncclMax : ncclSum), g_comm_nccl,
                           on_comm_stream ? comm_stream() : stream()));
     count_launch();
     return 0;

@@ -193,6 +193,11 @@ class FakeDevice(object):
     def gemm_tc_supported(self, mode, dt, dref):
         return 0
 
+    def prof_gemm(self, enable): pass
+
+    def prof_gemm_read(self, ms, n, fl):
+        ms._obj.value, n._obj.value, fl._obj.value = 0.0, 0, 0.0
+
     # ---- indexing
     def gather_rows(self, dt, idt, src, n_src, row_stride, idx, n_idx, row_len, out):
         self.launches += 1
