@@ -184,12 +184,13 @@ int lg_index_linearize(int n_arrays, const void* const* idx, const int* idx_dtyp
 int lg_softmax_fwd(int dtype, const void* x, void* y, int64_t rows, int64_t cols, double scale);
 /* dx = scale * y * (g - sum(g*y)) */
 int lg_softmax_bwd(int dtype, const void* y, const void* g, void* dx, int64_t rows, int64_t cols, double scale);
-/* loss_rows[i] = logsumexp(x[i,:]) - x[i,label[i]];  lse[i] saved for backward */
-int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, const void* labels,
+/* loss_rows[i] = logsumexp(x[i,:]) - x[i,label[i]];  lse[i] saved for backward.
+ * `ld` = elements between consecutive rows of logits (>= cols; rows may be padded for TMA alignment) */
+int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, int64_t ld, const void* labels,
                          void* loss_rows, void* lse, int64_t rows, int64_t cols);
-/* dlogits[i,j] = (exp(x[i,j]-lse[i]) - [j==label[i]]) * gscale[0] / rows ; may run in place on logits */
-int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, const void* labels, const void* lse,
-                         const void* gscale, void* dlogits, int64_t rows, int64_t cols);
+/* dlogits[i,j] = (exp(x[i,j]-lse[i]) - [j==label[i]]) / rows * gscale[0] ; may run in place on logits */
+int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, int64_t ld, const void* labels, const void* lse,
+                         const void* gscale, void* dlogits, int64_t ld_out, int64_t rows, int64_t cols);
 /* layer norm over the last axis (nn.py:109-124): y = (x-mean)/sqrt(var+eps)*gamma+beta */
 int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y,
                      void* mean, void* rstd, int64_t rows, int64_t cols, double eps);

@@ -649,7 +649,14 @@ def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
     ba, bb = a._shape[:-2], b._shape[:-2]
     bshape = _bshape(ba, bb)
     if out is None:
-        out = CudaTensor._new(bshape + (M, N), a._dtype)
+        use_mode = _matmul_mode if mode is None else mode
+        if use_mode != rt.GEMM_FP32_SIMT and N % 4 != 0 and N >= 64 and a._code == rt.F32:
+            # TMA needs 16-byte aligned row strides: pad the leading dimension and hand back a view
+            ld = (N + 31) // 32 * 32
+            full = CudaTensor._new(bshape + (M, ld), a._dtype)
+            out = full._view(bshape + (M, N), full._strides)
+        else:
+            out = CudaTensor._new(bshape + (M, N), a._dtype)
     sa = _bstrides(a._view(ba, a._strides[:-2]), bshape) if bshape else []
     sb = _bstrides(b._view(bb, b._strides[:-2]), bshape) if bshape else []
     sc = list(out._strides[:-2])
@@ -679,6 +686,14 @@ def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
             rt.api.gemm(_matmul_mode if mode is None else mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr,
                         bias.ptr if bias is not None else None, 1 if accumulate else 0)
     return out
+
+
+def _with_shape(t, shape):
+    """Re-view a fresh GEMM result under ``shape`` (same memory; keeps the sole-owner flag)."""
+    st = contiguous_strides(shape) if t._contig else _reshape_strides(t._shape, t._strides, shape)
+    v = t._view(shape, st)
+    v._temp = t._temp
+    return v
 
 
 def _fold_rows(t):
@@ -715,9 +730,7 @@ class dot(Function):
         if len(b._shape) == 2 and len(a._shape) > 2:
             # (batch.., M, K) @ (K, N): one GEMM with M' = batch*M
             a2 = _fold_rows(a)
-            out = _gemm(a2, b)
-            out = out._view(a._shape[:-1] + (b._shape[-1],), None)
-            out._temp = True
+            out = _with_shape(_gemm(a2, b), a._shape[:-1] + (b._shape[-1],))
         else:
             out = _gemm(a, b)
         if ctx.va or ctx.vb:
@@ -726,8 +739,7 @@ class dot(Function):
                 shp.pop(-1)
             if ctx.va:
                 shp.pop(-2 if not ctx.vb else -1)
-            out = out._view(tuple(shp), None)
-            out._temp = True
+            out = _with_shape(out, tuple(shp))
         return out
 
     def backward(ctx, out_grad):
@@ -743,8 +755,7 @@ class dot(Function):
         if len(b._shape) == 2 and len(a._shape) > 2:
             # dA = g @ b^T per row; dB = A2d^T @ g2d : the batch sum is folded into the GEMM's K dim
             g2, a2 = _fold_rows(g), _fold_rows(a)
-            da = _gemm(g2, _swap_last(b))._view(a._shape, None)
-            da._temp = True
+            da = _with_shape(_gemm(g2, _swap_last(b)), a._shape)
             db = _gemm(_swap_last(a2), g2)
         else:
             da = _gemm(g, _swap_last(b))
@@ -770,16 +781,12 @@ class linear(Function):
         x2 = _fold_rows(x)
         x2._mark_shared()
         ctx.save_for_backward(x2, weight, x._shape, bias is not None)
-        out = _gemm(x2, _swap_last(weight), bias=bias)
-        out = out._view(x._shape[:-1] + (weight._shape[0],), None)
-        out._temp = True
-        return out
+        return _with_shape(_gemm(x2, _swap_last(weight), bias=bias), x._shape[:-1] + (weight._shape[0],))
 
     def backward(ctx, out_grad):
         x2, weight, xshape, has_bias = ctx.get_saved_tensors()
-        g2 = _fold_rows(out_grad if out_grad._contig else out_grad.contiguous())
-        dx = _gemm(g2, weight)._view(xshape, None)
-        dx._temp = True
+        g2 = _fold_rows(out_grad)
+        dx = _with_shape(_gemm(g2, weight), xshape)
         dw = _gemm(_swap_last(g2), x2)
         if has_bias:
             db = _reduce(RED['SUM'], g2, (0,), False)
@@ -1050,15 +1057,17 @@ class layernorm(Function):
 
 def cross_entropy_forward(logits, labels):
     """Fused log-softmax + NLL over the last axis.  Returns (mean loss tensor of shape (), saved state)."""
-    x = _float_like(logits).contiguous()
-    rows, cols = x._shape[0], x._shape[-1]
+    x = _float_like(logits)
     assert len(x._shape) == 2, "fused cross entropy expects (rows, classes) logits"
+    if x._strides[1] != 1 or x._strides[0] < x._shape[1]:
+        x = x.contiguous()
+    rows, cols = x._shape
     lab = labels if isinstance(labels, CudaTensor) else CudaTensor.from_numpy(np.asarray(labels), requires_grad=False)
     lab = lab.contiguous()
     if lab._code not in (rt.I32, rt.I64, rt.I16):
         lab = lab.astype(np.int64)
     loss_rows, lse = CudaTensor._new((rows,), x._dtype), CudaTensor._new((rows,), x._dtype)
-    rt.api.cross_entropy_fwd(x._code, lab._code, x.ptr, lab.ptr, loss_rows.ptr, lse.ptr, rows, cols)
+    rt.api.cross_entropy_fwd(x._code, lab._code, x.ptr, x._strides[0], lab.ptr, loss_rows.ptr, lse.ptr, rows, cols)
     loss = _reduce(RED['SUM'], loss_rows, (0,), False, scale=1.0 / rows)
     x._mark_shared()
     return loss, (x, lab, lse)
@@ -1070,8 +1079,12 @@ def cross_entropy_backward(saved, out_grad):
     g = out_grad.contiguous()
     if g._code != x._code:
         g = g.astype(x._dtype)
-    dx = CudaTensor._new(x._shape, x._dtype)
-    rt.api.cross_entropy_bwd(x._code, lab._code, x.ptr, lab.ptr, lse.ptr, g.ptr, dx.ptr, rows, cols)
+    # same (possibly padded) row pitch as the logits, so the backward GEMMs can read it through TMA
+    ld = x._strides[0]
+    full = CudaTensor._new((rows, ld), x._dtype)
+    dx = full._view((rows, cols), (ld, 1))
+    dx._temp = True
+    rt.api.cross_entropy_bwd(x._code, lab._code, x.ptr, ld, lab.ptr, lse.ptr, g.ptr, dx.ptr, ld, rows, cols)
     return dx
 
 
@@ -1105,7 +1118,7 @@ class conv(Function):
         y = _gemm(flat_x, _swap_last(flat_w))              # (positions, out_channels)
         flat_x._mark_shared()
         ctx.save_for_backward(flat_x, flat_w, t._shape, kernel._shape, strides, lead)
-        y = y._view(lead + (kernel._shape[0],), None)
+        y = _with_shape(y, lead + (kernel._shape[0],))
         # move the channel axis to where the collapsed input-channel axis was, then drop that axis
         nd = len(y._shape)
         perm = list(range(nd))
@@ -1122,11 +1135,11 @@ class conv(Function):
         perm = [i for i in range(nd) if i != nd - n] + [nd - n]
         flat_g = g.transpose(*perm).contiguous()._view((_prod(g._shape) // w_shape[0], w_shape[0]), None)
         flat_xg = _gemm(flat_g, flat_w)                     # (positions, in_c*k*k)
-        w_grad = _gemm(_swap_last(flat_g), flat_x)._view(w_shape, None)
+        w_grad = _with_shape(_gemm(_swap_last(flat_g), flat_x), w_shape)
         # col2im: add every kernel-offset plane back into the input gradient (windows overlap)
         x_grad = CudaTensor.zeros(in_shape, dtype=flat_x._dtype, requires_grad=False)
         xw = _window_view(x_grad, w_shape[1:], strides)
-        src = flat_xg._view(xw._shape, None)
+        src = _with_shape(flat_xg, xw._shape)
         k_nd = len(w_shape[1:])
         for pos in np.ndindex(*w_shape[1:]):
             sel = (slice(None),) * (len(xw._shape) - k_nd) + tuple(pos)

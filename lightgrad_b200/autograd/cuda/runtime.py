@@ -75,8 +75,8 @@ _SIGNATURES = {
     'lg_index_linearize': [C.c_int, C.POINTER(_vp), C.POINTER(C.c_int), _i64p, _i64p, C.c_int64, _vp],
     'lg_softmax_fwd': [C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_softmax_bwd': [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
-    'lg_cross_entropy_fwd': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
-    'lg_cross_entropy_bwd': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
+    'lg_cross_entropy_fwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int64],
+    'lg_cross_entropy_bwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64],
     'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],

@@ -108,12 +108,12 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 // ================================ cross entropy ====================================================
 // One CTA per row; online max/sum in one sweep (logits rows are 122 KB at V = 30522).
 template <typename T, typename L>
-__global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, const L* __restrict__ labels,
-                                                     T* __restrict__ loss_rows, T* __restrict__ lse, int64_t rows,
-                                                     int64_t cols) {
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, int64_t ld,
+                                                     const L* __restrict__ labels, T* __restrict__ loss_rows,
+                                                     T* __restrict__ lse, int64_t rows, int64_t cols) {
     __shared__ T sm[8];
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const T* p = x + row * cols;
+        const T* p = x + row * ld;
         T m = -INFINITY, s = T(0);
         for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
             T v = p[j];
@@ -138,14 +138,15 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, co
 }
 
 template <typename T, typename L>
-__global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, const L* __restrict__ labels,
-                                                     const T* __restrict__ lse, const T* __restrict__ gscale,
-                                                     T* __restrict__ dx, int64_t rows, int64_t cols) {
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, int64_t ld,
+                                                     const L* __restrict__ labels, const T* __restrict__ lse,
+                                                     const T* __restrict__ gscale, T* __restrict__ dx, int64_t ld_dx,
+                                                     int64_t rows, int64_t cols) {
     const T gs = gscale[0];
     const T inv_rows = T(rows);
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const T* p = x + row * cols;
-        T* q = dx + row * cols;
+        const T* p = x + row * ld;
+        T* q = dx + row * ld_dx;
         const T l = lse[row];
         int64_t lab = (int64_t)labels[row];
         if (lab < 0) lab += cols;
@@ -270,18 +271,19 @@ int softmax_bwd(const void* y, const void* g, void* dx, int64_t rows, int64_t co
 }
 
 template <typename T, typename L>
-int ce_fwd(const void* x, const void* labels, void* loss_rows, void* lse, int64_t rows, int64_t cols) {
+int ce_fwd(const void* x, int64_t ld, const void* labels, void* loss_rows, void* lse, int64_t rows, int64_t cols) {
     int64_t cap = (int64_t)sm_count() * 8;
-    ce_fwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>((const T*)x, (const L*)labels,
+    ce_fwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>((const T*)x, ld, (const L*)labels,
                                                                               (T*)loss_rows, (T*)lse, rows, cols);
     LG_CHECK_LAUNCH();
     return 0;
 }
 template <typename T, typename L>
-int ce_bwd(const void* x, const void* labels, const void* lse, const void* gs, void* dx, int64_t rows, int64_t cols) {
+int ce_bwd(const void* x, int64_t ld, const void* labels, const void* lse, const void* gs, void* dx, int64_t ld_dx,
+           int64_t rows, int64_t cols) {
     int64_t cap = (int64_t)sm_count() * 8;
     ce_bwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>(
-        (const T*)x, (const L*)labels, (const T*)lse, (const T*)gs, (T*)dx, rows, cols);
+        (const T*)x, ld, (const L*)labels, (const T*)lse, (const T*)gs, (T*)dx, ld_dx, rows, cols);
     LG_CHECK_LAUNCH();
     return 0;
 }
@@ -304,16 +306,16 @@ int lg_softmax_bwd(int dtype, const void* y, const void* g, void* dx, int64_t ro
     return set_error("lg_softmax_bwd: unsupported dtype %d", dtype);
 }
 
-int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, const void* labels, void* loss_rows, void* lse,
-                         int64_t rows, int64_t cols) {
+int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, int64_t ld, const void* labels,
+                         void* loss_rows, void* lse, int64_t rows, int64_t cols) {
     LG_INIT();
     if (rows == 0) return 0;
-    LG_REQUIRE(cols > 0, "lg_cross_entropy_fwd: zero classes");
+    LG_REQUIRE(cols > 0 && ld >= cols, "lg_cross_entropy_fwd: need cols > 0 and ld >= cols");
 #define GO(T)                                                                                          \
     switch (idx_dtype) {                                                                               \
-        case LG_I32: return ce_fwd<T, int32_t>(logits, labels, loss_rows, lse, rows, cols);            \
-        case LG_I64: return ce_fwd<T, int64_t>(logits, labels, loss_rows, lse, rows, cols);            \
-        case LG_I16: return ce_fwd<T, int16_t>(logits, labels, loss_rows, lse, rows, cols);            \
+        case LG_I32: return ce_fwd<T, int32_t>(logits, ld, labels, loss_rows, lse, rows, cols);            \
+        case LG_I64: return ce_fwd<T, int64_t>(logits, ld, labels, loss_rows, lse, rows, cols);            \
+        case LG_I16: return ce_fwd<T, int16_t>(logits, ld, labels, loss_rows, lse, rows, cols);            \
         default: return set_error("lg_cross_entropy_fwd: label dtype %d unsupported", idx_dtype);      \
     }
     if (dtype == LG_F32) { GO(float) }
@@ -322,15 +324,15 @@ int lg_cross_entropy_fwd(int dtype, int idx_dtype, const void* logits, const voi
     return set_error("lg_cross_entropy_fwd: unsupported dtype %d", dtype);
 }
 
-int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, const void* labels, const void* lse,
-                         const void* gscale, void* dlogits, int64_t rows, int64_t cols) {
+int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, int64_t ld, const void* labels, const void* lse,
+                         const void* gscale, void* dlogits, int64_t ld_out, int64_t rows, int64_t cols) {
     LG_INIT();
     if (rows == 0) return 0;
 #define GO(T)                                                                                          \
     switch (idx_dtype) {                                                                               \
-        case LG_I32: return ce_bwd<T, int32_t>(logits, labels, lse, gscale, dlogits, rows, cols);      \
-        case LG_I64: return ce_bwd<T, int64_t>(logits, labels, lse, gscale, dlogits, rows, cols);      \
-        case LG_I16: return ce_bwd<T, int16_t>(logits, labels, lse, gscale, dlogits, rows, cols);      \
+        case LG_I32: return ce_bwd<T, int32_t>(logits, ld, labels, lse, gscale, dlogits, ld_out, rows, cols);      \
+        case LG_I64: return ce_bwd<T, int64_t>(logits, ld, labels, lse, gscale, dlogits, ld_out, rows, cols);      \
+        case LG_I16: return ce_bwd<T, int16_t>(logits, ld, labels, lse, gscale, dlogits, ld_out, rows, cols);      \
         default: return set_error("lg_cross_entropy_bwd: label dtype %d unsupported", idx_dtype);      \
     }
     if (dtype == LG_F32) { GO(float) }

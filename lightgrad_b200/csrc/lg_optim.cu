@@ -39,30 +39,54 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
     }
 }
 
+// per-tensor bias corrections 1 - beta^t with t = t0 + i + 1, evaluated in double like python does
+__global__ void adam_prep_kernel(int n_seg, int64_t t0, double b1, double b2, float* __restrict__ c1,
+                                 float* __restrict__ c2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_seg) {
+        const double t = (double)(t0 + i + 1);
+        c1[i] = (float)(1.0 - pow(b1, t));
+        c2[i] = (float)(1.0 - pow(b2, t));
+    }
+}
+
+// arenas are padded so that every tensor starts on a 64-element boundary: a float4 never straddles tensors
 template <bool BELIEF>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, int n_seg,
-                                                   const int64_t* __restrict__ seg_end, int64_t t0, double b1d,
-                                                   double b2d, float neg_lr, float b1, float b2, float omb1,
-                                                   float omb2, float eps) {
+                                                   const int64_t* __restrict__ seg_end, const float* __restrict__ c1,
+                                                   const float* __restrict__ c2, float neg_lr, float b1, float b2,
+                                                   float omb1, float omb2, float eps) {
+    const int64_t nv = n / 4;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = tid; i < n; i += nt) {
-        // segment of element i: first seg with seg_end > i
-        int lo = 0, hi = n_seg - 1;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (seg_end[mid] > i) hi = mid; else lo = mid + 1;
+    int seg = 0;
+    for (int64_t i = tid; i < nv; i += nt) {
+        const int64_t e = i * 4;
+        if (!(e < seg_end[seg] && (seg == 0 || e >= seg_end[seg - 1]))) {
+            int lo = 0, hi = n_seg - 1;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (seg_end[mid] > e) hi = mid; else lo = mid + 1;
+            }
+            seg = lo;
         }
-        const double t = (double)(t0 + lo + 1);
-        const float d1 = (float)(1.0 - pow(b1d, t)), d2 = (float)(1.0 - pow(b2d, t));
-        float gi = g[i];
-        float mi = b1 * m[i] + omb1 * gi;
-        float r = BELIEF ? (gi - mi) : gi;
-        float vi = b2 * v[i] + omb2 * (r * r);
-        m[i] = mi;
-        v[i] = vi;
-        float mh = mi / d1, vh = vi / d2;
-        p[i] += neg_lr * mh / (sqrtf(vh) + eps);
+        const float d1 = c1[seg], d2 = c2[seg];
+        float4 pv = reinterpret_cast<float4*>(p)[i], gv = reinterpret_cast<const float4*>(g)[i],
+               mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gi = gp[k];
+            const float mi = b1 * mp[k] + omb1 * gi;
+            const float r = BELIEF ? (gi - mi) : gi;
+            const float vi = b2 * vp[k] + omb2 * (r * r);
+            mp[k] = mi;
+            vp[k] = vi;
+            pp[k] += neg_lr * (mi / d1) / (sqrtf(vi / d2) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
     }
 }
 
@@ -85,18 +109,27 @@ int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, in
     LG_INIT();
     if (n == 0) return 0;
     LG_REQUIRE(n_seg >= 1, "lg_adam_step: need at least one segment");
-    int grid = grid_for(n, 256, 8);
+    LG_REQUIRE(n % 4 == 0 && aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v),
+               "lg_adam_step: arenas must be 16-byte aligned and padded to a multiple of 4 elements");
+    float* corr = (float*)tmp_alloc(2 * (size_t)n_seg * sizeof(float));
+    if (!corr) return 1;
+    float* seg_c1_dev = corr;
+    float* seg_c2_dev = corr + n_seg;
+    adam_prep_kernel<<<(n_seg + 127) / 128, 128, 0, stream()>>>(n_seg, t0, beta1, beta2, seg_c1_dev, seg_c2_dev);
+    count_launch();
+    int grid = grid_for(n / 4, 256, 8);
     float b1 = (float)beta1, b2 = (float)beta2;
     // (1 - beta) is formed in double by python and then rounded to fp32, as numpy does with the scalar
     float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
     if (belief)
         adam_kernel<true><<<grid, 256, 0, stream()>>>((float*)param, (const float*)grad, (float*)m, (float*)v, n,
-                                                      n_seg, seg_end_dev, t0, beta1, beta2, (float)(-lr), b1,
+                                                      n_seg, seg_end_dev, seg_c1_dev, seg_c2_dev, (float)(-lr), b1,
                                                       b2, omb1, omb2, (float)eps);
     else
         adam_kernel<false><<<grid, 256, 0, stream()>>>((float*)param, (const float*)grad, (float*)m, (float*)v, n,
-                                                       n_seg, seg_end_dev, t0, beta1, beta2, (float)(-lr), b1,
+                                                       n_seg, seg_end_dev, seg_c1_dev, seg_c2_dev, (float)(-lr), b1,
                                                        b2, omb1, omb2, (float)eps);
+    tmp_free(corr);
     LG_CHECK_LAUNCH();
     return 0;
 }

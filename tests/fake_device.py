@@ -191,7 +191,7 @@ class FakeDevice(object):
         Cm[...] = r
 
     def gemm_tc_supported(self, mode, dt, dref):
-        return 0
+        return 1 if mode != rt.GEMM_FP32_SIMT and dt == rt.F32 else 0
 
     def prof_gemm(self, enable): pass
 
@@ -245,20 +245,20 @@ class FakeDevice(object):
         Y, G = _arr(y, dt, [rows, cols]), _arr(g, dt, [rows, cols])
         _arr(dx, dt, [rows, cols])[...] = NP[dt](scale) * (Y * (G - (Y * G).sum(axis=1, keepdims=True)))
 
-    def cross_entropy_fwd(self, dt, idt, x, lab, loss_rows, lse, rows, cols):
+    def cross_entropy_fwd(self, dt, idt, x, ld, lab, loss_rows, lse, rows, cols):
         self.launches += 1
-        X, L = _arr(x, dt, [rows, cols]), _arr(lab, idt, [rows]).astype(np.int64)
+        X, L = _arr(x, dt, [rows, cols], [ld, 1]), _arr(lab, idt, [rows]).astype(np.int64)
         m = X.max(axis=1)
         l = m + np.log(np.exp(X - m[:, None]).sum(axis=1))
         _arr(lse, dt, [rows])[...] = l
         _arr(loss_rows, dt, [rows])[...] = l - X[np.arange(rows), L]
 
-    def cross_entropy_bwd(self, dt, idt, x, lab, lse, gs, dx, rows, cols):
+    def cross_entropy_bwd(self, dt, idt, x, ld, lab, lse, gs, dx, ld_dx, rows, cols):
         self.launches += 1
-        X, L = _arr(x, dt, [rows, cols]), _arr(lab, idt, [rows]).astype(np.int64)
+        X, L = _arr(x, dt, [rows, cols], [ld, 1]), _arr(lab, idt, [rows]).astype(np.int64)
         p = np.exp(X - _arr(lse, dt, [rows])[:, None])
         p[np.arange(rows), L] -= 1
-        _arr(dx, dt, [rows, cols])[...] = p / NP[dt](rows) * _arr(gs, dt, [1])[0]
+        _arr(dx, dt, [rows, cols], [ld_dx, 1])[...] = p / NP[dt](rows) * _arr(gs, dt, [1])[0]
 
     def layernorm_fwd(self, dt, x, w, b, y, mean, rstd, rows, cols, eps):
         self.launches += 1
