@@ -32,4 +32,29 @@ with light.no_grad():
                 bad += (not ok)
                 print("%s M=%5d N=%5d K=%5d ta=%d tb=%d bias=%d  rel_err=%.2e  shape=%s" %
                       ("ok " if ok else "BAD", M, N, K, ta, tb, with_bias, err, got.shape), flush=True)
+# batched problems with strided (head-split) views, as BertSelfAttention issues them
+with light.no_grad():
+    b, h, sq, d = 4, 12, 128, 64
+    q = rs.uniform(-1, 1, (b, sq, h * d)).astype(np.float32)
+    k = rs.uniform(-1, 1, (b, sq, h * d)).astype(np.float32)
+    v = rs.uniform(-1, 1, (b, sq, h * d)).astype(np.float32)
+    Q = T.from_numpy(q).reshape(b, sq, h, d).transpose(0, 2, 1, 3)
+    Kt = T.from_numpy(k).reshape(b, sq, h, d).transpose(0, 2, 3, 1)
+    V = T.from_numpy(v).reshape(b, sq, h, d).transpose(0, 2, 1, 3)
+    qn = q.reshape(b, sq, h, d).transpose(0, 2, 1, 3).astype(np.float64)
+    kn = k.reshape(b, sq, h, d).transpose(0, 2, 3, 1).astype(np.float64)
+    vn = v.reshape(b, sq, h, d).transpose(0, 2, 1, 3).astype(np.float64)
+    p_ = rs.uniform(0, 1, (b, h, sq, sq)).astype(np.float32)
+    P = T.from_numpy(p_)
+    cases = [("QK^T", Q, Kt, qn @ kn), ("PV", P, V, p_.astype(np.float64) @ vn),
+             ("dP=dC V^T", T.from_numpy(q).reshape(b, sq, h, d).transpose(0, 2, 1, 3), ops._swap_last(V), qn @ vn.transpose(0, 1, 3, 2)),
+             ("dV=P^T dC", ops._swap_last(P), Q, p_.astype(np.float64).transpose(0, 1, 3, 2) @ qn),
+             ("dK^T=Q^T dS", ops._swap_last(Q), P, qn.transpose(0, 1, 3, 2) @ p_.astype(np.float64)),
+             ("3d batch", T.from_numpy(q), T.from_numpy(k).transpose(0, 2, 1), q.astype(np.float64) @ k.astype(np.float64).transpose(0, 2, 1))]
+    for name, A, B, want in cases:
+        got = ops._gemm(A, B).numpy()
+        err = np.abs(got - want).max() / (np.abs(want).max() + 1e-30)
+        ok = err < 5e-3 and np.isfinite(got).all()
+        bad += (not ok)
+        print("%s batched %-12s rel_err=%.2e shape=%s" % ("ok " if ok else "BAD", name, err, got.shape), flush=True)
 print("bad:", bad)

@@ -120,6 +120,7 @@ int lg_event_elapsed_ms(void* start, void* stop, float* ms);
 int lg_event_destroy(void* ev);
 int lg_launch_count(uint64_t* n);         /* kernels launched by this library so far */
 void* lg_stream_handle(void);             /* cudaStream_t of the compute stream, for profilers */
+int lg_profiler_range(int start);         /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
 
 /* ---- elementwise (replaces kernels.atom) --------------------------------------------------- */
 /* all operands contiguous, n elements, same dtype; b/c may be NULL for 1/2-input ops */

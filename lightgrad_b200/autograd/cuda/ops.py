@@ -170,7 +170,11 @@ class transpose(Function):
         axes = tuple(ax % nd for ax in axes)
         assert sorted(axes) == list(range(nd)), "axes don't match tensor"
         ctx.save_for_backward(axes)
-        return a._view(tuple(a._shape[i] for i in axes), tuple(a._strides[i] for i in axes))
+        out = a._view(tuple(a._shape[i] for i in axes), tuple(a._strides[i] for i in axes))
+        if a._temp:
+            # sole ownership of the buffer moves to the view
+            a._temp, out._temp = False, True
+        return out
 
     def backward(ctx, out_grad):
         axes, = ctx.get_saved_tensors()
@@ -245,6 +249,8 @@ class reshape(Function):
             a._temp = False
             st = contiguous_strides(shape)
         out = a._view(shape, st)
+        if a._temp:
+            a._temp, out._temp = False, True
         return out
 
     def backward(ctx, out_grad):

@@ -60,6 +60,7 @@ _SIGNATURES = {
     'lg_event_elapsed_ms': [_vp, _vp, C.POINTER(C.c_float)],
     'lg_event_destroy': [_vp],
     'lg_launch_count': [C.POINTER(C.c_uint64)],
+    'lg_profiler_range': [C.c_int],
     'lg_ew_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_double],
     'lg_ew': [C.c_int, C.c_int, C.c_int, _i64p, _vp, _i64p, _vp, _i64p, _vp, _i64p, _vp, _i64p, C.c_double],
     'lg_ew_bwd2_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64],

@@ -106,9 +106,13 @@ class Gradients(object):
                     # nothing flowed into this node (e.g. a branch that only
                     # feeds non-differentiable consumers)
                     continue
-                node._backpropagate(g)
                 if not keep and owner is not None:
+                    # this gradient dies right after the node is processed: hand its buffer to the
+                    # node's backward, so a view of it (reshape / transpose backward) or the tensor
+                    # itself (add backward) can be adopted by a parent instead of copied
                     owner._drop_grad()
+                    g._temp = True
+                node._backpropagate(g)
         finally:
             d = Gradients._depth - 1
             Gradients._depth = d if d > 0 else 0

@@ -55,21 +55,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+// every tensor map is rank 4: (contiguous dim, strided dim, batch1, batch0); plain 2-D problems use batch = 1
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                                  int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 
@@ -98,6 +102,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool a_mn, 
 struct TcParams {
     int M, N, K;
     int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
+    int batch1, batches;      // batches = batch0 * batch1
     const float* bias;
 };
 
@@ -121,7 +126,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int work_items = p.tiles_m * p.tiles_n * p.splits;
+    const int items_per_batch = p.tiles_m * p.tiles_n * p.splits;
+    const int work_items = items_per_batch * p.batches;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -154,7 +160,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-                const int tile = w / p.splits, split = w - tile * p.splits;
+                const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+                const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
+                const int tile = wi / p.splits, split = wi - tile * p.splits;
                 const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
                 const int kb0 = split * p.kblocks_per_split;
                 int kb1 = kb0 + p.kblocks_per_split;
@@ -166,18 +174,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     const int k0 = kb * BK;
                     if (!A_MN) {
-                        tma_load_2d(&map_a, &full[stage], sa, k0, m0);
+                        tma_load_4d(&map_a, &full[stage], sa, k0, m0, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 32; ++j)
-                            tma_load_2d(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0);
+                            tma_load_4d(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
                     }
                     if (!B_MN) {
-                        tma_load_2d(&map_b, &full[stage], sb, k0, n0);
+                        tma_load_4d(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BN / 32; ++j)
-                            tma_load_2d(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0);
+                            tma_load_4d(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -195,7 +203,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-                const int split = w % p.splits;
+                const int split = (w % items_per_batch) % p.splits;
                 const int kb0 = split * p.kblocks_per_split;
                 int kb1 = kb0 + p.kblocks_per_split;
                 if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
@@ -254,7 +262,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t acc_phase = 0;
         int flip = 0;
         for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-            const int tile = w / p.splits, split = w - tile * p.splits;
+            const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+            const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
+            const int tile = wi / p.splits, split = wi - tile * p.splits;
             const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -306,8 +316,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.splits > 1) tma_reduce_add_2d(&map_c, buf, col0, m0 + 32 * q);
-                        else tma_store_2d(&map_c, buf, col0, m0 + 32 * q);
+                        if (p.splits > 1) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        else tma_store_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     flip ^= 1;
@@ -348,14 +358,21 @@ int load_encode() {
     return 0;
 }
 
-// 2-D fp32 tensor map: dim0 = contiguous extent, dim1 = strided extent
+// rank-4 fp32 tensor map: dim0 = contiguous extent, dim1 = strided extent, dim2 = batch1, dim3 = batch0
+struct BatchDims {
+    int64_t n1, s1, n0, s0;   // extents and element strides of batch1 (inner) and batch0 (outer)
+};
 int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t outer_stride_elems,
-             int box_inner, int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)outer_stride_elems * 4};
-    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+             const BatchDims& bd, int box_inner, int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)bd.n1, (cuuint64_t)bd.n0};
+    // a size-1 dim never advances: give it any legal (16-byte multiple, non-zero) stride
+    const int64_t s_outer = outer > 1 ? outer_stride_elems : ((inner + 3) / 4 * 4);
+    const int64_t dflt = s_outer * (outer > 0 ? outer : 1);
+    cuuint64_t strides[3] = {(cuuint64_t)s_outer * 4, (cuuint64_t)(bd.n1 > 1 ? bd.s1 : dflt) * 4,
+                             (cuuint64_t)(bd.n0 > 1 ? bd.s0 : dflt * (bd.n1 > 0 ? bd.n1 : 1)) * 4};
+    cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -402,7 +419,7 @@ struct Plan {
     int bn, splits, tiles_m, tiles_n, kblocks, kper;
 };
 
-Plan choose_plan(int64_t M, int64_t N, int64_t K) {
+Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches) {
     const int sms = sm_count();
     const int kblocks = (int)((K + BK - 1) / BK);
     Plan best{};
@@ -411,9 +428,9 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K) {
     for (int bn : cands) {
         if (bn > 64 && N <= bn / 2) continue;            // mostly padding
         const int tm = (int)((M + BM - 1) / BM), tn = (int)((N + bn - 1) / bn);
-        const int tiles = tm * tn;
+        const int tiles = tm * tn * (int)batches;
         int splits = 1;
-        if (tiles < sms) {
+        if (tiles < sms && batches == 1) {
             splits = sms / tiles;
             const int max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;   // >= 8 k-blocks (256 of K) per split
             if (splits > max_splits) splits = max_splits;
@@ -432,6 +449,7 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K) {
         if (score > best_score) {
             best_score = score;
             best = Plan{bn, splits, tm, tn, kblocks, kper};
+            (void)tiles;
         }
     }
     return best;
@@ -443,11 +461,17 @@ namespace lg {
 
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c) {
     if (mode != LG_GEMM_TF32_TC || dtype != LG_F32) return 0;
-    if (d->batch0 * d->batch1 != 1) return 0;
+    const int64_t batches = d->batch0 * d->batch1;
+    if (batches < 1 || batches > 65535) return 0;
     if (d->M < 1 || d->N < 1 || d->K < 1) return 0;
+    // batch strides go into the TMA descriptor: 16-byte multiples, no broadcast (stride 0) over a real batch dim
+    const int64_t bs[6][2] = {{d->batch1, d->sa_b1}, {d->batch0, d->sa_b0}, {d->batch1, d->sb_b1},
+                              {d->batch0, d->sb_b0}, {d->batch1, d->sc_b1}, {d->batch0, d->sc_b0}};
+    for (auto& e : bs)
+        if (e[0] > 1 && (e[1] <= 0 || e[1] % 4 != 0)) return 0;
     if (d->M > 0x7fffffff || d->N > 0x7fffffff || d->K > 0x7fffffff) return 0;
     // tiny problems are launch bound either way; keep them on the exact path
-    if ((double)d->M * d->N * d->K < 64.0 * 64.0 * 64.0 * 8) return 0;
+    if ((double)d->M * d->N * d->K * (double)batches < 64.0 * 64.0 * 64.0 * 8) return 0;
     const bool a_ok = k_major(d->sa_m, d->sa_k, d->M) || mn_major(d->sa_m, d->sa_k, d->K);
     const bool b_ok = k_major(d->sb_n, d->sb_k, d->N) || mn_major(d->sb_n, d->sb_k, d->K);
     const bool c_ok = d->sc_n == 1 && (d->sc_m % 4 == 0 || d->M == 1);
@@ -463,17 +487,20 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     const bool a_mn = !k_major(d->sa_m, d->sa_k, M);
     const bool b_mn = !k_major(d->sb_n, d->sb_k, N);
     if (accumulate) return set_error("gemm_tc: accumulate is served by the SIMT kernel");
-    Plan pl = choose_plan(M, N, K);
+    const int64_t batches = d->batch0 * d->batch1;
+    Plan pl = choose_plan(M, N, K, batches);
     CUtensorMap ma, mb, mc;
     int rc;
+    const BatchDims ba{d->batch1, d->sa_b1, d->batch0, d->sa_b0}, bb{d->batch1, d->sb_b1, d->batch0, d->sb_b0},
+        bc{d->batch1, d->sc_b1, d->batch0, d->sc_b0};
     // operand maps: K-major -> (inner = K, outer = rows); MN-major -> (inner = rows, outer = K)
-    if (!a_mn) rc = make_map(&ma, a, K, M, d->sa_m, BK, BM);
-    else rc = make_map(&ma, a, M, K, d->sa_k, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (!a_mn) rc = make_map(&ma, a, K, M, d->sa_m, ba, BK, BM);
+    else rc = make_map(&ma, a, M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, BK, pl.bn);
-    else rc = make_map(&mb, b, N, K, d->sb_k, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, bb, BK, pl.bn);
+    else rc = make_map(&mb, b, N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_map(&mc, c, N, M, d->sc_m, 32, 32);
+    rc = make_map(&mc, c, N, M, d->sc_m, bc, 32, 32);
     if (rc) return rc;
     TcParams p;
     p.M = (int)M;
@@ -484,6 +511,8 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     p.splits = pl.splits;
     p.kblocks_per_split = pl.kper;
     p.kblocks_total = pl.kblocks;
+    p.batch1 = (int)d->batch1;
+    p.batches = (int)batches;
     p.bias = (const float*)bias;
     if (pl.splits > 1) {
         // split-K partials are summed by TMA reduce-add into a zeroed C
@@ -493,7 +522,9 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
             LG_CUDA(cudaMemset2DAsync(c, (size_t)d->sc_m * 4, 0, (size_t)N * 4, (size_t)M, stream()));
         }
     }
-    const int items = pl.tiles_m * pl.tiles_n * pl.splits;
+    const int64_t items64 = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits * batches;
+    LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
+    const int items = (int)items64;
     const int grid = items < sm_count() ? items : sm_count();
     switch (pl.bn) {
         case 256: return launch_bn<256>(a_mn, b_mn, ma, mb, mc, p, grid);

@@ -9,6 +9,7 @@
 #include <vector>
 #include <atomic>
 #include <string.h>
+#include <cuda_profiler_api.h>
 
 namespace lg {
 
@@ -283,5 +284,13 @@ int lg_launch_count(uint64_t* n) {
 }
 
 void* lg_stream_handle(void) { return (void*)g_stream; }
+
+int lg_profiler_range(int start) {
+    LG_INIT();
+    LG_CUDA(cudaStreamSynchronize(g_stream));
+    if (start) LG_CUDA(cudaProfilerStart());
+    else LG_CUDA(cudaProfilerStop());
+    return 0;
+}
 
 }  // extern "C"

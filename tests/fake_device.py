@@ -97,6 +97,7 @@ class FakeDevice(object):
     def init(self, device): pass
     def sync(self): pass
     def empty_cache(self): pass
+    def profiler_range(self, start): pass
 
     def alloc(self, nbytes, ref):
         buf = np.zeros(int(nbytes) + 64, dtype=np.uint8)
