@@ -156,6 +156,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='override the global batch')
     ap.add_argument('--layers', type=int, default=0, help='debug only: fewer layers (marks the line invalid)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='dispatch every op from python every step (no CUDA graph replay)')
     ap.add_argument('--cpu-sample-batch', type=int, default=0, help='oracle sample batch (default 8 for --impl reference, 4 for the cpu_baseline leg)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -215,9 +216,30 @@ def main():
         rt.synchronize()
         comm.barrier()
 
-    # ---- phase A: inputs resident in HBM
-    for _ in range(W):
+    # ---- eager reference point: python dispatch of every op, every step
+    for _ in range(2):
         loss = step(ids_d, lab_d)
+    barrier()
+    ee0 = rt.Event().record()
+    for _ in range(3):
+        step(ids_d, lab_d)
+    ee1 = rt.Event().record()
+    ee1.synchronize()
+    eager_ms = ee0.elapsed_ms(ee1) / 3
+
+    # ---- the step is static-shape: record it once into a CUDA graph, replay it without python dispatch
+    if args.eager:
+        run_step = lambda: step(ids_d, lab_d)  # noqa: E731
+        for _ in range(W):
+            run_step()
+    else:
+        from lightgrad_b200.autograd.cuda.graph import StepGraph
+        sg = StepGraph(lambda: step(ids_d, lab_d), warmup=0)
+        run_step = sg.replay
+        for _ in range(W):
+            run_step()
+
+    # ---- phase A: inputs resident in HBM
     barrier()
     sampler = ClockSampler(int(os.environ.get('LOCAL_RANK', '0')))
     if rank == 0:
@@ -225,7 +247,7 @@ def main():
     n0 = rt.launch_count()
     e0 = rt.Event().record()
     for _ in range(args.steps):
-        loss = step(ids_d, lab_d)
+        loss = run_step()
     e1 = rt.Event().record()
     e1.synchronize()
     n1 = rt.launch_count()
@@ -243,7 +265,7 @@ def main():
     for _ in range(k_b):
         rt.api.memcpy_h2d(ids_d.ptr, pin_ids.ptr, ids_np.nbytes)
         rt.api.memcpy_h2d(lab_d.ptr, pin_lab.ptr, labels_np.nbytes)
-        loss_host = step(ids_d, lab_d).item()
+        loss_host = run_step().item()
     e3 = rt.Event().record()
     e3.synchronize()
     barrier()
@@ -284,6 +306,8 @@ def main():
         'scaling': 'weak' if args.gpus == 1 else 'strong', 'vs_baseline': None,
         'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'bf16': 'bf16'}[mode], 'data': 'synthetic', 'config': config,
         'loss': round(final_loss, 5),
+        'execution': 'eager python dispatch' if args.eager else 'whole step captured once into a CUDA graph, replayed per step',
+        'eager_ms_per_step': round(eager_ms, 3),
         'e2e': {'value': round(e2e, 2), 'unit': 'samples/s', 'h2d_bytes_per_step': int(ids_np.nbytes + labels_np.nbytes),
                 'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_b, 3), 'steps': k_b, 'last_loss': round(float(loss_host), 5)},
         'gpu_launches': int(n1 - n0), 'gpu_launches_per_step': round((n1 - n0) / args.steps, 1),

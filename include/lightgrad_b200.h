@@ -120,7 +120,16 @@ int lg_event_elapsed_ms(void* start, void* stop, float* ms);
 int lg_event_destroy(void* ev);
 int lg_launch_count(uint64_t* n);         /* kernels launched by this library so far */
 void* lg_stream_handle(void);             /* cudaStream_t of the compute stream, for profilers */
-int lg_profiler_range(int start);         /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
+int lg_profiler_range(int start);
+/* whole-step CUDA graphs: everything enqueued between begin and end (kernels, memsets, NCCL calls)
+ * is recorded instead of executed; allocations made meanwhile come from a pool private to the
+ * graph (*pool_id: 0 = create one, reused by later re-captures).  lg_graph_launch replays the step
+ * with no host-side dispatch.  Host copies and synchronisation are rejected during capture. */
+int lg_graph_begin(int* pool_id);
+int lg_graph_end(void** graph_exec, uint64_t* n_nodes);
+int lg_graph_abort(void);
+int lg_graph_launch(void* graph_exec, uint64_t n_kernels /* added to lg_launch_count */);
+int lg_graph_destroy(void* graph_exec);         /* cudaProfilerStart/Stop (ncu --profile-from-start off) */
 
 /* ---- elementwise (replaces kernels.atom) --------------------------------------------------- */
 /* all operands contiguous, n elements, same dtype; b/c may be NULL for 1/2-input ops */
@@ -200,11 +209,12 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
 
 /* ---- optimizers (replaces the per-parameter python loops of optim.py) ----------------------- */
 /* all tensors of one optimizer live in flat fp32 arenas; `seg_end_dev[i]` (device, int64) is the
- * exclusive end offset of tensor i.  Tensor i uses step count t = t0 + i + 1 in its bias
- * corrections 1 - beta^t (the reference advances t once per parameter, optim.py:36-37).        */
+ * exclusive end offset of tensor i.  Tensor i uses step count t = *t_dev + i + 1 in its bias
+ * corrections 1 - beta^t (the reference advances t once per parameter, optim.py:36-37); the counter
+ * lives on the device so that a captured step stays correct when replayed.                       */
 int lg_sgd_step(void* param, const void* grad, void* delta, int64_t n, double lr, double momentum);
 int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, int64_t n,
-                 int n_seg, const int64_t* seg_end_dev, int64_t t0,
+                 int n_seg, const int64_t* seg_end_dev, int64_t* t_dev /* device counter, advanced by n_seg */,
                  double lr, double beta1, double beta2, double eps);
 
 /* ---- collectives (new; NCCL over NVLink, one process per GPU) ------------------------------- */

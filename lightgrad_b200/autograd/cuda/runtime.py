@@ -61,6 +61,11 @@ _SIGNATURES = {
     'lg_event_destroy': [_vp],
     'lg_launch_count': [C.POINTER(C.c_uint64)],
     'lg_profiler_range': [C.c_int],
+    'lg_graph_begin': [C.POINTER(C.c_int)],
+    'lg_graph_end': [C.POINTER(_vp), C.POINTER(C.c_uint64)],
+    'lg_graph_abort': [],
+    'lg_graph_launch': [_vp, C.c_uint64],
+    'lg_graph_destroy': [_vp],
     'lg_ew_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_double],
     'lg_ew': [C.c_int, C.c_int, C.c_int, _i64p, _vp, _i64p, _vp, _i64p, _vp, _i64p, _vp, _i64p, C.c_double],
     'lg_ew_bwd2_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64],
@@ -81,7 +86,7 @@ _SIGNATURES = {
     'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
-    'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int64,
+    'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp,
                      C.c_double, C.c_double, C.c_double, C.c_double],
     'lg_nccl_unique_id': [_vp],
     'lg_nccl_init': [_vp, C.c_int, C.c_int],

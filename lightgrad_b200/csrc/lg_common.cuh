@@ -16,6 +16,7 @@ cudaStream_t comm_stream();   // collective stream
 int sm_count();
 void count_launch(int n = 1);
 int ensure_init();
+bool capturing();     // a whole-step CUDA graph capture is in progress on the compute stream
 
 #define LG_CUDA(expr)                                                                         \
     do {                                                                                      \

@@ -39,15 +39,18 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
     }
 }
 
-// per-tensor bias corrections 1 - beta^t with t = t0 + i + 1, evaluated in double like python does
-__global__ void adam_prep_kernel(int n_seg, int64_t t0, double b1, double b2, float* __restrict__ c1,
-                                 float* __restrict__ c2) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_seg) {
+// per-tensor bias corrections 1 - beta^t with t = *t_dev + i + 1, evaluated in double like python does;
+// one CTA, so the counter can be advanced after every thread has read it
+__global__ void adam_prep_kernel(int n_seg, int64_t* __restrict__ t_dev, double b1, double b2,
+                                 float* __restrict__ c1, float* __restrict__ c2) {
+    const int64_t t0 = *t_dev;
+    for (int i = threadIdx.x; i < n_seg; i += blockDim.x) {
         const double t = (double)(t0 + i + 1);
         c1[i] = (float)(1.0 - pow(b1, t));
         c2[i] = (float)(1.0 - pow(b2, t));
     }
+    __syncthreads();
+    if (threadIdx.x == 0) *t_dev = t0 + n_seg;
 }
 
 // arenas are padded so that every tensor starts on a 64-element boundary: a float4 never straddles tensors
@@ -105,7 +108,7 @@ int lg_sgd_step(void* param, const void* grad, void* delta, int64_t n, double lr
 }
 
 int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, int64_t n, int n_seg,
-                 const int64_t* seg_end_dev, int64_t t0, double lr, double beta1, double beta2, double eps) {
+                 const int64_t* seg_end_dev, int64_t* t_dev, double lr, double beta1, double beta2, double eps) {
     LG_INIT();
     if (n == 0) return 0;
     LG_REQUIRE(n_seg >= 1, "lg_adam_step: need at least one segment");
@@ -115,7 +118,7 @@ int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, in
     if (!corr) return 1;
     float* seg_c1_dev = corr;
     float* seg_c2_dev = corr + n_seg;
-    adam_prep_kernel<<<(n_seg + 127) / 128, 128, 0, stream()>>>(n_seg, t0, beta1, beta2, seg_c1_dev, seg_c2_dev);
+    adam_prep_kernel<<<1, 256, 0, stream()>>>(n_seg, t_dev, beta1, beta2, seg_c1_dev, seg_c2_dev);
     count_launch();
     int grid = grid_for(n / 4, 256, 8);
     float b1 = (float)beta1, b2 = (float)beta2;

@@ -35,11 +35,16 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 // Size-class free lists; a freed block is immediately reusable because every consumer runs on the
 // one compute stream (stream order == program order).  The comm stream only touches long-lived
 // arenas and is joined by events before those could be released.
+// Pools: pool 0 serves eager work.  While a step is being captured into a CUDA graph the allocator
+// switches to a pool private to that graph; its blocks are baked into the graph as raw addresses, so
+// they may only ever be recycled among that graph's own captures (never handed to eager tensors).
 struct Cache {
     std::mutex mu;
-    std::unordered_map<void*, size_t> live;              // ptr -> class size
-    std::map<size_t, std::vector<void*>> free_lists;     // class size -> blocks
+    struct Block { size_t cls; int pool; };
+    std::unordered_map<void*, Block> live;                              // ptr -> class size, pool
+    std::map<int, std::map<size_t, std::vector<void*>>> pools;         // pool -> class size -> free blocks
     size_t in_use = 0, reserved = 0, peak = 0;
+    int cur_pool = 0, next_pool = 0;
 
     static size_t size_class(size_t n) {
         if (n < 512) return 512;
@@ -51,6 +56,8 @@ struct Cache {
         return (n + step - 1) / step * step;
     }
     void release_all() {
+        // only the eager pool is trimmed: graph pools hold addresses that instantiated graphs still use
+        auto& free_lists = pools[0];
         for (auto& kv : free_lists) {
             for (void* p : kv.second) {
                 cudaFree(p);
@@ -63,6 +70,7 @@ struct Cache {
         size_t cls = size_class(n);
         std::lock_guard<std::mutex> lk(mu);
         void* p = nullptr;
+        auto& free_lists = pools[cur_pool];
         auto it = free_lists.find(cls);
         if (it != free_lists.end() && !it->second.empty()) {
             p = it->second.back();
@@ -83,7 +91,7 @@ struct Cache {
             }
             reserved += cls;
         }
-        live[p] = cls;
+        live[p] = Block{cls, cur_pool};
         in_use += cls;
         if (in_use > peak) peak = in_use;
         return p;
@@ -92,14 +100,17 @@ struct Cache {
         std::lock_guard<std::mutex> lk(mu);
         auto it = live.find(p);
         if (it == live.end()) return set_error("lg_free: unknown pointer %p", p);
-        size_t cls = it->second;
+        size_t cls = it->second.cls;
+        int pool = it->second.pool;
         live.erase(it);
         in_use -= cls;
-        free_lists[cls].push_back(p);
+        pools[pool][cls].push_back(p);
         return 0;
     }
 };
 static Cache* g_cache = nullptr;
+static bool g_capturing = false;
+bool capturing() { return g_capturing; }
 
 void* tmp_alloc(size_t nbytes) { return g_cache->get(nbytes ? nbytes : 1); }
 void tmp_free(void* p) {
@@ -180,6 +191,7 @@ int lg_device_props(int* sm_count_, int* cc_major, int* cc_minor, size_t* total_
 
 int lg_sync(void) {
     LG_INIT();
+    LG_REQUIRE(!g_capturing, "lg_sync: cannot synchronise while a step is being captured into a CUDA graph");
     LG_CUDA(cudaStreamSynchronize(g_stream));
     LG_CUDA(cudaStreamSynchronize(g_comm));
     return 0;
@@ -218,12 +230,16 @@ int lg_mem_stats(size_t* in_use, size_t* reserved, size_t* peak_in_use) {
 int lg_memcpy_h2d(void* dst, const void* src, size_t nbytes) {
     LG_INIT();
     if (nbytes == 0) return 0;
+    LG_REQUIRE(!g_capturing, "lg_memcpy_h2d: host copies cannot be captured into a CUDA graph; stage inputs in "
+                             "device tensors before capture and refresh them between replays");
     LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, g_stream));
     return 0;
 }
 
 int lg_memcpy_d2h(void* dst, const void* src, size_t nbytes) {
     LG_INIT();
+    LG_REQUIRE(!g_capturing, "lg_memcpy_d2h: reading a tensor back (numpy()/item()) is not possible while a step is "
+                             "being captured into a CUDA graph");
     if (nbytes) LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
     LG_CUDA(cudaStreamSynchronize(g_stream));
     return 0;
@@ -284,6 +300,72 @@ int lg_launch_count(uint64_t* n) {
 }
 
 void* lg_stream_handle(void) { return (void*)g_stream; }
+
+// ---- whole-step CUDA graphs ----------------------------------------------------------------------
+int lg_graph_begin(int* pool_id) {
+    LG_INIT();
+    LG_REQUIRE(!g_capturing, "lg_graph_begin: a capture is already in progress");
+    LG_CUDA(cudaStreamSynchronize(g_stream));
+    {
+        std::lock_guard<std::mutex> lk(g_cache->mu);
+        if (*pool_id <= 0) *pool_id = ++g_cache->next_pool;
+        g_cache->cur_pool = *pool_id;
+    }
+    cudaError_t e = cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) {
+        g_cache->cur_pool = 0;
+        return set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(e));
+    }
+    g_capturing = true;
+    return 0;
+}
+
+int lg_graph_end(void** graph_exec, uint64_t* n_nodes) {
+    LG_REQUIRE(g_capturing, "lg_graph_end: no capture in progress");
+    g_capturing = false;
+    {
+        std::lock_guard<std::mutex> lk(g_cache->mu);
+        g_cache->cur_pool = 0;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+    if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        return set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    }
+    size_t nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nodes);
+    *n_nodes = nodes;
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    *graph_exec = (void*)exec;
+    return 0;
+}
+
+int lg_graph_abort(void) {
+    if (!g_capturing) return 0;
+    g_capturing = false;
+    g_cache->cur_pool = 0;
+    cudaGraph_t graph = nullptr;
+    cudaStreamEndCapture(g_stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return 0;
+}
+
+int lg_graph_launch(void* graph_exec, uint64_t n_kernels) {
+    LG_REQUIRE(!g_capturing, "lg_graph_launch: cannot replay during a capture");
+    LG_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, g_stream));
+    count_launch((int)n_kernels);
+    return 0;
+}
+
+int lg_graph_destroy(void* graph_exec) {
+    if (graph_exec) LG_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return 0;
+}
 
 int lg_profiler_range(int start) {
     LG_INIT();

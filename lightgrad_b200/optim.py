@@ -175,11 +175,15 @@ class Adam(Optimizer):
         P = len(self.parameters)
         if self._m is None:
             self._m, self._v = a.state(), a.state()
+            # the step counter lives on the device (and is advanced there) so that a step captured into
+            # a CUDA graph keeps counting when it is replayed
+            self._t_dev = a.T.from_numpy(np.array([self.t], dtype=np.int64), requires_grad=False)
         seg = a.segments(self.parameters)
-        # parameter i uses t = self.t + i + 1 (the reference bumps t once per parameter); the kernel
+        # parameter i uses t = t_dev + i + 1 (the reference bumps t once per parameter); the kernel
         # derives the two bias corrections from t itself, so nothing is uploaded per step
         a.rt.api.adam_step(self._belief, a.param_buf.ptr, a.grad_buf.ptr, self._m.ptr, self._v.ptr, a.total,
-                           P, seg.ptr, int(self.t), float(self.lr), float(self.b1), float(self.b2), float(self.eps))
+                           P, seg.ptr, self._t_dev.ptr, float(self.lr), float(self.b1), float(self.b2),
+                           float(self.eps))
         self.t += P
 
 

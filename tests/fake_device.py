@@ -99,6 +99,13 @@ class FakeDevice(object):
     def empty_cache(self): pass
     def profiler_range(self, start): pass
 
+    # graphs: the double executes eagerly while 'capturing' and re-runs the recorded python thunk on replay
+    def graph_begin(self, pool): pool._obj.value = 1
+    def graph_end(self, exec_ref, n_ref): exec_ref._obj.value, n_ref._obj.value = 1, 0
+    def graph_abort(self): pass
+    def graph_launch(self, h, n): raise RuntimeError('the fake device cannot replay graphs')
+    def graph_destroy(self, h): pass
+
     def alloc(self, nbytes, ref):
         buf = np.zeros(int(nbytes) + 64, dtype=np.uint8)
         addr = (buf.ctypes.data + 63) // 64 * 64
@@ -293,8 +300,11 @@ class FakeDevice(object):
             D[...] = delta
         P[...] += delta
 
-    def adam_step(self, belief, p, g, m, v, n, n_seg, seg_end, t0, lr, b1, b2, eps):
+    def adam_step(self, belief, p, g, m, v, n, n_seg, seg_end, t_dev, lr, b1, b2, eps):
         self.launches += 1
+        tcount = _arr(t_dev, rt.I64, [1])
+        t0 = int(tcount[0])
+        tcount[0] = t0 + n_seg
         P, G, M, V = (_arr(q, rt.F32, [n]) for q in (p, g, m, v))
         ends = _arr(seg_end, rt.I64, [n_seg])
         seg = np.searchsorted(ends, np.arange(n), side='right')
