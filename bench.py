@@ -285,9 +285,7 @@ def main():
     rt.gemm_profile(False)
     step_ms_c = e4.elapsed_ms(e5) / k_c
     if rank != 0:
-        if dp is not None:
-            dp.close()
-        return
+        finish(comm)
 
     peaks = load_peaks()
     value = global_batch / (ms_a / 1e3)
@@ -326,8 +324,19 @@ def main():
         res = cpu_reference_leg(2, 1, args.cpu_sample_batch or 4, budget_s=90.0)
         line['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line), flush=True)
-    if dp is not None:
-        dp.close()
+    finish(comm)
+
+
+def finish(comm):
+    """Leave without running destructors: a NCCL communicator that was captured into a CUDA graph must not
+    be torn down rank by rank (ncclCommDestroy can wait for peers that have already gone)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        comm.barrier()
+    except Exception:
+        pass
+    os._exit(0)
 
 
 if __name__ == '__main__':

@@ -24,27 +24,38 @@ except Exception:
 
 
 def time_gpu(fn, iters, warmup=3, flush=None):
+    """Average device time of fn(): `iters` launches queued back to back between two CUDA events on the
+    compute stream (so host dispatch latency is not measured).  When `flush` is given it is queued before
+    every launch (evicts L2) and its own time, measured the same way, is subtracted."""
     from lightgrad_b200.autograd.cuda import runtime as rt
-    for _ in range(warmup):
-        fn()
-    rt.synchronize()
-    total = 0.0
-    for _ in range(iters):
-        if flush is not None:
-            flush()
+
+    def span(body):
+        rt.synchronize()
         e0 = rt.Event().record()
-        fn()
+        for _ in range(iters):
+            body()
         e1 = rt.Event().record()
         e1.synchronize()
-        total += e0.elapsed_ms(e1)
-    return total / iters
+        return e0.elapsed_ms(e1)
+    for _ in range(warmup):
+        fn()
+    if flush is None:
+        return span(fn) / iters
+    for _ in range(2):
+        flush()
+    t_flush = span(flush)
+
+    def both():
+        flush()
+        fn()
+    return max(span(both) - t_flush, 1e-6) / iters
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--suite', default='ew,reduce,gemm')
     ap.add_argument('--max-log2', type=int, default=28)
-    ap.add_argument('--min-log2', type=int, default=20)
+    ap.add_argument('--min-log2', type=int, default=10)
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--cpu', action='store_true')
     ap.add_argument('--modes', default='fp32')
