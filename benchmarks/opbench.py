@@ -145,5 +145,116 @@ def main():
             ops.set_matmul_mode('fp32')
 
 
+    if 'gemm_bwd' in suites:
+        # BASELINE config 3: forward + both backward GEMMs (dA = dC.B^T, dB = A^T.dC), 6*M*N*K flops
+        shapes = [(s_, s_, s_) for s_ in (1024, 2048, 4096)] + [(4096, 768, 768), (4096, 3072, 768), (4096, 768, 3072)]
+        for mode in args.modes.split(','):
+            ops.set_matmul_mode(mode)
+            for (M, N, K) in shapes:
+                a = T.from_numpy(rs.uniform(-1, 1, (M, K)).astype(np.float32))
+                b = T.from_numpy(rs.uniform(-1, 1, (K, N)).astype(np.float32))
+                g = T.from_numpy(rs.uniform(-1, 1, (M, N)).astype(np.float32))
+
+                def fwd_bwd():
+                    with light.no_grad():
+                        ops._gemm(a, b)
+                        ops._gemm(g, ops._swap_last(b))
+                        ops._gemm(ops._swap_last(a), g)
+                ms = time_gpu(fwd_bwd, max(3, args.iters // 2))
+                tf = 6.0 * M * N * K / ms / 1e9
+                peak = 74.0 if mode == 'fp32' else PEAKS['bf16_tflops'] / 2
+                emit(suite='gemm_bwd', mode=mode, M=M, N=N, K=K, ms=round(ms, 4), tflops=round(tf, 2),
+                     frac_of_peak=round(tf / peak, 3), peak_tflops=peak, flops='6*M*N*K')
+                if args.cpu and mode == args.modes.split(',')[0]:
+                    an, bn, gn = a.numpy(), b.numpy(), g.numpy()
+                    t0 = time.perf_counter(); an @ bn; gn @ bn.T; an.T @ gn; dt = time.perf_counter() - t0
+                    emit(suite='gemm_bwd', impl='cpu-openblas', M=M, N=N, K=K, ms=round(dt * 1e3, 2),
+                         tflops=round(6.0 * M * N * K / dt / 1e12, 3), cores=os.cpu_count())
+                del a, b, g
+        ops.set_matmul_mode('fp32')
+
+    if 'bwd' in suites:
+        # reduction / unary backward passes of BASELINE config 2 (through the autograd API, incl. the walk)
+        for lg in range(max(args.min_log2, 20), args.max_log2 + 1, 2):
+            n = 1 << lg
+            side = 1 << (lg // 2)
+            x = T.from_numpy(rs.uniform(-1, 1, (side, n // side)).astype(np.float32))
+            for name, bpe in (('sum', 4), ('max', 8), ('exp', 12), ('relu', 12)):
+                y = getattr(x, name)()
+                gy = T.ones(y.shape, requires_grad=False)
+
+                def bwd():
+                    with light.no_grad():
+                        return y.ctx.backward(gy)
+                ms = time_gpu(bwd, args.iters)
+                if name == 'sum':
+                    # the backward of sum is a zero-stride view; the bytes move when it is accumulated
+                    def bwd():  # noqa: F811
+                        with light.no_grad():
+                            return y.ctx.backward(gy).copy()
+                    ms = time_gpu(bwd, args.iters)
+                emit(suite='bwd', op=name + '_bwd', log2n=lg, ms=round(ms, 5), bytes_per_elem=bpe,
+                     gbs=round(bpe * n / ms / 1e6, 1), frac_of_measured_hbm=round(bpe * n / ms / 1e6 / PEAKS['hbm_gbs'], 3))
+            del x
+
+    if 'mnist' in suites:
+        # BASELINE config 1: MLP 784-128-10, batch 64, mse + SGD(lr=1e-4): launch-latency bound
+        import lightgrad_b200.nn as nn
+        from examples import mnist as mn
+        from lightgrad_b200.autograd.cuda.graph import StepGraph
+        np.random.seed(0)
+        model = mn.NN()
+        opt = light.optim.SGD(model.parameters(), lr=1e-4)
+        xb, yb = mn.synthetic_batch(64, seed=0)
+        xd, yd = T.from_numpy(xb, requires_grad=False), T.from_numpy(yb, requires_grad=False)
+        one_hot = T.zeros((64, 10), requires_grad=False)
+        one_hot[range(64), yd] = 1
+
+        def step():
+            y = model(xd)
+            loss = light.loss.mse(y, one_hot)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(5):
+            step()
+        rt.synchronize()
+        n0 = rt.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            step()
+        rt.synchronize()
+        dt = (time.perf_counter() - t0) / 200
+        emit(suite='mnist', impl='cuda-eager', ms_per_step=round(dt * 1e3, 4), samples_per_s=round(64 / dt, 1),
+             launches_per_step=(rt.launch_count() - n0) / 200)
+        sg = StepGraph(step, warmup=0)
+        for _ in range(5):
+            sg.replay()
+        rt.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(1000):
+            sg.replay()
+        rt.synchronize()
+        dt = (time.perf_counter() - t0) / 1000
+        emit(suite='mnist', impl='cuda-graph', ms_per_step=round(dt * 1e3, 4), samples_per_s=round(64 / dt, 1),
+             kernels_per_step=sg.n_kernels)
+        if args.cpu:
+            from oracle import CpuTensor
+            with nn.use_tensor(CpuTensor):
+                np.random.seed(0)
+                cm = mn.NN()
+            copt = light.optim.SGD(cm.parameters(), lr=1e-4)
+            cx, cy = CpuTensor.from_numpy(xb, requires_grad=False), CpuTensor.from_numpy(yb, requires_grad=False)
+            for _ in range(5):
+                mn.train_step(cm, copt, cx, cy, CpuTensor)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                mn.train_step(cm, copt, cx, cy, CpuTensor)
+            dt = (time.perf_counter() - t0) / 200
+            emit(suite='mnist', impl='cpu-oracle', ms_per_step=round(dt * 1e3, 4), samples_per_s=round(64 / dt, 1),
+                 cores=os.cpu_count())
+
+
 if __name__ == '__main__':
     main()

@@ -152,6 +152,10 @@ int lg_cast(int src_dtype, int dst_dtype, int ndim, const int64_t* shape,
 /* x is a contiguous (outer, reduce, inner) block; out is (outer, inner); out = scale * reduce(x) */
 int lg_reduce(int op, int dtype, const void* x, void* out,
               int64_t outer, int64_t reduce, int64_t inner, double scale);
+/* same with rows `ld` elements apart (ld >= inner > 1): element (o, r, c) at x[(o*reduce + r)*ld + c].
+ * Lets a column reduction read a GEMM result whose leading dimension was padded for TMA. */
+int lg_reduce_pitched(int op, int dtype, const void* x, void* out,
+                      int64_t outer, int64_t reduce, int64_t inner, int64_t ld, double scale);
 
 /* ---- matmul (replaces kernels.dot) ---------------------------------------------------------- */
 /* C[b0,b1] (M x N) = A[b0,b1] (M x K) * B[b0,b1] (K x N) (+ bias[N] if bias != NULL)

@@ -530,6 +530,16 @@ def _reduce(op, x, axes, keepdims, scale=1.0):
     full_shape = x._shape
     if x._numel == 0:
         raise ValueError("zero-size array to reduction operation")
+    if not x._contig and nd >= 2 and axes == tuple(range(nd - 1)) and x._strides[-1] == 1:
+        # rows with a padded pitch (a GEMM result written for TMA alignment) reduced over all leading dims:
+        # the column-reduce kernel reads them in place
+        rows = _prod(full_shape[:-1])
+        st = _reshape_strides(full_shape, x._strides, (rows, full_shape[-1]))
+        if st is not None and st[1] == 1 and st[0] >= full_shape[-1]:
+            kshape = (1,) * (nd - 1) + (full_shape[-1],)
+            out = CudaTensor._new(kshape if keepdims else (full_shape[-1],), x._dtype)
+            rt.api.reduce_pitched(op, x._code, x.ptr, out.ptr, 1, rows, full_shape[-1], st[0], scale)
+            return out
     cur = x.contiguous()
     shape = list(full_shape)
     # group adjacent axes, reduce from the last group to the first so earlier dims keep their place

@@ -115,15 +115,25 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, in
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const T* p = x + row * ld;
         T m = -INFINITY, s = T(0);
-        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
-            T v = p[j];
+        auto feed = [&](T v) {
             if (v > m) {
                 s = s * f_exp(m - v) + T(1);
                 m = v;
             } else {
                 s += f_exp(v - m);
             }
+        };
+        constexpr int V = 16 / sizeof(T);
+        int64_t nv = 0;
+        if (((uintptr_t)p & 15) == 0) {
+            nv = cols / V;
+            for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
+                Vec<T, V> w = reinterpret_cast<const Vec<T, V>*>(p)[j];
+#pragma unroll
+                for (int k = 0; k < V; ++k) feed(w.v[k]);
+            }
         }
+        for (int64_t j = nv * V + threadIdx.x; j < cols; j += blockDim.x) feed(p[j]);
         T gm = block_max(m, sm);
         T part = (m == -INFINITY) ? T(0) : s * f_exp(m - gm);
         T gs = block_sum(part, sm);
@@ -150,7 +160,22 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, in
         const T l = lse[row];
         int64_t lab = (int64_t)labels[row];
         if (lab < 0) lab += cols;
-        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+        constexpr int V = 16 / sizeof(T);
+        int64_t nv = 0;
+        if ((((uintptr_t)p | (uintptr_t)q) & 15) == 0) {
+            nv = cols / V;
+            for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
+                Vec<T, V> w = reinterpret_cast<const Vec<T, V>*>(p)[j], o;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    T pr = f_exp(w.v[k] - l);
+                    if (j * V + k == lab) pr -= T(1);
+                    o.v[k] = pr / inv_rows * gs;
+                }
+                reinterpret_cast<Vec<T, V>*>(q)[j] = o;
+            }
+        }
+        for (int64_t j = nv * V + threadIdx.x; j < cols; j += blockDim.x) {
             T pr = f_exp(p[j] - l);
             if (j == lab) pr -= T(1);
             q[j] = pr / inv_rows * gs;   // (p - onehot) / N * out_grad, as loss.py:20-24
@@ -237,6 +262,162 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
         dgamma_part[(int64_t)blockIdx.x * cols + j] = sg[j];
         dbeta_part[(int64_t)blockIdx.x * cols + j] = sb[j];
     }
+}
+
+// ---- float32 fast path: one warp per row, the row lives in registers (NV float4 per lane), 128-bit accesses.
+// Valid for cols % 4 == 0 and cols <= NV*128 (BERT: 768 -> NV = 6).
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ y,
+                                                         float* __restrict__ mean, float* __restrict__ rstd,
+                                                         int64_t rows, int cols, float eps) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inv = 1.0f / (float)cols;
+    const int nchunks = cols >> 2;
+    float4 gm[NV], bt[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nchunks) {
+            gm[j] = reinterpret_cast<const float4*>(gamma)[c];
+            bt[j] = reinterpret_cast<const float4*>(beta)[c];
+        }
+    }
+    for (; row < rows; row += row_step) {
+        const float4* p = reinterpret_cast<const float4*>(x + row * cols);
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                v[j] = p[c];
+                s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            }
+        }
+        const float mu = warp_sum(s) * inv;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
+                q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+            }
+        }
+        const float var = warp_sum(q) * inv;
+        const float rs = 1.0f / sqrtf(var + eps);
+        float4* o = reinterpret_cast<float4*>(y + row * cols);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                float4 r;
+                r.x = v[j].x * rs * gm[j].x + bt[j].x;
+                r.y = v[j].y * rs * gm[j].y + bt[j].y;
+                r.z = v[j].z * rs * gm[j].z + bt[j].z;
+                r.w = v[j].w * rs * gm[j].w + bt[j].w;
+                o[c] = r;
+            }
+        }
+        if (lane == 0) {
+            mean[row] = mu;
+            rstd[row] = rs;
+        }
+    }
+}
+
+// dx per row; dgamma / dbeta accumulate in registers over the rows a warp owns, are combined per CTA in
+// shared memory and written as one partial row per CTA ([gridDim.x, cols], reduced afterwards).
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd, const float* __restrict__ g,
+                                                         float* __restrict__ dx, float* __restrict__ dgamma_part,
+                                                         float* __restrict__ dbeta_part, int64_t rows, int cols) {
+    extern __shared__ unsigned char smem_raw[];
+    float* sg = reinterpret_cast<float*>(smem_raw);
+    float* sb = sg + cols;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        sg[j] = 0.f;
+        sb[j] = 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inv = 1.0f / (float)cols;
+    const int nchunks = cols >> 2;
+    float4 gm[NV], ag[NV], ab[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = lane + 32 * j;
+        ag[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nchunks) gm[j] = reinterpret_cast<const float4*>(gamma)[c];
+    }
+    for (; row < rows; row += row_step) {
+        const float4* px = reinterpret_cast<const float4*>(x + row * cols);
+        const float4* pg = reinterpret_cast<const float4*>(g + row * cols);
+        const float mu = mean[row], rs = rstd[row];
+        float4 xh[NV], gv[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                float4 xv = px[c];
+                gv[j] = pg[c];
+                xh[j].x = (xv.x - mu) * rs; xh[j].y = (xv.y - mu) * rs;
+                xh[j].z = (xv.z - mu) * rs; xh[j].w = (xv.w - mu) * rs;
+                const float d0 = gv[j].x * gm[j].x, d1 = gv[j].y * gm[j].y, d2 = gv[j].z * gm[j].z,
+                            d3 = gv[j].w * gm[j].w;
+                s1 += (d0 + d1) + (d2 + d3);
+                s2 += (d0 * xh[j].x + d1 * xh[j].y) + (d2 * xh[j].z + d3 * xh[j].w);
+            }
+        }
+        s1 = warp_sum(s1) * inv;
+        s2 = warp_sum(s2) * inv;
+        float4* pd = reinterpret_cast<float4*>(dx + row * cols);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                float4 r;
+                r.x = rs * (gv[j].x * gm[j].x - s1 - xh[j].x * s2);
+                r.y = rs * (gv[j].y * gm[j].y - s1 - xh[j].y * s2);
+                r.z = rs * (gv[j].z * gm[j].z - s1 - xh[j].z * s2);
+                r.w = rs * (gv[j].w * gm[j].w - s1 - xh[j].w * s2);
+                pd[c] = r;
+                ag[j].x += gv[j].x * xh[j].x; ag[j].y += gv[j].y * xh[j].y;
+                ag[j].z += gv[j].z * xh[j].z; ag[j].w += gv[j].w * xh[j].w;
+                ab[j].x += gv[j].x; ab[j].y += gv[j].y; ab[j].z += gv[j].z; ab[j].w += gv[j].w;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nchunks) {
+            atomicAdd(&sg[4 * c + 0], ag[j].x); atomicAdd(&sg[4 * c + 1], ag[j].y);
+            atomicAdd(&sg[4 * c + 2], ag[j].z); atomicAdd(&sg[4 * c + 3], ag[j].w);
+            atomicAdd(&sb[4 * c + 0], ab[j].x); atomicAdd(&sb[4 * c + 1], ab[j].y);
+            atomicAdd(&sb[4 * c + 2], ab[j].z); atomicAdd(&sb[4 * c + 3], ab[j].w);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        dgamma_part[(int64_t)blockIdx.x * cols + j] = sg[j];
+        dbeta_part[(int64_t)blockIdx.x * cols + j] = sb[j];
+    }
+}
+
+inline int ln_nv(int64_t cols) {
+    if (cols % 4 != 0 || cols > 1024) return 0;
+    const int need = (int)((cols / 4 + 31) / 32);
+    return need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 6 ? 6 : 8));
 }
 
 template <typename T>
@@ -347,6 +528,18 @@ int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* be
     if (rows * cols == 0) return 0;
     int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
     int grid = (int)(blocks < cap ? blocks : cap);
+    const int nv = ln_nv(cols);
+    if (dtype == LG_F32 && nv && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta)) {
+        int64_t cap2 = (int64_t)sm_count() * 4;
+        int g2 = (int)(blocks < cap2 ? blocks : cap2);
+#define LN_F(NV_)                                                                                           \
+    ln_fwd_vec_kernel<NV_><<<g2, 256, 0, stream()>>>((const float*)x, (const float*)gamma, (const float*)beta, \
+                                                     (float*)y, (float*)mean, (float*)rstd, rows, (int)cols, (float)eps)
+        if (nv == 2) LN_F(2); else if (nv == 4) LN_F(4); else if (nv == 6) LN_F(6); else LN_F(8);
+#undef LN_F
+        LG_CHECK_LAUNCH();
+        return 0;
+    }
     if (dtype == LG_F32)
         ln_fwd_kernel<float><<<grid, 256, 0, stream()>>>((const float*)x, (const float*)gamma, (const float*)beta,
                                                          (float*)y, (float*)mean, (float*)rstd, rows, cols,
@@ -372,11 +565,24 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
                (long long)cols);
     int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 2;
     int grid = (int)(blocks < cap ? blocks : cap);
+    const int nv = ln_nv(cols);
+    const bool fast = dtype == LG_F32 && nv && aligned16(x) && aligned16(g) && aligned16(dx) && aligned16(gamma);
+    if (fast) {
+        int64_t cap2 = (int64_t)sm_count();
+        grid = (int)(blocks < cap2 ? blocks : cap2);
+    }
     void* part = tmp_alloc(2 * (size_t)grid * cols * es);
     if (!part) return 1;
     void* pg = part;
     void* pb = (char*)part + (size_t)grid * cols * es;
-    if (dtype == LG_F32)
+    if (fast) {
+#define LN_B(NV_)                                                                                              \
+    ln_bwd_vec_kernel<NV_><<<grid, 256, smem, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean, \
+                                                          (const float*)rstd, (const float*)g, (float*)dx,     \
+                                                          (float*)pg, (float*)pb, rows, (int)cols)
+        if (nv == 2) LN_B(2); else if (nv == 4) LN_B(4); else if (nv == 6) LN_B(6); else LN_B(8);
+#undef LN_B
+    } else if (dtype == LG_F32)
         ln_bwd_kernel<float><<<grid, 256, smem, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean,
                                                             (const float*)rstd, (const float*)g, (float*)dx,
                                                             (float*)pg, (float*)pb, rows, cols);

@@ -64,6 +64,25 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// same load, delivered to the same shared-memory offset (and signalling the same mbarrier offset) in every
+// CTA of the cluster named by `mask`
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+        "{%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -106,7 +125,11 @@ struct TcParams {
     const float* bias;
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+// CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on vertically adjacent output tiles
+// (same N block): each loads its own A tile and HALF of the shared B tile, multicast to both -- L2 -> SM
+// traffic per CTA drops from A + B to A + B/2.  A stage may be refilled only when BOTH consumers have
+// released it, so the MMA warps commit to the `empty` barrier of both CTAs.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, TcParams p) {
@@ -126,13 +149,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // p.tiles_m counts groups of CL vertically adjacent tiles; work items are distributed over clusters
     const int items_per_batch = p.tiles_m * p.tiles_n * p.splits;
     const int work_items = items_per_batch * p.batches;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = (int)blockIdx.x / CL, n_clusters = (int)gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
@@ -151,6 +177,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -159,11 +186,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+            for (int w = cluster_id; w < work_items; w += n_clusters) {
                 const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
                 const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
                 const int tile = wi / p.splits, split = wi - tile * p.splits;
-                const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+                const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
                 const int kb0 = split * p.kblocks_per_split;
                 int kb1 = kb0 + p.kblocks_per_split;
                 if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
@@ -180,12 +207,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int j = 0; j < BM / 32; ++j)
                             tma_load_4d(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
                     }
-                    if (!B_MN) {
-                        tma_load_4d(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
-                    } else {
+                    if (CL == 1) {
+                        if (!B_MN) {
+                            tma_load_4d(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j)
-                            tma_load_4d(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
+                            for (int j = 0; j < BN / 32; ++j)
+                                tma_load_4d(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
+                        }
+                    } else {
+                        // this CTA fetches its half of the B tile for the whole cluster
+                        constexpr uint16_t kAll = (uint16_t)((1u << CL) - 1);
+                        if (!B_MN) {
+                            constexpr int HALF = BN / CL;   // rows of B per CTA (the map's box height)
+                            tma_load_4d_mc(&map_b, &full[stage], sb + crank * HALF * 128, k0, n0 + crank * HALF, bc1,
+                                           bc0, kAll);
+                        } else {
+                            constexpr int PER = (BN / 32) / CL;
+#pragma unroll
+                            for (int jj = 0; jj < PER; ++jj) {
+                                const int j = crank * PER + jj;
+                                tma_load_4d_mc(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0,
+                                               kAll);
+                            }
+                        }
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -202,7 +247,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+            for (int w = cluster_id; w < work_items; w += n_clusters) {
                 const int split = (w % items_per_batch) % p.splits;
                 const int kb0 = split * p.kblocks_per_split;
                 int kb1 = kb0 + p.kblocks_per_split;
@@ -234,10 +279,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             "l"(da), "l"(db), "r"(idesc), "r"(accum)
                             : "memory");
                     }
-                    // frees the smem stage once the MMAs above have consumed it
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                     smem_u32(&empty[stage]))
-                                 : "memory");
+                    // frees the smem stage once the MMAs above have consumed it (in every CTA that fills it)
+                    if (CL == 1) {
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                         smem_u32(&empty[stage]))
+                                     : "memory");
+                    } else {
+                        asm volatile(
+                            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+                            "[%0], %1;" ::"r"(smem_u32(&empty[stage])),
+                            "h"((uint16_t)((1u << CL) - 1))
+                            : "memory");
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -261,11 +314,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         int flip = 0;
-        for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        for (int w = cluster_id; w < work_items; w += n_clusters) {
             const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
             const int tile = wi / p.splits, split = wi - tile * p.splits;
-            const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+            const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool rows_live = (m0 + 32 * q) < p.M;
@@ -336,6 +389,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -388,28 +442,40 @@ constexpr size_t smem_for() {
            (2 * stages_for<BN>() + 4) * 8 + 16 + 1024;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CL>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, int grid) {
     constexpr int ST = stages_for<BN>();
     constexpr size_t smem = smem_for<BN>();
-    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, ST>;
+    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, ST, CL>;
     static bool attr_done = false;
     if (!attr_done) {
         LG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    kern<<<grid, 192, smem, stream()>>>(ma, mb, mc, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
     LG_CHECK_LAUNCH();
     return 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
               const TcParams& p, int grid) {
-    if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(ma, mb, mc, p, grid);
-    if (!a_mn && b_mn) return launch_cfg<BN, false, true>(ma, mb, mc, p, grid);
-    if (a_mn && !b_mn) return launch_cfg<BN, true, false>(ma, mb, mc, p, grid);
-    return launch_cfg<BN, true, true>(ma, mb, mc, p, grid);
+    if (!a_mn && !b_mn) return launch_cfg<BN, false, false, CL>(ma, mb, mc, p, grid);
+    if (!a_mn && b_mn) return launch_cfg<BN, false, true, CL>(ma, mb, mc, p, grid);
+    if (a_mn && !b_mn) return launch_cfg<BN, true, false, CL>(ma, mb, mc, p, grid);
+    return launch_cfg<BN, true, true, CL>(ma, mb, mc, p, grid);
 }
 
 bool k_major(int64_t s_mn, int64_t s_k, int64_t extent_mn) { return s_k == 1 && (s_mn % 4 == 0 || extent_mn == 1); }
@@ -497,7 +563,9 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     if (!a_mn) rc = make_map(&ma, a, K, M, d->sa_m, ba, BK, BM);
     else rc = make_map(&ma, a, M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, bb, BK, pl.bn);
+    // clusters of two CTAs share the B tile (each fetches half of it and multicasts); needs >= 2 tile rows
+    const int cl = (batches == 1 && pl.tiles_m >= 2 && getenv("LG_GEMM_NO_CLUSTER") == nullptr) ? 2 : 1;
+    if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, bb, BK, pl.bn / cl);
     else rc = make_map(&mb, b, N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     rc = make_map(&mc, c, N, M, d->sc_m, bc, 32, 32);
@@ -506,7 +574,7 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     p.M = (int)M;
     p.N = (int)N;
     p.K = (int)K;
-    p.tiles_m = pl.tiles_m;
+    p.tiles_m = (pl.tiles_m + cl - 1) / cl;
     p.tiles_n = pl.tiles_n;
     p.splits = pl.splits;
     p.kblocks_per_split = pl.kper;
@@ -522,15 +590,24 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
             LG_CUDA(cudaMemset2DAsync(c, (size_t)d->sc_m * 4, 0, (size_t)N * 4, (size_t)M, stream()));
         }
     }
-    const int64_t items64 = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits * batches;
+    const int64_t items64 = (int64_t)p.tiles_m * pl.tiles_n * pl.splits * batches;   // cluster work items
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
-    const int grid = items < sm_count() ? items : sm_count();
+    const int max_clusters = sm_count() / cl;
+    const int grid = cl * (items < max_clusters ? items : max_clusters);
+    if (cl == 2) {
+        switch (pl.bn) {
+            case 256: return launch_bn<256, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
+            case 192: return launch_bn<192, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
+            case 128: return launch_bn<128, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
+            default: return launch_bn<64, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
+        }
+    }
     switch (pl.bn) {
-        case 256: return launch_bn<256>(a_mn, b_mn, ma, mb, mc, p, grid);
-        case 192: return launch_bn<192>(a_mn, b_mn, ma, mb, mc, p, grid);
-        case 128: return launch_bn<128>(a_mn, b_mn, ma, mb, mc, p, grid);
-        default: return launch_bn<64>(a_mn, b_mn, ma, mb, mc, p, grid);
+        case 256: return launch_bn<256, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
+        case 192: return launch_bn<192, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
+        case 128: return launch_bn<128, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
+        default: return launch_bn<64, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
     }
 }
 

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T
 // ---- inner > 1 -----------------------------------------------------------------------------------
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __restrict__ out, int64_t rlen,
-                                                int64_t inner, int64_t chunk, int S, int64_t ntiles, T scale) {
+                                                int64_t inner, int64_t ld, int64_t chunk, int S, int64_t ntiles,
+                                                T scale) {
     using VT = Vec<T, V>;
     __shared__ T sm[8][32 * V + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -124,19 +125,19 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = R::template init<T>();
     if (col < inner) {
-        const T* p = x + o * rlen * inner + col;
+        const T* p = x + o * rlen * ld + col;   // ld = elements between consecutive rows (>= inner)
         int64_t r = beg + ty;
         for (; r + 24 < end; r += 32) {
-            VT v0 = *reinterpret_cast<const VT*>(p + r * inner), v1 = *reinterpret_cast<const VT*>(p + (r + 8) * inner),
-               v2 = *reinterpret_cast<const VT*>(p + (r + 16) * inner),
-               v3 = *reinterpret_cast<const VT*>(p + (r + 24) * inner);
+            VT v0 = *reinterpret_cast<const VT*>(p + r * ld), v1 = *reinterpret_cast<const VT*>(p + (r + 8) * ld),
+               v2 = *reinterpret_cast<const VT*>(p + (r + 16) * ld),
+               v3 = *reinterpret_cast<const VT*>(p + (r + 24) * ld);
 #pragma unroll
             for (int k = 0; k < V; ++k)
                 acc[k] = R::template comb<T>(R::template comb<T>(R::template comb<T>(acc[k], v0.v[k]), v1.v[k]),
                                              R::template comb<T>(v2.v[k], v3.v[k]));
         }
         for (; r < end; r += 8) {
-            VT v0 = *reinterpret_cast<const VT*>(p + r * inner);
+            VT v0 = *reinterpret_cast<const VT*>(p + r * ld);
 #pragma unroll
             for (int k = 0; k < V; ++k) acc[k] = R::template comb<T>(acc[k], v0.v[k]);
         }
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
 }
 
 template <class R, typename T>
-int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, T scale) {
+int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, T scale, int64_t ld = 0) {
+    if (ld <= 0 || inner == 1) ld = inner;
     constexpr int VMAX = 16 / sizeof(T);
     const int sms = sm_count();
     if (outer * inner == 0) return 0;
@@ -203,7 +205,7 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
         return 0;
     }
     // column reduce
-    const bool vec = (inner % VMAX == 0) && aligned16(x);
+    const bool vec = (inner % VMAX == 0) && (ld % VMAX == 0) && aligned16(x);
     const int V = vec ? VMAX : 1;
     int64_t ntiles = (inner + 32 * V - 1) / (32 * V);
     int64_t S = 1;
@@ -225,8 +227,8 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
     }
     T sc = (S > 1) ? T(1) : scale;
     int grid = (int)(ntiles * outer * S);
-    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, chunk, (int)S, ntiles, sc);
-    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, chunk, (int)S, ntiles, sc);
+    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc);
+    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc);
     LG_CHECK_LAUNCH();
     if (S > 1) {
         int rc = reduce_impl<R, T>(partial, out, outer, S, inner, scale);
@@ -237,11 +239,11 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
 }
 
 template <typename T>
-int reduce_op(int op, const void* x, void* out, int64_t outer, int64_t rlen, int64_t inner, double scale) {
+int reduce_op(int op, const void* x, void* out, int64_t outer, int64_t rlen, int64_t inner, double scale, int64_t ld) {
     switch (op) {
-        case LG_RED_SUM: return reduce_impl<RSum, T>((const T*)x, (T*)out, outer, rlen, inner, (T)scale);
-        case LG_RED_MAX: return reduce_impl<RMax, T>((const T*)x, (T*)out, outer, rlen, inner, (T)1);
-        case LG_RED_MIN: return reduce_impl<RMin, T>((const T*)x, (T*)out, outer, rlen, inner, (T)1);
+        case LG_RED_SUM: return reduce_impl<RSum, T>((const T*)x, (T*)out, outer, rlen, inner, (T)scale, ld);
+        case LG_RED_MAX: return reduce_impl<RMax, T>((const T*)x, (T*)out, outer, rlen, inner, (T)1, ld);
+        case LG_RED_MIN: return reduce_impl<RMin, T>((const T*)x, (T*)out, outer, rlen, inner, (T)1, ld);
     }
     return set_error("lg_reduce: unknown op %d", op);
 }
@@ -251,7 +253,17 @@ int reduce_op(int op, const void* x, void* out, int64_t outer, int64_t rlen, int
 extern "C" int lg_reduce(int op, int dtype, const void* x, void* out, int64_t outer, int64_t rlen, int64_t inner,
                          double scale) {
     LG_INIT();
-    if (dtype == LG_F32) return reduce_op<float>(op, x, out, outer, rlen, inner, scale);
-    if (dtype == LG_F64) return reduce_op<double>(op, x, out, outer, rlen, inner, scale);
+    if (dtype == LG_F32) return reduce_op<float>(op, x, out, outer, rlen, inner, scale, 0);
+    if (dtype == LG_F64) return reduce_op<double>(op, x, out, outer, rlen, inner, scale, 0);
     return set_error("lg_reduce: unsupported dtype %d", dtype);
+}
+
+extern "C" int lg_reduce_pitched(int op, int dtype, const void* x, void* out, int64_t outer, int64_t rlen,
+                                 int64_t inner, int64_t ld, double scale) {
+    LG_INIT();
+    LG_REQUIRE(ld >= inner && inner >= 1, "lg_reduce_pitched: need ld >= inner >= 1");
+    LG_REQUIRE(inner > 1 || ld == 1, "lg_reduce_pitched: a pitch needs inner > 1");
+    if (dtype == LG_F32) return reduce_op<float>(op, x, out, outer, rlen, inner, scale, ld);
+    if (dtype == LG_F64) return reduce_op<double>(op, x, out, outer, rlen, inner, scale, ld);
+    return set_error("lg_reduce_pitched: unsupported dtype %d", dtype);
 }

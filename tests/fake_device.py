@@ -183,6 +183,15 @@ class FakeDevice(object):
             r = r * NP[dt](scale)
         _arr(out, dt, [outer, inner])[...] = r
 
+    def reduce_pitched(self, op, dt, x, out, outer, red, inner, ld, scale):
+        self.launches += 1
+        X = _arr(x, dt, [outer, red, inner], [red * ld, ld, 1])
+        fn = {0: np.sum, 1: np.max, 2: np.min}[op]
+        r = fn(X, axis=1)
+        if op == 0:
+            r = r * NP[dt](scale)
+        _arr(out, dt, [outer, inner])[...] = r
+
     # ---- matmul
     def gemm(self, mode, dt, dref, a, b, c, bias, accumulate):
         self.launches += 1
