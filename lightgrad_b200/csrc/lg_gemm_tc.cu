@@ -41,18 +41,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread for a bounded time per call; the outer loop is capped so that a protocol bug
+// surfaces as a trapped launch (an error the host sees) instead of a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "LG_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LG_DONE;\n\t"
-        "bra LG_WAIT;\n\t"
-        "LG_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && spins > (1u << 24)) __trap();
+    }
 }
 
 // every tensor map is rank 4: (contiguous dim, strided dim, batch1, batch0); plain 2-D problems use batch = 1
@@ -72,6 +76,28 @@ __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t*
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
         "{%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) helpers ------------------------------------------------------------
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the
+// shared::cluster address cleared), executed by both CTAs of the pair for their own halves
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                                int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 raddr;\n\t"
+        "mapa.shared::cluster.u32 raddr, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(rank)
         : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -396,6 +422,260 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+// =====================================================================================================
+// CTA-pair variant: two CTAs on neighbouring SMs compute one 256 x BN tile with tcgen05.mma.cta_group::2.
+// Each CTA stages only ITS 128 rows of A and ITS half (BN/2 rows) of B: shared-memory footprint and
+// L2 -> SM traffic per k-step drop from 16 KB + BN*128 B to 16 KB + BN*64 B per CTA, so the ring holds
+// 6 stages instead of 4 at BN = 256 -- what the fp32-operand (tf32) GEMM needs to cover L2 latency.
+//   both CTAs : warp 0 = TMA producer (completion credited to the leader's `full` barrier)
+//               warp 1 = collective TMEM allocation; in the leader also the single MMA-issuing thread
+//               warps 2..5 = epilogue on the CTA's own 128 accumulator rows
+//   leader    : waits `full`, issues m256 nBN k8 MMAs, tcgen05.commit(multicast) -> `empty` of both CTAs,
+//               and `tfull` of both CTAs when a tile is complete; waits `tempty` (8 warp arrivals: 4 local,
+//               4 remote) before overwriting an accumulator stage.
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_c, TcParams p) {
+    constexpr int HB = BN / 2;                          // B rows staged per CTA
+    constexpr int B_STAGE_BYTES = HB * 128;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(epi_base + EPI_WARPS * 2 * EPI_BUF_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items_per_batch = p.tiles_m * p.tiles_n * p.splits;   // p.tiles_m counts 256-row tile pairs
+    const int work_items = items_per_batch * p.batches;
+    const int crank = (int)cluster_ctarank();
+    const bool leader = crank == 0;
+    const int cluster_id = (int)blockIdx.x / 2, n_clusters = (int)gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 2 * EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c));
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs) ===========================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = cluster_id; w < work_items; w += n_clusters) {
+                const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+                const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
+                const int tile = wi / p.splits, split = wi - tile * p.splits;
+                const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM;
+                const int n0 = (tile / p.tiles_m) * BN + crank * HB;     // this CTA's half of the B tile
+                const int kb0 = split * p.kblocks_per_split;
+                int kb1 = kb0 + p.kblocks_per_split;
+                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = stage_base + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    // the leader's barrier collects the bytes of both CTAs
+                    if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    if (!A_MN) {
+                        tma_load_4d_2sm(&map_a, &full[stage], sa, k0, m0, bc1, bc0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j)
+                            tma_load_4d_2sm(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
+                    }
+                    if (!B_MN) {
+                        tma_load_4d_2sm(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < HB / 32; ++j)
+                            tma_load_4d_2sm(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =======================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * BM, BN, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int w = cluster_id; w < work_items; w += n_clusters) {
+                const int split = (w % items_per_batch) % p.splits;
+                const int kb0 = split * p.kblocks_per_split;
+                int kb1 = kb0 + p.kblocks_per_split;
+                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t da = A_MN ? umma_desc(sa + ks * 1024, BK * 128, 512, 1)
+                                                 : umma_desc(sa + ks * 32, 16, 1024, 2);
+                        const uint64_t db = B_MN ? umma_desc(sb + ks * 1024, BK * 128, 512, 1)
+                                                 : umma_desc(sb + ks * 32, 16, 1024, 2);
+                        const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+                            "}" ::"r"(d_tmem),
+                            "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                            : "memory");
+                    }
+                    asm volatile(
+                        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], "
+                        "%1;" ::"r"(smem_u32(&empty[stage])),
+                        "h"((uint16_t)3)
+                        : "memory");
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                asm volatile(
+                    "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                        smem_u32(&tfull[acc])),
+                    "h"((uint16_t)3)
+                    : "memory");
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue (both CTAs, own 128 rows) ==================
+        const int q = warp & 3;
+        const int ew = warp - 2;
+        uint8_t* buf0 = epi_base + ew * 2 * EPI_BUF_BYTES;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int flip = 0;
+        for (int w = cluster_id; w < work_items; w += n_clusters) {
+            const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+            const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
+            const int tile = wi / p.splits, split = wi - tile * p.splits;
+            const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM, n0 = (tile / p.tiles_m) * BN;
+            mbar_wait(&tfull[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool rows_live = (m0 + 32 * q) < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (rows_live) {
+                    uint8_t* buf = buf0 + flip * EPI_BUF_BYTES;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const bool add_bias = p.bias != nullptr && split == 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o;
+                        o.x = __uint_as_float(v[4 * j + 0]);
+                        o.y = __uint_as_float(v[4 * j + 1]);
+                        o.z = __uint_as_float(v[4 * j + 2]);
+                        o.w = __uint_as_float(v[4 * j + 3]);
+                        if (add_bias) {
+                            const int cn = col0 + 4 * j;
+                            if (cn + 3 < p.N) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cn);
+                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                            } else {
+                                if (cn + 0 < p.N) o.x += p.bias[cn + 0];
+                                if (cn + 1 < p.N) o.y += p.bias[cn + 1];
+                                if (cn + 2 < p.N) o.z += p.bias[cn + 2];
+                            }
+                        }
+                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.splits > 1) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        else tma_store_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    flip ^= 1;
+                }
+            }
+            // one arrival per warp on the LEADER's barrier: the accumulator stage of this CTA is drained
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -440,6 +720,53 @@ template <int BN>
 constexpr size_t smem_for() {
     return (size_t)stages_for<BN>() * (A_STAGE_BYTES + BN * 128) + EPI_WARPS * 2 * EPI_BUF_BYTES +
            (2 * stages_for<BN>() + 4) * 8 + 16 + 1024;
+}
+
+template <int BN>
+constexpr int stages2_for() {
+    // per-CTA stage = 16 KB of A + BN*64 B of B; keep ~192 KB of operands in flight
+    return (192 * 1024) / (A_STAGE_BYTES + BN * 64) > 10 ? 10 : (192 * 1024) / (A_STAGE_BYTES + BN * 64);
+}
+template <int BN>
+constexpr size_t smem2_for() {
+    return (size_t)stages2_for<BN>() * (A_STAGE_BYTES + BN * 64) + EPI_WARPS * 2 * EPI_BUF_BYTES +
+           (2 * stages2_for<BN>() + 4) * 8 + 16 + 1024;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, int grid) {
+    constexpr int ST = stages2_for<BN>();
+    constexpr size_t smem = smem2_for<BN>();
+    auto kern = gemm_tf32_2cta_kernel<BN, A_MN, B_MN, ST>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int BN>
+int launch_2cta_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                   const TcParams& p, int grid) {
+    if (!a_mn && !b_mn) return launch_2cta<BN, false, false>(ma, mb, mc, p, grid);
+    if (!a_mn && b_mn) return launch_2cta<BN, false, true>(ma, mb, mc, p, grid);
+    if (a_mn && !b_mn) return launch_2cta<BN, true, false>(ma, mb, mc, p, grid);
+    return launch_2cta<BN, true, true>(ma, mb, mc, p, grid);
 }
 
 template <int BN, bool A_MN, bool B_MN, int CL>
@@ -563,8 +890,9 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     if (!a_mn) rc = make_map(&ma, a, K, M, d->sa_m, ba, BK, BM);
     else rc = make_map(&ma, a, M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    // clusters of two CTAs share the B tile (each fetches half of it and multicasts); needs >= 2 tile rows
+    // CTA pairs (cta_group::2) take 256-row tiles and split the B tile between the two SMs; needs >= 2 tile rows
     const int cl = (batches == 1 && pl.tiles_m >= 2 && getenv("LG_GEMM_NO_CLUSTER") == nullptr) ? 2 : 1;
+    const bool pair_mma = cl == 2 && getenv("LG_GEMM_MULTICAST_ONLY") == nullptr;
     if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, bb, BK, pl.bn / cl);
     else rc = make_map(&mb, b, N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
@@ -595,6 +923,14 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     const int items = (int)items64;
     const int max_clusters = sm_count() / cl;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
+    if (pair_mma) {
+        switch (pl.bn) {
+            case 256: return launch_2cta_bn<256>(a_mn, b_mn, ma, mb, mc, p, grid);
+            case 192: return launch_2cta_bn<192>(a_mn, b_mn, ma, mb, mc, p, grid);
+            case 128: return launch_2cta_bn<128>(a_mn, b_mn, ma, mb, mc, p, grid);
+            default: return launch_2cta_bn<64>(a_mn, b_mn, ma, mb, mc, p, grid);
+        }
+    }
     if (cl == 2) {
         switch (pl.bn) {
             case 256: return launch_bn<256, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
