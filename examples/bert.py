@@ -77,7 +77,11 @@ class BertSelfAttention(nn.Module):
                 attention_mask = (1.0 - attention_mask) * -10000.0
                 scores = scores + attention_mask.detach()
             scores = scores.softmax(axis=-1)
-        context = (scores @ V).transpose(0, 2, 1, 3)
+        if getattr(scores.__class__, 'dot_supports_layout', False):
+            # the product lands in V's (batch, seq, head, dim) memory order: the head merge below is a view
+            context = scores.dot(V, out_layout='rhs').transpose(0, 2, 1, 3)
+        else:
+            context = (scores @ V).transpose(0, 2, 1, 3)
         return context.reshape(b, s, self.h * self.d), scores
 
 

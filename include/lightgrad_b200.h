@@ -152,10 +152,11 @@ int lg_cast(int src_dtype, int dst_dtype, int ndim, const int64_t* shape,
 /* x is a contiguous (outer, reduce, inner) block; out is (outer, inner); out = scale * reduce(x) */
 int lg_reduce(int op, int dtype, const void* x, void* out,
               int64_t outer, int64_t reduce, int64_t inner, double scale);
-/* same with rows `ld` elements apart (ld >= inner > 1): element (o, r, c) at x[(o*reduce + r)*ld + c].
- * Lets a column reduction read a GEMM result whose leading dimension was padded for TMA. */
+/* same with rows `ld` elements apart (ld >= inner > 1): element (o, r, c) at x[(o*reduce + r)*ld + c]
+ * (lets a column reduction read a GEMM result whose leading dimension was padded for TMA);
+ * accumulate != 0 (sums only): out += scale * sum, e.g. a bias gradient added straight into .grad */
 int lg_reduce_pitched(int op, int dtype, const void* x, void* out,
-                      int64_t outer, int64_t reduce, int64_t inner, int64_t ld, double scale);
+                      int64_t outer, int64_t reduce, int64_t inner, int64_t ld, double scale, int accumulate);
 
 /* ---- matmul (replaces kernels.dot) ---------------------------------------------------------- */
 /* C[b0,b1] (M x N) = A[b0,b1] (M x K) * B[b0,b1] (K x N) (+ bias[N] if bias != NULL)
@@ -208,8 +209,10 @@ int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, int64_t l
 /* layer norm over the last axis (nn.py:109-124): y = (x-mean)/sqrt(var+eps)*gamma+beta */
 int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y,
                      void* mean, void* rstd, int64_t rows, int64_t cols, double eps);
+/* accumulate != 0: dgamma / dbeta are added to the buffers (existing .grad) instead of overwriting them */
 int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd,
-                     const void* g, void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols);
+                     const void* g, void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols,
+                     int accumulate);
 
 /* ---- optimizers (replaces the per-parameter python loops of optim.py) ----------------------- */
 /* all tensors of one optimizer live in flat fp32 arenas; `seg_end_dev[i]` (device, int64) is the

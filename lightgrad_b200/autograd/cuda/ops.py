@@ -538,7 +538,7 @@ def _reduce(op, x, axes, keepdims, scale=1.0):
         if st is not None and st[1] == 1 and st[0] >= full_shape[-1]:
             kshape = (1,) * (nd - 1) + (full_shape[-1],)
             out = CudaTensor._new(kshape if keepdims else (full_shape[-1],), x._dtype)
-            rt.api.reduce_pitched(op, x._code, x.ptr, out.ptr, 1, rows, full_shape[-1], st[0], scale)
+            rt.api.reduce_pitched(op, x._code, x.ptr, out.ptr, 1, rows, full_shape[-1], st[0], scale, 0)
             return out
     cur = x.contiguous()
     shape = list(full_shape)
@@ -724,6 +724,41 @@ def _fold_rows(t):
     return t._view((rows, t._shape[-1]), st)
 
 
+def _empty_like_layout(ref):
+    """Uninitialised tensor of ref's shape whose memory order follows ref's strides (None if ref broadcasts)."""
+    shape, strides = ref._shape, ref._strides
+    if ref._contig:
+        return CudaTensor._new(shape, ref._dtype)
+    if any(st <= 0 and s > 1 for s, st in zip(shape, strides)):
+        return None
+    order = sorted(range(len(shape)), key=lambda i: (-strides[i] if shape[i] > 1 else 0, i))
+    dense = contiguous_strides(tuple(shape[i] for i in order))
+    st = [0] * len(shape)
+    for pos, i in enumerate(order):
+        st[i] = dense[pos]
+    base = CudaTensor._new(tuple(shape[i] for i in order), ref._dtype)
+    out = base._view(shape, tuple(st))
+    out._temp = True
+    return out
+
+
+def _gemm_like(ref, x, y):
+    """x @ y written in the memory layout of ``ref`` (the operand this is the gradient of), so that the
+    transpose / reshape backward that follows stays a view instead of a strided copy."""
+    if ref._contig or ref._shape[:-2] != _bshape(x._shape[:-2], y._shape[:-2]) or ref._code != x._code:
+        return _gemm(x, y)
+    out = _empty_like_layout(ref)
+    if out is None:
+        return _gemm(x, y)
+    if out._strides[-1] == 1:
+        return _gemm(x, y, out=out)
+    if out._strides[-2] == 1:
+        # column-major result: compute the transposed product into the transposed view
+        _gemm(_swap_last(y), _swap_last(x), out=_swap_last(out))
+        return out
+    return _gemm(x, y)
+
+
 def _swap_last(t):
     return t._view(t._shape[:-2] + (t._shape[-1], t._shape[-2]), t._strides[:-2] + (t._strides[-1], t._strides[-2]))
 
@@ -731,7 +766,9 @@ def _swap_last(t):
 @CudaTensor.register_op()
 @CudaTensor.register_op("__matmul__")
 class dot(Function):
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, out_layout=None):
+        """``out_layout='rhs'``: lay the result out in memory like ``b`` (same logical shape required), e.g.
+        attention's P @ V lands directly in the (batch, seq, head, dim) order its head-merge expects."""
         if not isinstance(b, CudaTensor):
             b = _as_tensor(b, a)
         a, b = _promote(a, b)
@@ -747,6 +784,10 @@ class dot(Function):
             # (batch.., M, K) @ (K, N): one GEMM with M' = batch*M
             a2 = _fold_rows(a)
             out = _with_shape(_gemm(a2, b), a._shape[:-1] + (b._shape[-1],))
+        elif out_layout == 'rhs' and not b._contig and b._shape == a._shape[:-1] + b._shape[-1:] \
+                and a._shape[:-2] == b._shape[:-2]:
+            out = _empty_like_layout(b)
+            out = _gemm(a, b, out=out) if out is not None and out._strides[-1] == 1 else _gemm(a, b)
         else:
             out = _gemm(a, b)
         if ctx.va or ctx.vb:
@@ -774,8 +815,8 @@ class dot(Function):
             da = _with_shape(_gemm(g2, _swap_last(b)), a._shape)
             db = _gemm(_swap_last(a2), g2)
         else:
-            da = _gemm(g, _swap_last(b))
-            db = _gemm(_swap_last(a), g)
+            da = _gemm_like(a, g, _swap_last(b))
+            db = _gemm_like(b, _swap_last(a), g)
             da, db = _unbroadcast(da, a._shape), _unbroadcast(db, b._shape)
         if ctx.va:
             da = da.reshape(da._shape[-1])
@@ -803,10 +844,24 @@ class linear(Function):
         x2, weight, xshape, has_bias = ctx.get_saved_tensors()
         g2 = _fold_rows(out_grad)
         dx = _with_shape(_gemm(g2, weight), xshape)
-        dw = _gemm(_swap_last(g2), x2)
+        wg = weight.grad
+        if weight.requires_grad and wg is not None and wg._contig and wg._code == g2._code == rt.F32 \
+                and wg._shape == weight._shape:
+            # dW += dY^T X straight into the existing gradient (the optimizer's arena): no temporary, no add pass
+            _gemm(_swap_last(g2), x2, out=wg, accumulate=True)
+            dw = Function.ACCUMULATED
+        else:
+            dw = _gemm(_swap_last(g2), x2)
         if has_bias:
-            db = _reduce(RED['SUM'], g2, (0,), False)
-            return dx, dw, db
+            bias = ctx._parents[2]
+            bg = bias.grad if isinstance(bias, CudaTensor) and bias.requires_grad else None
+            if bg is not None and bg._contig and bg._code == g2._code and bg._shape == (g2._shape[1],) \
+                    and g2._strides[1] == 1 and g2._shape[1] > 1:
+                # db += column sums of dY, reduced straight into the existing gradient
+                rt.api.reduce_pitched(RED['SUM'], g2._code, g2.ptr, bg.ptr, 1, g2._shape[0], g2._shape[1],
+                                      g2._strides[0], 1.0, 1)
+                return dx, dw, Function.ACCUMULATED
+            return dx, dw, _reduce(RED['SUM'], g2, (0,), False)
         return dx, dw
 
 
@@ -947,12 +1002,24 @@ class getitem(Function):
         rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, idx_dev = plan
         # keep the uploaded index arrays so backward does not stage them again
         ctx.save_for_backward(a._shape, a._dtype, idx_dev)
+        ctx.source = a
         out = CudaTensor._new(bshape + tail_shape, a._dtype)
         rt.api.gather_rows(a._code, rows._code, src.ptr, n_rows, row_stride, rows.ptr, n_idx, row_len, out.ptr)
         return out
 
     def backward(ctx, out_grad):
         shape, dtype, idx = ctx.get_saved_tensors()
+        a = getattr(ctx, 'source', None)
+        if a is not None and a.requires_grad and a.grad is not None and a.grad._contig and a.grad._shape == shape \
+                and a.grad._code == out_grad._code and a.grad._code in (rt.F32, rt.F64):
+            # scatter-add straight into the existing gradient of the table (skips zero-filling and adding a
+            # table-sized temporary: 94 MB for BERT's word embeddings)
+            src, plan = _index_plan(a.grad, idx)
+            rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, _keep = plan
+            if src._data is a.grad._data:
+                g = out_grad.contiguous()
+                rt.api.scatter_add_rows(g._code, rows._code, src.ptr, n_rows, row_stride, rows.ptr, n_idx, row_len, g.ptr)
+                return Function.ACCUMULATED
         grad = CudaTensor.zeros(shape, dtype=np.float32 if dtype.kind != 'f' else dtype, requires_grad=False)
         src, plan = _index_plan(grad, idx)
         g = out_grad if out_grad._code == grad._code else out_grad.astype(grad._dtype)
@@ -1066,8 +1133,15 @@ class layernorm(Function):
         cols = x._shape[-1]
         rows = x._numel // cols
         dx = CudaTensor._new(x._shape, x._dtype)
+        weight, bias = ctx._parents[1], ctx._parents[2]
+        wg, bg = weight.grad, bias.grad
+        if weight.requires_grad and bias.requires_grad and wg is not None and bg is not None and wg._contig \
+                and bg._contig and wg._code == bg._code == x._code and wg._shape == bg._shape == (cols,):
+            # d(gamma), d(beta) are added straight into the existing gradients
+            rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, wg.ptr, bg.ptr, rows, cols, 1)
+            return dx, Function.ACCUMULATED, Function.ACCUMULATED
         dw, db = CudaTensor._new((cols,), x._dtype), CudaTensor._new((cols,), x._dtype)
-        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols)
+        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols, 0)
         return dx, dw, db
 
 

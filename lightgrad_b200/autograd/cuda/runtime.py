@@ -71,7 +71,7 @@ _SIGNATURES = {
     'lg_ew_bwd2_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int64],
     'lg_cast': [C.c_int, C.c_int, C.c_int, _i64p, _vp, _i64p, _vp, _i64p],
     'lg_reduce': [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_double],
-    'lg_reduce_pitched': [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double],
+    'lg_reduce_pitched': [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int],
     'lg_gemm': [C.c_int, C.c_int, C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, C.c_int],
     'lg_gemm_tc_supported': [C.c_int, C.c_int, C.POINTER(GemmDesc)],
     'lg_prof_gemm': [C.c_int],
@@ -85,7 +85,7 @@ _SIGNATURES = {
     'lg_cross_entropy_fwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int64],
     'lg_cross_entropy_bwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64],
     'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
-    'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64],
+    'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
     'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp,
                      C.c_double, C.c_double, C.c_double, C.c_double],

@@ -46,6 +46,8 @@ def i64arr(values):
 class CudaTensor(AbstractTensor):
     # softmax(axis, scale=...) multiplies its input first (lets attention fuse the 1/sqrt(d))
     has_scaled_softmax = True
+    # dot(other, out_layout='rhs') writes the product in the memory order of ``other``
+    dot_supports_layout = True
 
     def __init__(self, data, shape=None, strides=None, offset=0, dtype=np.float32, requires_grad=True):
         if not isinstance(data, (rt.Buffer, rt.ArenaSlice)):

@@ -60,6 +60,9 @@ class _FunctionMeta(type):
 
 
 class Function(object, metaclass=_FunctionMeta):
+    # a backward may add a parent's gradient straight into ``parent.grad`` (e.g. a GEMM epilogue that
+    # accumulates into the optimizer's gradient arena) and return this marker in that slot instead
+    ACCUMULATED = type('Accumulated', (), {'__repr__': lambda self: 'Function.ACCUMULATED'})()
 
     def __init__(self, *parents):
         self._parents = parents
@@ -74,6 +77,8 @@ class Function(object, metaclass=_FunctionMeta):
         in_grads = in_grads if isinstance(in_grads, tuple) else (in_grads,)
         for t, g in zip(self._parents, in_grads):
             if not (isinstance(t, AbstractTensor) and t.requires_grad):
+                continue
+            if g is Function.ACCUMULATED:
                 continue
             assert g is not None
             gs, ts = g.shape, t.shape

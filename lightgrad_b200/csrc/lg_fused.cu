@@ -555,7 +555,7 @@ int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* be
 }
 
 int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd, const void* g,
-                     void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols) {
+                     void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols, int accumulate) {
     LG_INIT();
     if (rows * cols == 0) return 0;
     size_t es = dtype_size(dtype);
@@ -568,7 +568,7 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
     const int nv = ln_nv(cols);
     const bool fast = dtype == LG_F32 && nv && aligned16(x) && aligned16(g) && aligned16(dx) && aligned16(gamma);
     if (fast) {
-        int64_t cap2 = (int64_t)sm_count();
+        int64_t cap2 = (int64_t)sm_count() * 4;   // ~1 row per warp: memory-level parallelism over register reuse
         grid = (int)(blocks < cap2 ? blocks : cap2);
     }
     void* part = tmp_alloc(2 * (size_t)grid * cols * es);
@@ -597,8 +597,9 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
         return set_error("ln_bwd launch failed: %s", cudaGetErrorString(e));
     }
     count_launch();
-    int rc = lg_reduce(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, 1.0);
-    if (!rc) rc = lg_reduce(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, 1.0);
+    int rc = cols > 1 ? lg_reduce_pitched(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, cols, 1.0, accumulate)
+                      : set_error("lg_layernorm_bwd: cols must be > 1");
+    if (!rc) rc = lg_reduce_pitched(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, cols, 1.0, accumulate);
     tmp_free(part);
     return rc;
 }

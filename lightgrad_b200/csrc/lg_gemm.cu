@@ -63,7 +63,7 @@ int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void*
         LG_CUDA(cudaEventRecord(pr.e0, stream()));
     }
     int rc;
-    if (mode != LG_GEMM_FP32_SIMT && !accumulate && gemm_tc_supported(mode, dtype, d, a, b, c))
+    if (mode != LG_GEMM_FP32_SIMT && !(accumulate && bias) && gemm_tc_supported(mode, dtype, d, a, b, c))
         rc = gemm_tc(mode, d, a, b, c, bias, accumulate);
     else
         rc = gemm_simt(dtype, d, a, b, c, bias, accumulate);

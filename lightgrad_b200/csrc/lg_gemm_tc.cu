@@ -148,6 +148,7 @@ struct TcParams {
     int M, N, K;
     int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
     int batch1, batches;      // batches = batch0 * batch1
+    int reduce_out;           // 1: C += tile (TMA reduce-add): split-K partials and/or accumulate mode
     const float* bias;
 };
 
@@ -395,7 +396,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.splits > 1) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        if (p.reduce_out) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
                         else tma_store_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -648,7 +649,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.splits > 1) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        if (p.reduce_out) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
                         else tma_store_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -879,7 +880,6 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     const int64_t M = d->M, N = d->N, K = d->K;
     const bool a_mn = !k_major(d->sa_m, d->sa_k, M);
     const bool b_mn = !k_major(d->sb_n, d->sb_k, N);
-    if (accumulate) return set_error("gemm_tc: accumulate is served by the SIMT kernel");
     const int64_t batches = d->batch0 * d->batch1;
     Plan pl = choose_plan(M, N, K, batches);
     CUtensorMap ma, mb, mc;
@@ -891,8 +891,12 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     else rc = make_map(&ma, a, M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     // CTA pairs (cta_group::2) take 256-row tiles and split the B tile between the two SMs; needs >= 2 tile rows
-    const int cl = (batches == 1 && pl.tiles_m >= 2 && getenv("LG_GEMM_NO_CLUSTER") == nullptr) ? 2 : 1;
-    const bool pair_mma = cl == 2 && getenv("LG_GEMM_MULTICAST_ONLY") == nullptr;
+    // (measured: +5..8 % on >= 2-wave problems such as 4096^3 or the 30522-wide decoder, but slower than
+    //  independent CTAs on the one-wave BERT projections, which therefore keep cta_group::1)
+    static const int force_pair = getenv("LG_GEMM_PAIR") ? atoi(getenv("LG_GEMM_PAIR")) : -1;
+    const bool big = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits >= 2 * (int64_t)sm_count();
+    const bool pair_mma = batches == 1 && pl.tiles_m >= 2 && (force_pair < 0 ? big : force_pair == 1);
+    const int cl = pair_mma ? 2 : 1;
     if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, bb, BK, pl.bn / cl);
     else rc = make_map(&mb, b, N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
@@ -910,7 +914,8 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     p.batch1 = (int)d->batch1;
     p.batches = (int)batches;
     p.bias = (const float*)bias;
-    if (pl.splits > 1) {
+    p.reduce_out = (pl.splits > 1 || accumulate) ? 1 : 0;
+    if (pl.splits > 1 && !accumulate) {
         // split-K partials are summed by TMA reduce-add into a zeroed C
         if (d->sc_m == N) {
             LG_CUDA(cudaMemsetAsync(c, 0, (size_t)M * N * 4, stream()));

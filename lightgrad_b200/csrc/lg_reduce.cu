@@ -41,7 +41,7 @@ __device__ __forceinline__ T warp_reduce(T v) {
 // ---- inner == 1, short rows ----------------------------------------------------------------------
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_rows_warp(const T* __restrict__ x, T* __restrict__ out, int64_t rows,
-                                                     int64_t len, T scale) {
+                                                     int64_t len, T scale, int acc_out) {
     using VT = Vec<T, V>;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -57,14 +57,14 @@ __global__ void __launch_bounds__(256) red_rows_warp(const T* __restrict__ x, T*
         }
         for (int64_t i = nv * V + lane; i < len; i += 32) acc = R::template comb<T>(acc, p[i]);
         acc = warp_reduce<R, T>(acc);
-        if (lane == 0) out[row] = acc * scale;
+        if (lane == 0) out[row] = acc_out ? out[row] + acc * scale : acc * scale;
     }
 }
 
 // ---- inner == 1, long rows -----------------------------------------------------------------------
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T* __restrict__ out, int64_t len,
-                                                      int64_t chunk, int S, T scale) {
+                                                      int64_t chunk, int S, T scale, int acc_out) {
     using VT = Vec<T, V>;
     __shared__ T sm[8];
     const int64_t row = blockIdx.x / S;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T
     if (threadIdx.x < 32) {
         T v = threadIdx.x < 8 ? sm[threadIdx.x] : R::template init<T>();
         v = warp_reduce<R, T>(v);
-        if (threadIdx.x == 0) out[row * S + part] = v * scale;
+        if (threadIdx.x == 0) out[row * S + part] = acc_out ? out[row * S + part] + v * scale : v * scale;
     }
 }
 
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __restrict__ out, int64_t rlen,
                                                 int64_t inner, int64_t ld, int64_t chunk, int S, int64_t ntiles,
-                                                T scale) {
+                                                T scale, int acc_out) {
     using VT = Vec<T, V>;
     __shared__ T sm[8][32 * V + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -151,12 +151,16 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
 #pragma unroll
         for (int j = 1; j < 8; ++j) v = R::template comb<T>(v, sm[j][c]);
         int64_t gc = tile * 32 * V + c;
-        if (gc < inner) out[(o * S + part) * inner + gc] = v * scale;
+        if (gc < inner) {
+            T* dst = out + (o * S + part) * inner + gc;
+            *dst = acc_out ? *dst + v * scale : v * scale;
+        }
     }
 }
 
 template <class R, typename T>
-int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, T scale, int64_t ld = 0) {
+int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, T scale, int64_t ld = 0,
+                int acc_out = 0) {
     if (ld <= 0 || inner == 1) ld = inner;
     constexpr int VMAX = 16 / sizeof(T);
     const int sms = sm_count();
@@ -168,8 +172,8 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
             int64_t blocks = (outer + 7) / 8;
             int64_t cap = (int64_t)sms * 32;
             int grid = (int)(blocks < cap ? blocks : cap);
-            if (vec) red_rows_warp<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, out, outer, rlen, scale);
-            else red_rows_warp<R, T, 1><<<grid, 256, 0, stream()>>>(x, out, outer, rlen, scale);
+            if (vec) red_rows_warp<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, out, outer, rlen, scale, acc_out);
+            else red_rows_warp<R, T, 1><<<grid, 256, 0, stream()>>>(x, out, outer, rlen, scale, acc_out);
             LG_CHECK_LAUNCH();
             return 0;
         }
@@ -194,11 +198,11 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
         }
         T sc = (S > 1) ? T(1) : scale;
         int grid = (int)(outer * S);
-        if (vec) red_rows_block<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, chunk, (int)S, sc);
-        else red_rows_block<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, chunk, (int)S, sc);
+        if (vec) red_rows_block<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, chunk, (int)S, sc, S > 1 ? 0 : acc_out);
+        else red_rows_block<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, chunk, (int)S, sc, S > 1 ? 0 : acc_out);
         LG_CHECK_LAUNCH();
         if (S > 1) {
-            int rc = reduce_impl<R, T>(partial, out, outer, S, 1, scale);
+            int rc = reduce_impl<R, T>(partial, out, outer, S, 1, scale, 0, acc_out);
             tmp_free(partial);
             return rc;
         }
@@ -227,11 +231,11 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
     }
     T sc = (S > 1) ? T(1) : scale;
     int grid = (int)(ntiles * outer * S);
-    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc);
-    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc);
+    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out);
+    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out);
     LG_CHECK_LAUNCH();
     if (S > 1) {
-        int rc = reduce_impl<R, T>(partial, out, outer, S, inner, scale);
+        int rc = reduce_impl<R, T>(partial, out, outer, S, inner, scale, 0, acc_out);
         tmp_free(partial);
         return rc;
     }
@@ -239,9 +243,10 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
 }
 
 template <typename T>
-int reduce_op(int op, const void* x, void* out, int64_t outer, int64_t rlen, int64_t inner, double scale, int64_t ld) {
+int reduce_op(int op, const void* x, void* out, int64_t outer, int64_t rlen, int64_t inner, double scale, int64_t ld,
+              int acc_out = 0) {
     switch (op) {
-        case LG_RED_SUM: return reduce_impl<RSum, T>((const T*)x, (T*)out, outer, rlen, inner, (T)scale, ld);
+        case LG_RED_SUM: return reduce_impl<RSum, T>((const T*)x, (T*)out, outer, rlen, inner, (T)scale, ld, acc_out);
         case LG_RED_MAX: return reduce_impl<RMax, T>((const T*)x, (T*)out, outer, rlen, inner, (T)1, ld);
         case LG_RED_MIN: return reduce_impl<RMin, T>((const T*)x, (T*)out, outer, rlen, inner, (T)1, ld);
     }
@@ -259,11 +264,12 @@ extern "C" int lg_reduce(int op, int dtype, const void* x, void* out, int64_t ou
 }
 
 extern "C" int lg_reduce_pitched(int op, int dtype, const void* x, void* out, int64_t outer, int64_t rlen,
-                                 int64_t inner, int64_t ld, double scale) {
+                                 int64_t inner, int64_t ld, double scale, int accumulate) {
     LG_INIT();
     LG_REQUIRE(ld >= inner && inner >= 1, "lg_reduce_pitched: need ld >= inner >= 1");
     LG_REQUIRE(inner > 1 || ld == 1, "lg_reduce_pitched: a pitch needs inner > 1");
-    if (dtype == LG_F32) return reduce_op<float>(op, x, out, outer, rlen, inner, scale, ld);
-    if (dtype == LG_F64) return reduce_op<double>(op, x, out, outer, rlen, inner, scale, ld);
+    LG_REQUIRE(!accumulate || op == LG_RED_SUM, "lg_reduce_pitched: accumulate is defined for sums only");
+    if (dtype == LG_F32) return reduce_op<float>(op, x, out, outer, rlen, inner, scale, ld, accumulate);
+    if (dtype == LG_F64) return reduce_op<double>(op, x, out, outer, rlen, inner, scale, ld, accumulate);
     return set_error("lg_reduce_pitched: unsupported dtype %d", dtype);
 }

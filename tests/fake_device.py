@@ -183,14 +183,15 @@ class FakeDevice(object):
             r = r * NP[dt](scale)
         _arr(out, dt, [outer, inner])[...] = r
 
-    def reduce_pitched(self, op, dt, x, out, outer, red, inner, ld, scale):
+    def reduce_pitched(self, op, dt, x, out, outer, red, inner, ld, scale, accumulate):
         self.launches += 1
         X = _arr(x, dt, [outer, red, inner], [red * ld, ld, 1])
         fn = {0: np.sum, 1: np.max, 2: np.min}[op]
         r = fn(X, axis=1)
         if op == 0:
             r = r * NP[dt](scale)
-        _arr(out, dt, [outer, inner])[...] = r
+        O = _arr(out, dt, [outer, inner])
+        O[...] = (O + r) if accumulate else r
 
     # ---- matmul
     def gemm(self, mode, dt, dref, a, b, c, bias, accumulate):
@@ -287,7 +288,7 @@ class FakeDevice(object):
         _arr(mean, dt, [rows])[...] = mu[:, 0]
         _arr(rstd, dt, [rows])[...] = rs[:, 0]
 
-    def layernorm_bwd(self, dt, x, w, mean, rstd, g, dx, dw, db, rows, cols):
+    def layernorm_bwd(self, dt, x, w, mean, rstd, g, dx, dw, db, rows, cols, accumulate):
         self.launches += 1
         X, G, W = _arr(x, dt, [rows, cols]), _arr(g, dt, [rows, cols]), _arr(w, dt, [cols])
         mu, rs = _arr(mean, dt, [rows])[:, None], _arr(rstd, dt, [rows])[:, None]
@@ -295,8 +296,9 @@ class FakeDevice(object):
         dxh = G * W
         _arr(dx, dt, [rows, cols])[...] = rs * (dxh - dxh.mean(axis=1, keepdims=True)
                                                 - xh * (dxh * xh).mean(axis=1, keepdims=True))
-        _arr(dw, dt, [cols])[...] = (G * xh).sum(axis=0)
-        _arr(db, dt, [cols])[...] = G.sum(axis=0)
+        DW, DB = _arr(dw, dt, [cols]), _arr(db, dt, [cols])
+        DW[...] = (DW if accumulate else 0) + (G * xh).sum(axis=0)
+        DB[...] = (DB if accumulate else 0) + G.sum(axis=0)
 
     # ---- optimizers
     def sgd_step(self, p, g, d, n, lr, mom):
