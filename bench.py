@@ -26,6 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 import numpy as np  # noqa: E402
 
@@ -105,9 +107,10 @@ def make_step(model, opt, dp, light):
         logits = model(ids)
         loss = light.loss.cross_entropy(logits.reshape(-1, model.vocab_size), labels)
         opt.zero_grad()
-        loss.backward()
         if dp is not None:
-            dp.sync_gradients()
+            dp.backward(loss)          # backward with the bucketed gradient all-reduce overlapped
+        else:
+            loss.backward()
         opt.step()
         return loss
     return step

@@ -43,6 +43,11 @@ class Gradients(object):
     # keep ``.grad`` of intermediate (non-leaf) tensors after the walk, as the
     # reference does.  Trainers may switch it off to release memory early.
     retain_intermediate = True
+    # optional callable(tensor): invoked by the outermost walk as soon as a leaf has received its last
+    # gradient contribution (lets the data-parallel wrapper start reducing finished gradients while the
+    # rest of backward is still running)
+    leaf_hook = None
+    _walking = 0
 
     @staticmethod
     def disable():
@@ -98,7 +103,17 @@ class Gradients(object):
         """
         order = Gradients._order(ctx)
         keep = Gradients.retain_intermediate if retain is None else retain
+        hook = Gradients.leaf_hook if Gradients._walking == 0 else None
+        pending = None
+        if hook is not None:
+            # number of graph nodes that still owe each leaf a contribution
+            pending = {}
+            for node, _ in order:
+                for t in node.parent_tensors:
+                    if t.ctx is None:
+                        pending[id(t)] = pending.get(id(t), 0) + 1
         Gradients._depth += 1
+        Gradients._walking += 1
         try:
             for node, owner in order:
                 g = grad if owner is None else owner.grad
@@ -113,6 +128,15 @@ class Gradients(object):
                     owner._drop_grad()
                     g._temp = True
                 node._backpropagate(g)
+                if pending is not None:
+                    for t in node.parent_tensors:
+                        k = id(t)
+                        if k in pending:
+                            pending[k] -= 1
+                            if pending[k] == 0:
+                                del pending[k]
+                                hook(t)
         finally:
+            Gradients._walking -= 1
             d = Gradients._depth - 1
             Gradients._depth = d if d > 0 else 0

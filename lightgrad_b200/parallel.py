@@ -129,6 +129,61 @@ class DataParallel(object):
             p.fill(0.0)
             p += p.__class__.from_numpy(new.copy(), requires_grad=False)
 
+    def backward(self, loss, bucket_bytes=64 << 20):
+        """``loss.backward()`` with the gradient exchange overlapped: the flat gradient arena is cut into
+        ~``bucket_bytes`` buckets of consecutive parameters; as soon as the walk has delivered the last
+        contribution to every parameter of a bucket, its all-reduce is queued on the communication
+        stream while the compute stream carries on with the rest of backward.  Backward reaches the
+        parameters in reverse registration order, so buckets complete from the tail of the arena.
+        The optimizer (compute stream) waits for the communication stream at the end."""
+        if self.world == 1 or not self._nccl:
+            loss.backward()
+            self.sync_gradients()
+            return
+        from .autograd import Gradients
+        a, params = self.arena, self.optimizer.parameters
+        a.adopt_grads(params)
+        if getattr(self, '_buckets', None) is None:
+            ends = [o + p.numel() for p, o in zip(params, a.offsets)]
+            ends[-1] = a.total
+            self._bucket_of, self._buckets = [], []      # per param -> bucket; bucket -> [lo, hi, n_params]
+            lo, count = 0, 0
+            for i, hi in enumerate(ends):
+                self._bucket_of.append(len(self._buckets))
+                count += 1
+                if (hi - lo) * 4 >= bucket_bytes or i == len(ends) - 1:
+                    self._buckets.append([lo, hi, count])
+                    lo, count = hi, 0
+            self._index = {id(p): i for i, p in enumerate(params)}
+        remaining = [b[2] for b in self._buckets]
+        launched = [False] * len(self._buckets)
+        api = a.rt.api
+
+        def launch(b):
+            lo, hi, _ = self._buckets[b]
+            launched[b] = True
+            api.nccl_fork()                                   # comm stream waits for the gradients written so far
+            api.nccl_allreduce_f32(a.grad_buf.ptr + lo * 4, hi - lo, 1, 1)
+
+        def leaf_done(t):
+            i = self._index.get(id(t))
+            if i is None:
+                return
+            b = self._bucket_of[i]
+            remaining[b] -= 1
+            if remaining[b] == 0 and not launched[b]:
+                launch(b)
+        prev = Gradients.leaf_hook
+        Gradients.leaf_hook = leaf_done
+        try:
+            loss.backward()
+        finally:
+            Gradients.leaf_hook = prev
+        for b in range(len(self._buckets)):                   # parameters the loss does not reach
+            if not launched[b]:
+                launch(b)
+        api.nccl_wait()                                       # compute stream waits for every bucket
+
     def sync_gradients(self):
         """Average ``.grad`` of every parameter over the ranks (in place)."""
         if self.world == 1:

@@ -41,3 +41,25 @@ def test_walker_visits_shared_nodes_once():
     (h.exp() + h).sum().backward()
     hn = np.tanh(np.linspace(-1, 1, 7))
     np.testing.assert_allclose(x.grad.numpy(), (np.exp(hn) + 1) * (1 - hn ** 2), rtol=1e-5)
+
+
+def test_leaf_hook_fires_after_last_contribution():
+    # the data-parallel wrapper relies on this to start reducing finished gradients during backward
+    from lightgrad_b200.autograd import Gradients
+    a = CpuTensor.from_numpy(np.ones((3, 3), dtype=np.float32))
+    b = CpuTensor.from_numpy(np.ones((3, 3), dtype=np.float32))
+    seen = []
+
+    def hook(t):
+        seen.append((t is a, t.grad.numpy().copy()))
+    y = ((a * b) + a.exp() + a).sum()        # a has three consumers, b one
+    a.zero_grad(), b.zero_grad()
+    Gradients.leaf_hook = hook
+    try:
+        y.backward()
+    finally:
+        Gradients.leaf_hook = None
+    assert len(seen) == 2
+    for is_a, g in seen:
+        want = (1 + np.e + 1) if is_a else 1.0
+        np.testing.assert_allclose(g, want, rtol=1e-6)      # complete at the time the hook ran
