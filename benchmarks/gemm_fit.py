@@ -11,8 +11,10 @@ from lightgrad_b200.autograd.cuda.graph import StepGraph
 ops.set_matmul_mode('tf32')
 rs = np.random.RandomState(0)
 REP = 40
-for (M, N) in ((4096, 768), (4096, 3072), (768, 768), (4096, 2304)):
-    for K in (32, 128, 256, 768, 1536, 3072, 4096):
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or \
+    [(M, N, K) for (M, N) in ((4096, 768), (4096, 3072), (768, 768), (4096, 2304)) for K in (32, 128, 256, 768, 1536, 3072, 4096)]
+for (M, N, K) in SHAPES:
+    if True:
         a = T.from_numpy(rs.uniform(-1, 1, (M, K)).astype(np.float32))
         w = T.from_numpy(rs.uniform(-1, 1, (N, K)).astype(np.float32))
         outs = []

@@ -337,15 +337,10 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
                                                          const float* __restrict__ rstd, const float* __restrict__ g,
                                                          float* __restrict__ dx, float* __restrict__ dgamma_part,
                                                          float* __restrict__ dbeta_part, int64_t rows, int cols) {
+    // 8 warps x cols floats: every warp parks its register partials here, then columns are summed over warps
     extern __shared__ unsigned char smem_raw[];
-    float* sg = reinterpret_cast<float*>(smem_raw);
-    float* sb = sg + cols;
-    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
-        sg[j] = 0.f;
-        sb[j] = 0.f;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inv = 1.0f / (float)cols;
@@ -397,20 +392,31 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
             }
         }
     }
+    float4* mine = reinterpret_cast<float4*>(stage + (size_t)warp * cols);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int c = lane + 32 * j;
-        if (c < nchunks) {
-            atomicAdd(&sg[4 * c + 0], ag[j].x); atomicAdd(&sg[4 * c + 1], ag[j].y);
-            atomicAdd(&sg[4 * c + 2], ag[j].z); atomicAdd(&sg[4 * c + 3], ag[j].w);
-            atomicAdd(&sb[4 * c + 0], ab[j].x); atomicAdd(&sb[4 * c + 1], ab[j].y);
-            atomicAdd(&sb[4 * c + 2], ab[j].z); atomicAdd(&sb[4 * c + 3], ab[j].w);
-        }
+        if (c < nchunks) mine[c] = ag[j];
     }
     __syncthreads();
     for (int j = threadIdx.x; j < cols; j += blockDim.x) {
-        dgamma_part[(int64_t)blockIdx.x * cols + j] = sg[j];
-        dbeta_part[(int64_t)blockIdx.x * cols + j] = sb[j];
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += stage[(size_t)w * cols + j];
+        dgamma_part[(int64_t)blockIdx.x * cols + j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nchunks) mine[c] = ab[j];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += stage[(size_t)w * cols + j];
+        dbeta_part[(int64_t)blockIdx.x * cols + j] = v;
     }
 }
 
@@ -568,7 +574,7 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
     const int nv = ln_nv(cols);
     const bool fast = dtype == LG_F32 && nv && aligned16(x) && aligned16(g) && aligned16(dx) && aligned16(gamma);
     if (fast) {
-        int64_t cap2 = (int64_t)sm_count() * 4;   // ~1 row per warp: memory-level parallelism over register reuse
+        int64_t cap2 = (int64_t)sm_count() * 2;
         grid = (int)(blocks < cap2 ? blocks : cap2);
     }
     void* part = tmp_alloc(2 * (size_t)grid * cols * es);
@@ -576,8 +582,9 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
     void* pg = part;
     void* pb = (char*)part + (size_t)grid * cols * es;
     if (fast) {
+        const size_t smem_fast = 8 * (size_t)cols * sizeof(float);   // <= 32 KB for cols <= 1024
 #define LN_B(NV_)                                                                                              \
-    ln_bwd_vec_kernel<NV_><<<grid, 256, smem, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean, \
+    ln_bwd_vec_kernel<NV_><<<grid, 256, smem_fast, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean, \
                                                           (const float*)rstd, (const float*)g, (float*)dx,     \
                                                           (float*)pg, (float*)pb, rows, (int)cols)
         if (nv == 2) LN_B(2); else if (nv == 4) LN_B(4); else if (nv == 6) LN_B(6); else LN_B(8);

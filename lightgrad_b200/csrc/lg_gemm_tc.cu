@@ -819,7 +819,10 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches) {
     Plan best{};
     double best_score = -1.0;
     const int cands[4] = {256, 192, 128, 64};
+    static const int force_bn = getenv("LG_GEMM_BN") ? atoi(getenv("LG_GEMM_BN")) : 0;        // tuning knobs
+    static const int force_splits = getenv("LG_GEMM_SPLITS") ? atoi(getenv("LG_GEMM_SPLITS")) : 0;
     for (int bn : cands) {
+        if (force_bn && bn != force_bn) continue;
         if (bn > 64 && N <= bn / 2) continue;            // mostly padding
         const int tm = (int)((M + BM - 1) / BM), tn = (int)((N + bn - 1) / bn);
         const int tiles = tm * tn * (int)batches;
@@ -831,6 +834,7 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches) {
             if (splits > 16) splits = 16;
             if (splits < 1) splits = 1;
         }
+        if (force_splits && batches == 1) splits = force_splits < kblocks ? force_splits : kblocks;
         int kper = (kblocks + splits - 1) / splits;
         splits = (kblocks + kper - 1) / kper;
         const int items = tiles * splits;

@@ -109,9 +109,13 @@ __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __restrict__ out, int64_t rlen,
                                                 int64_t inner, int64_t ld, int64_t chunk, int S, int64_t ntiles,
-                                                T scale, int acc_out) {
+                                                T scale, int acc_out, T* __restrict__ final_out,
+                                                unsigned int* __restrict__ tickets) {
+    // final_out != nullptr (S > 1): `out` holds the per-chunk partials and the LAST CTA to finish a column
+    // tile (ticket counter) sums them in chunk order into final_out -- one launch, still deterministic
     using VT = Vec<T, V>;
     __shared__ T sm[8][32 * V + 1];
+    __shared__ int s_last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t tile = blockIdx.x % ntiles;
     const int64_t rest = blockIdx.x / ntiles;
@@ -153,9 +157,44 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
         int64_t gc = tile * 32 * V + c;
         if (gc < inner) {
             T* dst = out + (o * S + part) * inner + gc;
-            *dst = acc_out ? *dst + v * scale : v * scale;
+            if (final_out) *dst = v;
+            else *dst = acc_out ? *dst + v * scale : v * scale;
         }
     }
+    if (final_out == nullptr) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(&tickets[o * ntiles + tile], 1u);
+        s_last = (t == (unsigned int)(S - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < 32 * V; c += 256) {
+        int64_t gc = tile * 32 * V + c;
+        if (gc >= inner) continue;
+        T v = R::template init<T>();
+        for (int pp = 0; pp < S; ++pp) v = R::template comb<T>(v, __ldcg(out + (o * S + pp) * inner + gc));
+        T* dst = final_out + o * inner + gc;
+        *dst = acc_out ? *dst + v * scale : v * scale;
+    }
+    if (threadIdx.x == 0) tickets[o * ntiles + tile] = 0;   // ready for the next launch
+}
+
+// ticket counters of the single-launch column reduction (zeroed once; every launch leaves them zero)
+constexpr int64_t kTicketSlots = 16384;
+unsigned int* ticket_buffer() {
+    static unsigned int* buf = nullptr;
+    if (!buf) {
+        if (cudaMalloc(&buf, kTicketSlots * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError();
+            buf = nullptr;
+            return nullptr;
+        }
+        cudaMemsetAsync(buf, 0, kTicketSlots * sizeof(unsigned int), stream());
+    }
+    return buf;
 }
 
 template <class R, typename T>
@@ -231,8 +270,17 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
     }
     T sc = (S > 1) ? T(1) : scale;
     int grid = (int)(ntiles * outer * S);
-    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out);
-    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out);
+    unsigned int* tickets = (S > 1 && ntiles * outer <= kTicketSlots) ? ticket_buffer() : nullptr;
+    if (tickets) {
+        // single launch: partials + last-CTA final pass
+        if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, scale, acc_out, out, tickets);
+        else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, scale, acc_out, out, tickets);
+        LG_CHECK_LAUNCH();
+        tmp_free(partial);
+        return 0;
+    }
+    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out, (T*)nullptr, nullptr);
+    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out, (T*)nullptr, nullptr);
     LG_CHECK_LAUNCH();
     if (S > 1) {
         int rc = reduce_impl<R, T>(partial, out, outer, S, inner, scale, 0, acc_out);
