@@ -142,6 +142,16 @@ def main():
                     emit(suite='gemm', impl='cpu-openblas', M=M, N=N, K=K, ms=round(dt * 1e3, 2),
                          tflops=round(2.0 * M * N * K / dt / 1e12, 3), cores=os.cpu_count())
                 del a, w
+            # batched attention shapes of BASELINE config 3: (384, 128, 64) x (384, 64, 128) and P @ V
+            for (Bt, M, K, N) in ((384, 128, 64, 128), (384, 128, 128, 64)):
+                a = T.from_numpy(rs.uniform(-1, 1, (Bt, M, K)).astype(np.float32))
+                b = T.from_numpy(rs.uniform(-1, 1, (Bt, K, N)).astype(np.float32))
+                with light.no_grad():
+                    ms = time_gpu(lambda: ops._gemm(a, b), max(3, args.iters // 2))
+                tf = 2.0 * Bt * M * N * K / ms / 1e9
+                emit(suite='gemm', mode=mode, batch=Bt, M=M, N=N, K=K, ms=round(ms, 4), tflops=round(tf, 2),
+                     note='host-dispatch bound at this size; see gemm_fit.py for device time')
+                del a, b
             ops.set_matmul_mode('fp32')
 
 

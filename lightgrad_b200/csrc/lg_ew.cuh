@@ -81,54 +81,68 @@ __global__ void __launch_bounds__(256) ew_ndvec_kernel(const T* __restrict__ a, 
                                                        const T* __restrict__ c, T* __restrict__ out, EwShape s,
                                                        int64_t total_vecs, T alpha) {
     using VT = Vec<T, V>;
+    constexpr int U = 4;   // independent vectors in flight per thread
     const int nd = s.ndim;
     const I inner_vecs = (I)(s.shape[nd - 1] / V);
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_vecs;
-         w += (int64_t)gridDim.x * blockDim.x) {
-        I rest = (I)w;
-        I iv = rest % inner_vecs;
-        rest /= inner_vecs;
-        int64_t oa = (int64_t)iv * V * s.st[0][nd - 1];
-        int64_t ob = NIN > 1 ? (int64_t)iv * V * s.st[1][nd - 1] : 0;
-        int64_t oc = NIN > 2 ? (int64_t)iv * V * s.st[2][nd - 1] : 0;
-        int64_t oo = (int64_t)iv * V;
-        for (int d = nd - 2; d >= 0; --d) {
-            I dim = (I)s.shape[d];
-            I q = rest / dim;
-            I r = rest - q * dim;
-            rest = q;
-            oa += (int64_t)r * s.st[0][d];
-            if (NIN > 1) ob += (int64_t)r * s.st[1][d];
-            if (NIN > 2) oc += (int64_t)r * s.st[2][d];
-            oo += (int64_t)r * s.st[3][d];
-        }
-        VT ra, rb, rc, r;
-        if (s.st[0][nd - 1] == 1) ra = *reinterpret_cast<const VT*>(a + oa);
-        else {
-            T x = a[oa];
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total_vecs; w0 += U * nthreads) {
+        VT ra[U], rb[U], rc[U];
+        int64_t oo[U];
+        bool live[U];
 #pragma unroll
-            for (int k = 0; k < V; ++k) ra.v[k] = x;
-        }
-        if (NIN > 1) {
-            if (s.st[1][nd - 1] == 1) rb = *reinterpret_cast<const VT*>(b + ob);
+        for (int u = 0; u < U; ++u) {
+            const int64_t w = w0 + u * nthreads;
+            live[u] = w < total_vecs;
+            if (!live[u]) continue;
+            I rest = (I)w;
+            I iv = rest % inner_vecs;
+            rest /= inner_vecs;
+            int64_t oa = (int64_t)iv * V * s.st[0][nd - 1];
+            int64_t ob = NIN > 1 ? (int64_t)iv * V * s.st[1][nd - 1] : 0;
+            int64_t oc = NIN > 2 ? (int64_t)iv * V * s.st[2][nd - 1] : 0;
+            oo[u] = (int64_t)iv * V;
+            for (int d = nd - 2; d >= 0; --d) {
+                I dim = (I)s.shape[d];
+                I q = rest / dim;
+                I r = rest - q * dim;
+                rest = q;
+                oa += (int64_t)r * s.st[0][d];
+                if (NIN > 1) ob += (int64_t)r * s.st[1][d];
+                if (NIN > 2) oc += (int64_t)r * s.st[2][d];
+                oo[u] += (int64_t)r * s.st[3][d];
+            }
+            if (s.st[0][nd - 1] == 1) ra[u] = *reinterpret_cast<const VT*>(a + oa);
             else {
-                T x = b[ob];
+                T x = a[oa];
 #pragma unroll
-                for (int k = 0; k < V; ++k) rb.v[k] = x;
+                for (int k = 0; k < V; ++k) ra[u].v[k] = x;
+            }
+            if (NIN > 1) {
+                if (s.st[1][nd - 1] == 1) rb[u] = *reinterpret_cast<const VT*>(b + ob);
+                else {
+                    T x = b[ob];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) rb[u].v[k] = x;
+                }
+            }
+            if (NIN > 2) {
+                if (s.st[2][nd - 1] == 1) rc[u] = *reinterpret_cast<const VT*>(c + oc);
+                else {
+                    T x = c[oc];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) rc[u].v[k] = x;
+                }
             }
         }
-        if (NIN > 2) {
-            if (s.st[2][nd - 1] == 1) rc = *reinterpret_cast<const VT*>(c + oc);
-            else {
-                T x = c[oc];
 #pragma unroll
-                for (int k = 0; k < V; ++k) rc.v[k] = x;
-            }
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            VT r;
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                r.v[k] = Op::apply(ra[u].v[k], NIN > 1 ? rb[u].v[k] : T(0), NIN > 2 ? rc[u].v[k] : T(0), alpha);
+            *reinterpret_cast<VT*>(out + oo[u]) = r;
         }
-#pragma unroll
-        for (int k = 0; k < V; ++k)
-            r.v[k] = Op::apply(ra.v[k], NIN > 1 ? rb.v[k] : T(0), NIN > 2 ? rc.v[k] : T(0), alpha);
-        *reinterpret_cast<VT*>(out + oo) = r;
     }
 }
 
@@ -262,7 +276,7 @@ int ew_launch(const void* a_, const void* b_, const void* c_, void* out_, const 
     }
     if (vec) {
         int64_t tv = total / V;
-        int grid = grid_for(tv, 256, 8);
+        int grid = grid_for((tv + 3) / 4, 256, 8);
         if (small)
             ew_ndvec_kernel<Op, T, NIN, V, uint32_t><<<grid, 256, 0, stream()>>>(a, b, c, out, s, tv, alpha);
         else

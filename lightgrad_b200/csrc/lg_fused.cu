@@ -420,6 +420,89 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
     }
 }
 
+// softmax rows of <= 1024 floats (attention: 128): one warp per row, row in registers, 128-bit accesses
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_fwd_vec_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                              int64_t rows, int cols, float scale) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nchunks = cols >> 2;
+    for (; row < rows; row += row_step) {
+        const float4* p = reinterpret_cast<const float4*>(x + row * cols);
+        float4 v[NV];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                v[j] = p[c];
+                v[j].x *= scale; v[j].y *= scale; v[j].z *= scale; v[j].w *= scale;
+                m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+            }
+        }
+        m = warp_max(m);
+        float ssum = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                v[j].x = expf(v[j].x - m); v[j].y = expf(v[j].y - m);
+                v[j].z = expf(v[j].z - m); v[j].w = expf(v[j].w - m);
+                ssum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            }
+        }
+        ssum = warp_sum(ssum);
+        float4* q = reinterpret_cast<float4*>(y + row * cols);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                float4 r;
+                r.x = v[j].x / ssum; r.y = v[j].y / ssum; r.z = v[j].z / ssum; r.w = v[j].w / ssum;
+                q[c] = r;
+            }
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_bwd_vec_kernel(const float* __restrict__ y, const float* __restrict__ g,
+                                                              float* __restrict__ dx, int64_t rows, int cols,
+                                                              float scale) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nchunks = cols >> 2;
+    for (; row < rows; row += row_step) {
+        const float4* py = reinterpret_cast<const float4*>(y + row * cols);
+        const float4* pg = reinterpret_cast<const float4*>(g + row * cols);
+        float4 yv[NV], gv[NV];
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                yv[j] = py[c];
+                gv[j] = pg[c];
+                dot += (yv[j].x * gv[j].x + yv[j].y * gv[j].y) + (yv[j].z * gv[j].z + yv[j].w * gv[j].w);
+            }
+        }
+        dot = warp_sum(dot);
+        float4* pd = reinterpret_cast<float4*>(dx + row * cols);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                float4 r;
+                r.x = scale * (yv[j].x * (gv[j].x - dot)); r.y = scale * (yv[j].y * (gv[j].y - dot));
+                r.z = scale * (yv[j].z * (gv[j].z - dot)); r.w = scale * (yv[j].w * (gv[j].w - dot));
+                pd[c] = r;
+            }
+        }
+    }
+}
+
 inline int ln_nv(int64_t cols) {
     if (cols % 4 != 0 || cols > 1024) return 0;
     const int need = (int)((cols / 4 + 31) / 32);
@@ -429,6 +512,16 @@ inline int ln_nv(int64_t cols) {
 template <typename T>
 int softmax_fwd(const void* x, void* y, int64_t rows, int64_t cols, double scale) {
     if (rows * cols == 0) return 0;
+    if (sizeof(T) == 4 && ln_nv(cols) && aligned16(x) && aligned16(y)) {
+        const int nv = ln_nv(cols);
+        int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 8;
+        const int grid = (int)(blocks < cap ? blocks : cap);
+#define SM_F(NV_) softmax_fwd_vec_kernel<NV_><<<grid, 256, 0, stream()>>>((const float*)x, (float*)y, rows, (int)cols, (float)scale)
+        if (nv == 2) SM_F(2); else if (nv == 4) SM_F(4); else if (nv == 6) SM_F(6); else SM_F(8);
+#undef SM_F
+        LG_CHECK_LAUNCH();
+        return 0;
+    }
     if (cols <= 2048) {
         int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
         softmax_fwd_kernel<T, false><<<(int)(blocks < cap ? blocks : cap), 256, 0, stream()>>>(
@@ -444,6 +537,16 @@ int softmax_fwd(const void* x, void* y, int64_t rows, int64_t cols, double scale
 template <typename T>
 int softmax_bwd(const void* y, const void* g, void* dx, int64_t rows, int64_t cols, double scale) {
     if (rows * cols == 0) return 0;
+    if (sizeof(T) == 4 && ln_nv(cols) && aligned16(y) && aligned16(g) && aligned16(dx)) {
+        const int nv = ln_nv(cols);
+        int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 8;
+        const int grid = (int)(blocks < cap ? blocks : cap);
+#define SM_B(NV_) softmax_bwd_vec_kernel<NV_><<<grid, 256, 0, stream()>>>((const float*)y, (const float*)g, (float*)dx, rows, (int)cols, (float)scale)
+        if (nv == 2) SM_B(2); else if (nv == 4) SM_B(4); else if (nv == 6) SM_B(6); else SM_B(8);
+#undef SM_B
+        LG_CHECK_LAUNCH();
+        return 0;
+    }
     if (cols <= 2048) {
         int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
         softmax_bwd_kernel<T, false><<<(int)(blocks < cap ? blocks : cap), 256, 0, stream()>>>(

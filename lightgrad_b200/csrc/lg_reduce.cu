@@ -131,6 +131,18 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
     if (col < inner) {
         const T* p = x + o * rlen * ld + col;   // ld = elements between consecutive rows (>= inner)
         int64_t r = beg + ty;
+        for (; r + 56 < end; r += 64) {
+            VT w0 = *reinterpret_cast<const VT*>(p + r * ld), w1 = *reinterpret_cast<const VT*>(p + (r + 8) * ld),
+               w2 = *reinterpret_cast<const VT*>(p + (r + 16) * ld), w3 = *reinterpret_cast<const VT*>(p + (r + 24) * ld),
+               w4 = *reinterpret_cast<const VT*>(p + (r + 32) * ld), w5 = *reinterpret_cast<const VT*>(p + (r + 40) * ld),
+               w6 = *reinterpret_cast<const VT*>(p + (r + 48) * ld), w7 = *reinterpret_cast<const VT*>(p + (r + 56) * ld);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                T lo = R::template comb<T>(R::template comb<T>(w0.v[k], w1.v[k]), R::template comb<T>(w2.v[k], w3.v[k]));
+                T hi = R::template comb<T>(R::template comb<T>(w4.v[k], w5.v[k]), R::template comb<T>(w6.v[k], w7.v[k]));
+                acc[k] = R::template comb<T>(acc[k], R::template comb<T>(lo, hi));
+            }
+        }
         for (; r + 24 < end; r += 32) {
             VT v0 = *reinterpret_cast<const VT*>(p + r * ld), v1 = *reinterpret_cast<const VT*>(p + (r + 8) * ld),
                v2 = *reinterpret_cast<const VT*>(p + (r + 16) * ld),

@@ -268,3 +268,17 @@ def test_gradient_descent_example(device):
 def test_same_type_assertion(device):
     with pytest.raises(AssertionError):
         CudaTensor.ones((2, 2)).add(CpuTensor.ones((2, 2)))
+
+
+def test_profiler_accounts_ops(device):
+    # utils/profiler.py of the reference: per-op forward/backward time and call counts; on the device the
+    # tracker drains the stream so asynchronous launches are billed to the op that issued them
+    from lightgrad_b200.autograd.utils.profiler import Profiler
+    x = CudaTensor.from_numpy(np.random.uniform(-1, 1, (64, 64)).astype(np.float32))
+    with Profiler() as p:
+        y = (x.exp() * x).sum()
+        y.backward()
+    table = p.table()
+    assert table['exp'][1] == 1 and table['exp'][3] == 1        # one forward, one backward call
+    assert table['mul'][1] == 1 and table['sum'][1] == 1
+    assert all(v[0] >= 0 and v[2] >= 0 for v in table.values())
