@@ -275,18 +275,47 @@ def main():
     ms_b = comm.max_float(e2.elapsed_ms(e3)) / k_b
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- phase C: per-launch CUDA-event timing of the dominant kernel (matmul) on the same workload
-    k_c = 3
-    rt.gemm_profile(True)
+    # ---- phase C: device time of the dominant kernel (matmul) inside the step.
+    # Event pairs around every launch serialise neighbouring kernels (~9 us per small GEMM), so with graph
+    # replay the matmul time is measured by ablation instead: the same step is captured a second time with
+    # lg_gemm launching nothing (lg_prof_gemm(2); values are garbage, the other kernels and their order are
+    # identical) and both graphs are timed with CUDA events on the compute stream; the difference is what
+    # the matmul launches cost inside the replayed step.  (--eager: event pairs around every launch, the
+    # step queued behind a stream delay so the events see no host dispatch latency.)
+    k_c = 5
     rt.gemm_profile_read()
-    e4 = rt.Event().record()
-    for _ in range(k_c):
+    if args.eager:
+        rt.gemm_profile(1)
+        rt.synchronize()
+        rt.api.stream_delay_us(int(3 * eager_ms * 1000) + 20000)
+        e4 = rt.Event().record()
         step(ids_d, lab_d)
-    e5 = rt.Event().record()
-    e5.synchronize()
-    gemm_ms, gemm_launches, gemm_flops = rt.gemm_profile_read()
+        e5 = rt.Event().record()
+        e5.synchronize()
+        gemm_ms, gemm_launches, gemm_flops = rt.gemm_profile_read()
+        step_ms_c = e4.elapsed_ms(e5)
+        roof_how = ('CUDA events on the compute stream around every lg_gemm launch of one extra step queued behind '
+                    'a stream delay (no host dispatch latency inside the events)')
+    else:
+        def timed(replay):
+            rt.synchronize()
+            t0 = rt.Event().record()
+            for _ in range(k_c):
+                replay()
+            t1 = rt.Event().record()
+            t1.synchronize()
+            return comm.max_float(t0.elapsed_ms(t1)) / k_c
+        step_ms_c = timed(sg.replay)
+        rt.gemm_profile(2)
+        sg_nogemm = StepGraph(lambda: step(ids_d, lab_d), warmup=0)
+        _, gemm_launches, gemm_flops = rt.gemm_profile_read()
+        rt.gemm_profile(0)
+        nogemm_ms = timed(sg_nogemm.replay)
+        gemm_ms = max(step_ms_c - nogemm_ms, 1e-6)
+        roof_how = ('ablation inside the replayed CUDA graph: %d replays of the step (%.3f ms) minus %d replays of the '
+                    'same captured step with the lg_gemm launches removed (%.3f ms), both timed with CUDA events on '
+                    'the compute stream right after the timed region' % (k_c, step_ms_c, k_c, nogemm_ms))
     rt.gemm_profile(False)
-    step_ms_c = e4.elapsed_ms(e5) / k_c
     if rank != 0:
         finish(comm)
 
@@ -294,6 +323,7 @@ def main():
     value = global_batch / (ms_a / 1e3)
     e2e = global_batch / (ms_b / 1e3)
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    k_c = 1   # gemm_ms / gemm_launches / gemm_flops are per step from here on
     if mode == 'bf16':
         peak_tf, peak_name = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']), 'measured cuBLAS bf16 (sustained)'
     elif mode == 'tf32':
@@ -319,8 +349,7 @@ def main():
                      'launches_per_step': gemm_launches // k_c, 'kernel_ms_per_step': round(gemm_ms / k_c, 3),
                      'kernel_share_of_step': round(gemm_ms / k_c / step_ms_c, 3),
                      'algorithmic_flops_per_step': gemm_flops / k_c,
-                     'how': 'CUDA events on the compute stream around every lg_gemm launch over %d extra steps of '
-                            'the same workload right after the timed region' % k_c},
+                     'how': roof_how},
         'mfu_vs_measured_bf16': round(GEMM_FLOPS_PER_SAMPLE * value / 1e12 / peaks['bf16_tflops'], 4),
     }
     if args.gpus == 1 and not args.no_cpu_baseline:

@@ -121,6 +121,9 @@ int lg_event_destroy(void* ev);
 int lg_launch_count(uint64_t* n);         /* kernels launched by this library so far */
 void* lg_stream_handle(void);             /* cudaStream_t of the compute stream, for profilers */
 int lg_profiler_range(int start);
+/* keeps the compute stream busy for `us` microseconds (measurement aid: work queued behind it runs back
+ * to back on the device, so events between kernels are free of host dispatch latency) */
+int lg_stream_delay_us(uint64_t us);
 /* whole-step CUDA graphs: everything enqueued between begin and end (kernels, memsets, NCCL calls)
  * is recorded instead of executed; allocations made meanwhile come from a pool private to the
  * graph (*pool_id: 0 = create one, reused by later re-captures).  lg_graph_launch replays the step
@@ -172,9 +175,12 @@ typedef struct LgGemmDesc {
 } LgGemmDesc;
 int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c,
             const void* bias, int accumulate);
-/* per-launch timing of lg_gemm with CUDA events on the compute stream (off by default):
- * lg_prof_gemm(1) starts collecting, lg_prof_gemm_read drains the stream and returns the summed
- * kernel time, the number of launches and their algorithmic flops (2*M*N*K*batch) since the last read */
+/* measurement hooks for the matmul share of a step (off by default):
+ * lg_prof_gemm(1): CUDA events on the compute stream around every lg_gemm launch;
+ * lg_prof_gemm(2): lg_gemm launches NOTHING and only counts -- timing a captured step with and without its
+ *                  matmuls gives their cost inside the replayed step (results are garbage in this mode);
+ * lg_prof_gemm_read drains the stream and returns the summed event time (mode 1), the number of launches
+ * and their algorithmic flops (2*M*N*K*batch) since the last read */
 int lg_prof_gemm(int enable);
 int lg_prof_gemm_read(double* total_ms, uint64_t* launches, double* total_flops);
 /* 1 if the tensor-core kernel can take this problem in `mode` without a fallback */

@@ -61,6 +61,7 @@ _SIGNATURES = {
     'lg_event_destroy': [_vp],
     'lg_launch_count': [C.POINTER(C.c_uint64)],
     'lg_profiler_range': [C.c_int],
+    'lg_stream_delay_us': [C.c_uint64],
     'lg_graph_begin': [C.POINTER(C.c_int)],
     'lg_graph_end': [C.POINTER(_vp), C.POINTER(C.c_uint64)],
     'lg_graph_abort': [],
@@ -173,8 +174,9 @@ def launch_count():
     return n.value
 
 
-def gemm_profile(enable):
-    ensure_device().prof_gemm(1 if enable else 0)
+def gemm_profile(mode):
+    """0 / False: off; 1 / True: event pair around every lg_gemm launch; 2: count only, launch nothing."""
+    ensure_device().prof_gemm(int(mode))
 
 
 def gemm_profile_read():

@@ -155,7 +155,27 @@ int ensure_init() { return do_init(-1); }
 
 using namespace lg;
 
+namespace {
+// occupies the compute stream for `ns` nanoseconds: lets the host queue a whole step behind it, so that
+// CUDA events recorded between the queued kernels time the kernels and not the host's dispatch latency
+__global__ void spin_kernel(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+}  // namespace
+
 extern "C" {
+
+int lg_stream_delay_us(uint64_t us) {
+    LG_INIT();
+    LG_REQUIRE(us <= 2000000, "lg_stream_delay_us: at most 2 s");
+    spin_kernel<<<1, 1, 0, g_stream>>>((unsigned long long)us * 1000ull);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
 
 const char* lg_last_error(void) { return g_err; }
 

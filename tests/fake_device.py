@@ -98,6 +98,7 @@ class FakeDevice(object):
     def sync(self): pass
     def empty_cache(self): pass
     def profiler_range(self, start): pass
+    def stream_delay_us(self, us): pass
 
     # graphs: the double executes eagerly while 'capturing' and re-runs the recorded python thunk on replay
     def graph_begin(self, pool): pool._obj.value = 1

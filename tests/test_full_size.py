@@ -1,0 +1,135 @@
+"""Parity at BASELINE.json's full sizes, where the oracle is too slow to run element by element on every
+case: exact comparisons where IEEE arithmetic makes them exact, and size-independent properties elsewhere
+(rows of a softmax sum to one, a sum of partial sums equals the full sum, gather -> scatter-add round trips,
+matmul linearity, DP-style batch splitting of a mean loss)."""
+import numpy as np
+import pytest
+import lightgrad_b200 as light
+from lightgrad_b200 import CudaTensor
+from lightgrad_b200.autograd.cuda import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _dev(cuda):
+    yield
+
+
+def test_elementwise_2pow26_exact_against_numpy():
+    rs = np.random.RandomState(0)
+    n = 1 << 26
+    a = rs.uniform(-1, 1, n).astype(np.float32)
+    b = rs.uniform(-1, 1, n).astype(np.float32)
+    A, B = CudaTensor.from_numpy(a), CudaTensor.from_numpy(b)
+    with light.no_grad():
+        np.testing.assert_array_equal((A + B).numpy(), a + b)          # IEEE add / mul: bit-exact
+        np.testing.assert_array_equal((A * B).numpy(), a * b)
+        np.testing.assert_array_equal(A.relu().numpy(), np.maximum(a, 0))
+        np.testing.assert_allclose(A.exp().numpy(), np.exp(a), rtol=1e-6)
+        bias = rs.uniform(-1, 1, 1024).astype(np.float32)
+        np.testing.assert_array_equal((A.reshape(-1, 1024) + CudaTensor.from_numpy(bias)).numpy(),
+                                      a.reshape(-1, 1024) + bias)
+
+
+def test_reductions_2pow26_any_axis():
+    rs = np.random.RandomState(1)
+    x = rs.uniform(-1, 1, (8192, 8192)).astype(np.float32)
+    X = CudaTensor.from_numpy(x)
+    x64 = x.astype(np.float64)
+    with light.no_grad():
+        for axis in (None, 0, 1):
+            got = X.sum(axis=axis).numpy()
+            want = x64.sum(axis=axis)
+            np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6 * np.abs(x64).sum(axis=axis).max())
+            np.testing.assert_array_equal(X.max(axis=axis).numpy(), x.max(axis=axis))      # exact
+            np.testing.assert_array_equal(X.min(axis=axis).numpy(), x.min(axis=axis))
+        # a checksum of checksums: reducing in two steps must agree with one step
+        # (the total is ~1e3 while the summed magnitudes are ~3e7: hold the difference to 1e-7 of the latter)
+        assert abs(X.sum(axis=0).sum().item() - X.sum().item()) <= 1e-7 * np.abs(x64).sum()
+
+
+def test_matmul_4096_cubed_rows_and_linearity():
+    rs = np.random.RandomState(2)
+    a = rs.uniform(-1, 1, (4096, 4096)).astype(np.float32)
+    b = rs.uniform(-1, 1, (4096, 4096)).astype(np.float32)
+    A, B = CudaTensor.from_numpy(a), CudaTensor.from_numpy(b)
+    rows = rs.choice(4096, 16, replace=False)
+    want = a[rows].astype(np.float64) @ b.astype(np.float64)
+    for mode, tol in (('fp32', 1e-5), ('tf32', 5e-3)):
+        prev = ops.set_matmul_mode(mode)
+        try:
+            with light.no_grad():
+                c = (A @ B)
+                got = c.numpy()[rows]
+                assert np.abs(got - want).max() <= tol * np.abs(want).max(), mode
+                # linearity: (2A) @ B == 2 (A @ B) exactly (scaling by 2 commutes with every rounding)
+                c2 = ((A * 2.0) @ B)
+                np.testing.assert_array_equal(c2.numpy()[rows], 2 * got)
+        finally:
+            ops.set_matmul_mode(prev)
+
+
+def test_softmax_and_cross_entropy_at_vocab_size():
+    rs = np.random.RandomState(3)
+    logits = rs.uniform(-4, 4, (512, 30522)).astype(np.float32)
+    labels = rs.randint(0, 30522, size=(512,)).astype(np.int32)
+    L = CudaTensor.from_numpy(logits)
+    with light.no_grad():
+        p = L.softmax(axis=-1).numpy()
+    np.testing.assert_allclose(p.sum(axis=1), 1.0, rtol=1e-5)
+    loss = light.loss.cross_entropy(L, CudaTensor.from_numpy(labels, requires_grad=False))
+    loss.backward()
+    z = logits.astype(np.float64)
+    lse = np.log(np.exp(z - z.max(axis=1, keepdims=True)).sum(axis=1)) + z.max(axis=1)
+    want = (lse - z[np.arange(512), labels]).mean()
+    assert abs(loss.item() - want) <= 1e-5 * abs(want)
+    g = L.grad.numpy()
+    np.testing.assert_allclose(g.sum(axis=1), 0.0, atol=1e-7)          # (softmax - onehot) rows sum to zero
+    assert (g[np.arange(512), labels] < 0).all()
+
+
+def test_embedding_gather_scatter_roundtrip_bert_sizes():
+    rs = np.random.RandomState(4)
+    table = rs.uniform(-1, 1, (30522, 768)).astype(np.float32)
+    ids = rs.randint(0, 30522, size=(32, 128)).astype(np.int32)
+    W = CudaTensor.from_numpy(table)
+    out = W[CudaTensor.from_numpy(ids, requires_grad=False)]
+    np.testing.assert_array_equal(out.numpy(), table[ids])                # gather is bit-exact
+    W.zero_grad()
+    out.sum().backward()
+    counts = np.bincount(ids.reshape(-1), minlength=30522).astype(np.float32)
+    np.testing.assert_array_equal(W.grad.numpy()[:, 0], counts)           # scatter-ADD: duplicates accumulate
+    np.testing.assert_array_equal(W.grad.numpy()[:, 767], counts)
+
+
+def test_bert_base_full_size_step_is_sane_and_batch_splits_average():
+    # full BERT-base, batch 8: the loss starts at ~ln(V); gradients of a batch equal the mean of the
+    # gradients of its two halves (the identity the data-parallel wrapper relies on)
+    from examples import bert
+    np.random.seed(0)
+    model = bert.BertForMaskedLM(**bert.BERT_BASE)
+    ids, labels = bert.synthetic_batch(8, 128, 30522)
+    prev = ops.set_matmul_mode('tf32')
+    try:
+        def grads(lo, hi):
+            for p in model.parameters():
+                p.zero_grad()
+            logits = model(CudaTensor.from_numpy(ids[lo:hi], requires_grad=False))
+            loss = light.loss.cross_entropy(logits.reshape(-1, 30522),
+                                            CudaTensor.from_numpy(labels[lo * 128:hi * 128], requires_grad=False))
+            loss.backward()
+            return loss.item(), {n: p.grad.numpy().copy() for n, p in model.named_parameters()
+                                 if n.endswith(('query.weight', 'decoder.weight', 'LayerNorm.bias', 'word_embeddings.weight'))}
+        l_all, g_all = grads(0, 8)
+        l_a, g_a = grads(0, 4)
+        l_b, g_b = grads(4, 8)
+    finally:
+        ops.set_matmul_mode(prev)
+    assert abs(l_all - np.log(30522)) < 0.05
+    assert abs(l_all - 0.5 * (l_a + l_b)) <= 1e-5 * l_all
+    gmax = max(np.abs(v).max() for v in g_all.values())
+    for n in g_all:
+        assert np.isfinite(g_all[n]).all(), n
+        err = np.abs(g_all[n] - 0.5 * (g_a[n] + g_b[n])).max()
+        assert err <= 5e-3 * max(np.abs(g_all[n]).max(), 1e-3 * gmax), n
