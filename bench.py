@@ -298,7 +298,8 @@ def main():
                     'a stream delay (no host dispatch latency inside the events)')
     else:
         def timed(replay):
-            rt.synchronize()
+            replay()
+            barrier()                       # ranks enter the timed replays together
             t0 = rt.Event().record()
             for _ in range(k_c):
                 replay()
