@@ -153,9 +153,11 @@ struct TcParams {
 };
 
 // CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on vertically adjacent output tiles
-// (same N block): each loads its own A tile and HALF of the shared B tile, multicast to both -- L2 -> SM
-// traffic per CTA drops from A + B to A + B/2.  A stage may be refilled only when BOTH consumers have
-// released it, so the MMA warps commit to the `empty` barrier of both CTAs.
+// (same N block): each loads its own A tile and HALF of the shared B tile, multicast to both; a stage may be
+// refilled only when BOTH consumers have released it, so the MMA warps commit to the `empty` barrier of
+// both CTAs.  Measured on B200: no faster than CL = 1 (a 2-CTA multicast does not reduce L2 traffic, and
+// every CTA still stages the whole B tile), so only CL = 1 is instantiated; CTA pairs use the
+// cta_group::2 kernel below, which really halves the B bytes per SM.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -938,14 +940,6 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
             case 192: return launch_2cta_bn<192>(a_mn, b_mn, ma, mb, mc, p, grid);
             case 128: return launch_2cta_bn<128>(a_mn, b_mn, ma, mb, mc, p, grid);
             default: return launch_2cta_bn<64>(a_mn, b_mn, ma, mb, mc, p, grid);
-        }
-    }
-    if (cl == 2) {
-        switch (pl.bn) {
-            case 256: return launch_bn<256, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
-            case 192: return launch_bn<192, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
-            case 128: return launch_bn<128, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
-            default: return launch_bn<64, 2>(a_mn, b_mn, ma, mb, mc, p, grid);
         }
     }
     switch (pl.bn) {
