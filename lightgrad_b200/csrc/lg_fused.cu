@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
                                                      const T* __restrict__ mean, const T* __restrict__ rstd,
                                                      const T* __restrict__ g, T* __restrict__ dx,
                                                      T* __restrict__ dgamma_part, T* __restrict__ dbeta_part,
-                                                     int64_t rows, int64_t cols) {
+                                                     int64_t rows, int64_t cols, int64_t part_ld) {
     extern __shared__ unsigned char smem_raw[];
     T* sg = reinterpret_cast<T*>(smem_raw);  // [cols] dgamma accumulators for this CTA
     T* sb = sg + cols;                        // [cols] dbeta
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
     }
     __syncthreads();
     for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
-        dgamma_part[(int64_t)blockIdx.x * cols + j] = sg[j];
-        dbeta_part[(int64_t)blockIdx.x * cols + j] = sb[j];
+        dgamma_part[(int64_t)blockIdx.x * part_ld + j] = sg[j];
+        dbeta_part[(int64_t)blockIdx.x * part_ld + j] = sb[j];
     }
 }
 
@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
                                                          const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, const float* __restrict__ g,
                                                          float* __restrict__ dx, float* __restrict__ dgamma_part,
-                                                         float* __restrict__ dbeta_part, int64_t rows, int cols) {
+                                                         float* __restrict__ dbeta_part, int64_t rows, int cols,
+                                                         int64_t part_ld) {
     // 8 warps x cols floats: every warp parks its register partials here, then columns are summed over warps
     extern __shared__ unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += stage[(size_t)w * cols + j];
-        dgamma_part[(int64_t)blockIdx.x * cols + j] = v;
+        dgamma_part[(int64_t)blockIdx.x * part_ld + j] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += stage[(size_t)w * cols + j];
-        dbeta_part[(int64_t)blockIdx.x * cols + j] = v;
+        dbeta_part[(int64_t)blockIdx.x * part_ld + j] = v;
     }
 }
 
@@ -682,34 +683,42 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
     }
     void* part = tmp_alloc(2 * (size_t)grid * cols * es);
     if (!part) return 1;
+    // partial rows are [dgamma | dbeta] side by side: when the two gradients are adjacent in memory (LayerNorm's
+    // weight and bias are consecutive parameters of the gradient arena) one column reduction finishes both
+    const int64_t part_ld = 2 * cols;
     void* pg = part;
-    void* pb = (char*)part + (size_t)grid * cols * es;
+    void* pb = (char*)part + (size_t)cols * es;
     if (fast) {
         const size_t smem_fast = 8 * (size_t)cols * sizeof(float);   // <= 32 KB for cols <= 1024
 #define LN_B(NV_)                                                                                              \
     ln_bwd_vec_kernel<NV_><<<grid, 256, smem_fast, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean, \
                                                           (const float*)rstd, (const float*)g, (float*)dx,     \
-                                                          (float*)pg, (float*)pb, rows, (int)cols)
+                                                          (float*)pg, (float*)pb, rows, (int)cols, part_ld)
         if (nv == 2) LN_B(2); else if (nv == 4) LN_B(4); else if (nv == 6) LN_B(6); else LN_B(8);
 #undef LN_B
     } else if (dtype == LG_F32)
         ln_bwd_kernel<float><<<grid, 256, smem, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean,
                                                             (const float*)rstd, (const float*)g, (float*)dx,
-                                                            (float*)pg, (float*)pb, rows, cols);
+                                                            (float*)pg, (float*)pb, rows, cols, part_ld);
     else
         ln_bwd_kernel<double><<<grid, 256, smem, stream()>>>((const double*)x, (const double*)gamma,
                                                              (const double*)mean, (const double*)rstd,
                                                              (const double*)g, (double*)dx, (double*)pg, (double*)pb,
-                                                             rows, cols);
+                                                             rows, cols, part_ld);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         tmp_free(part);
         return set_error("ln_bwd launch failed: %s", cudaGetErrorString(e));
     }
     count_launch();
-    int rc = cols > 1 ? lg_reduce_pitched(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, cols, 1.0, accumulate)
-                      : set_error("lg_layernorm_bwd: cols must be > 1");
-    if (!rc) rc = lg_reduce_pitched(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, cols, 1.0, accumulate);
+    int rc;
+    if (cols <= 1) rc = set_error("lg_layernorm_bwd: cols must be > 1");
+    else if ((char*)dbeta == (char*)dgamma + (size_t)cols * es)
+        rc = lg_reduce_pitched(LG_RED_SUM, dtype, pg, dgamma, 1, grid, 2 * cols, part_ld, 1.0, accumulate);
+    else {
+        rc = lg_reduce_pitched(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, part_ld, 1.0, accumulate);
+        if (!rc) rc = lg_reduce_pitched(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, part_ld, 1.0, accumulate);
+    }
     tmp_free(part);
     return rc;
 }

@@ -282,3 +282,43 @@ def test_profiler_accounts_ops(device):
     assert table['exp'][1] == 1 and table['exp'][3] == 1        # one forward, one backward call
     assert table['mul'][1] == 1 and table['sum'][1] == 1
     assert all(v[0] >= 0 and v[2] >= 0 for v in table.values())
+
+
+def test_cnn_example_matches_cpu_tensor(device):
+    # examples/mnist.py CNN (conv -> max_pool -> relu twice, linear head): forward and every gradient against
+    # the CPU tensor on the same parameters -- exercises conv/pad/pool/getitem/setitem together
+    from examples import mnist as mn
+    with nn.use_tensor(CpuTensor):
+        np.random.seed(3)
+        cpu_model = mn.CNN()
+    dev_model = mn.CNN()
+    dev_model.load_parameters(cpu_model.named_parameters())
+    x = np.random.uniform(0, 1, (4, 1, 28, 28)).astype(np.float32)
+    cy, dy = cpu_model(CpuTensor.from_numpy(x)), dev_model(CudaTensor.from_numpy(x))
+    np.testing.assert_allclose(dy.numpy(), cy.numpy(), rtol=1e-4, atol=1e-6)
+    cy.backward(True)
+    dy.backward(True)
+    for (n, p), (_, q) in zip(cpu_model.named_parameters(), dev_model.named_parameters()):
+        np.testing.assert_allclose(q.grad.numpy(), p.grad.numpy(), rtol=2e-4, atol=2e-6, err_msg=n)
+
+
+def test_optimizers_track_cpu_tensor_over_steps(device):
+    # SGD / momentum / Adam / AdaBelief through the fused arena path vs the generic path on the CPU tensor
+    x = np.random.uniform(-1, 1, (32, 16)).astype(np.float32)
+    t = np.random.uniform(-1, 1, (32, 4)).astype(np.float32)
+    for make in (lambda ps: light.optim.SGD(ps, lr=0.05), lambda ps: light.optim.SGD(ps, lr=0.05, momentum=0.9),
+                 lambda ps: light.optim.Adam(ps, lr=0.01), lambda ps: light.optim.AdaBelief(ps, lr=0.01)):
+        results = []
+        for T in (CpuTensor, CudaTensor):
+            with nn.use_tensor(T):
+                np.random.seed(11)
+                lin = nn.Linear(16, 4)
+            opt = make(lin.parameters())
+            for _ in range(6):
+                loss = light.loss.mse(lin(T.from_numpy(x, requires_grad=False)), T.from_numpy(t, requires_grad=False))
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            results.append([p.numpy() for p in lin.parameters()])
+        for a, b in zip(*results):
+            np.testing.assert_allclose(b, a, rtol=2e-5, atol=2e-6)
