@@ -10,6 +10,7 @@ namespace {
 
 template <typename S, typename D>
 __global__ void __launch_bounds__(256) cast_flat_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+    LG_PDL_TRIGGER();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = (D)src[i];
 }
@@ -17,6 +18,7 @@ __global__ void __launch_bounds__(256) cast_flat_kernel(const S* __restrict__ sr
 template <typename S, typename D>
 __global__ void __launch_bounds__(256) cast_nd_kernel(const S* __restrict__ src, D* __restrict__ dst, EwShape s,
                                                       int64_t total) {
+    LG_PDL_TRIGGER();
     const int nd = s.ndim;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
          w += (int64_t)gridDim.x * blockDim.x) {

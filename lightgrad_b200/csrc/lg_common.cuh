@@ -7,6 +7,12 @@
 #include <stdarg.h>
 #include "../../include/lightgrad_b200.h"
 
+// Programmatic dependent launch: every kernel signals at its very start that a dependent kernel launched
+// with the programmatic-serialisation attribute (the tensor-core GEMMs) may begin its prologue; that kernel
+// executes LG_PDL_WAIT() -- completion and memory flush of everything before it -- before touching memory.
+#define LG_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define LG_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
 namespace lg {
 
 // ---- error plumbing ---------------------------------------------------------------------------

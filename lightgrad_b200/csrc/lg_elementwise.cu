@@ -22,6 +22,7 @@ template <typename T, int KIND, int V>
 __global__ void __launch_bounds__(256) ew_bwd2_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                       const T* __restrict__ g, T* __restrict__ da,
                                                       T* __restrict__ db, int64_t n) {
+    LG_PDL_TRIGGER();
     using VT = Vec<T, V>;
     const int64_t nv = n / V;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

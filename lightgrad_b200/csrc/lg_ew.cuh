@@ -34,6 +34,7 @@ template <class Op, typename T, int NIN, int V>
 __global__ void __launch_bounds__(256) ew_flat_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                       const T* __restrict__ c, T* __restrict__ out, int64_t n,
                                                       T alpha) {
+    LG_PDL_TRIGGER();
     using VT = Vec<T, V>;
     constexpr int U = 4;
     const int64_t nv = n / V;
@@ -80,6 +81,7 @@ template <class Op, typename T, int NIN, int V, typename I>
 __global__ void __launch_bounds__(256) ew_ndvec_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                        const T* __restrict__ c, T* __restrict__ out, EwShape s,
                                                        int64_t total_vecs, T alpha) {
+    LG_PDL_TRIGGER();
     using VT = Vec<T, V>;
     constexpr int U = 4;   // independent vectors in flight per thread
     const int nd = s.ndim;
@@ -151,6 +153,7 @@ template <class Op, typename T, int NIN, typename I>
 __global__ void __launch_bounds__(256) ew_ndany_kernel(const T* __restrict__ a, const T* __restrict__ b,
                                                        const T* __restrict__ c, T* __restrict__ out, EwShape s,
                                                        int64_t total, T alpha) {
+    LG_PDL_TRIGGER();
     const int nd = s.ndim;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
          w += (int64_t)gridDim.x * blockDim.x) {

@@ -65,6 +65,7 @@ __device__ __forceinline__ T block_max(T v, T* sm) {
 template <typename T, bool BLOCK>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,
                                                           int64_t cols, T scale) {
+    LG_PDL_TRIGGER();
     __shared__ T sm[8];
     const int lane = BLOCK ? threadIdx.x : (threadIdx.x & 31);
     const int step = BLOCK ? blockDim.x : 32;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ 
 template <typename T, bool BLOCK>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ y, const T* __restrict__ g,
                                                           T* __restrict__ dx, int64_t rows, int64_t cols, T scale) {
+    LG_PDL_TRIGGER();
     __shared__ T sm[8];
     const int lane = BLOCK ? threadIdx.x : (threadIdx.x & 31);
     const int step = BLOCK ? blockDim.x : 32;
@@ -111,6 +113,7 @@ template <typename T, typename L>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, int64_t ld,
                                                      const L* __restrict__ labels, T* __restrict__ loss_rows,
                                                      T* __restrict__ lse, int64_t rows, int64_t cols) {
+    LG_PDL_TRIGGER();
     __shared__ T sm[8];
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const T* p = x + row * ld;
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, in
                                                      const L* __restrict__ labels, const T* __restrict__ lse,
                                                      const T* __restrict__ gscale, T* __restrict__ dx, int64_t ld_dx,
                                                      int64_t rows, int64_t cols) {
+    LG_PDL_TRIGGER();
     const T gs = gscale[0];
     const T inv_rows = T(rows);
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
                                                      const T* __restrict__ beta, T* __restrict__ y,
                                                      T* __restrict__ mean, T* __restrict__ rstd, int64_t rows,
                                                      int64_t cols, T eps) {
+    LG_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
                                                      const T* __restrict__ g, T* __restrict__ dx,
                                                      T* __restrict__ dgamma_part, T* __restrict__ dbeta_part,
                                                      int64_t rows, int64_t cols, int64_t part_ld) {
+    LG_PDL_TRIGGER();
     extern __shared__ unsigned char smem_raw[];
     T* sg = reinterpret_cast<T*>(smem_raw);  // [cols] dgamma accumulators for this CTA
     T* sb = sg + cols;                        // [cols] dbeta
@@ -271,6 +277,7 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
                                                          const float* __restrict__ beta, float* __restrict__ y,
                                                          float* __restrict__ mean, float* __restrict__ rstd,
                                                          int64_t rows, int cols, float eps) {
+    LG_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
                                                          float* __restrict__ dx, float* __restrict__ dgamma_part,
                                                          float* __restrict__ dbeta_part, int64_t rows, int cols,
                                                          int64_t part_ld) {
+    LG_PDL_TRIGGER();
     // 8 warps x cols floats: every warp parks its register partials here, then columns are summed over warps
     extern __shared__ unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_fwd_vec_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                               int64_t rows, int cols, float scale) {
+    LG_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -471,6 +480,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) softmax_bwd_vec_kernel(const float* __restrict__ y, const float* __restrict__ g,
                                                               float* __restrict__ dx, int64_t rows, int cols,
                                                               float scale) {
+    LG_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;

@@ -16,6 +16,7 @@ template <typename T, int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, const T* __restrict__ bias,
                  LgGemmDesc d, int accumulate, int a_m_fast, int b_n_fast) {
+    LG_PDL_TRIGGER();
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int HM = TM / 2, HN = TN / 2;       // micro-tile halves
     constexpr int LA = BM * BK / NT, LB = BN * BK / NT;  // elements per thread per tile

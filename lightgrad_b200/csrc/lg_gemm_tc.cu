@@ -162,6 +162,7 @@ template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, TcParams p) {
+    LG_PDL_TRIGGER();
     constexpr int B_STAGE_BYTES = BN * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -209,6 +210,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the preceding kernel
+    LG_PDL_WAIT();
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -440,6 +443,7 @@ template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_c, TcParams p) {
+    LG_PDL_TRIGGER();
     constexpr int HB = BN / 2;                          // B rows staged per CTA
     constexpr int B_STAGE_BYTES = HB * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -489,6 +493,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    LG_PDL_WAIT();
 
     if (warp == 0) {
         // ===================================== TMA producer (both CTAs) ===========================
@@ -725,6 +730,11 @@ constexpr size_t smem_for() {
            (2 * stages_for<BN>() + 4) * 8 + 16 + 1024;
 }
 
+inline bool pdl_enabled() {
+    static const bool on = getenv("LG_GEMM_NO_PDL") == nullptr;
+    return on;
+}
+
 template <int BN>
 constexpr int stages2_for() {
     // per-CTA stage = 16 KB of A + BN*64 B of B; keep ~192 KB of operands in flight
@@ -751,13 +761,15 @@ int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream();
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     LG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
     LG_CHECK_LAUNCH();
     return 0;
@@ -787,13 +799,15 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream();
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     LG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
     LG_CHECK_LAUNCH();
     return 0;

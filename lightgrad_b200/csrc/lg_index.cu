@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const W* __restrict__ 
                                                           int64_t row_stride_w, const void* __restrict__ idx,
                                                           int idx_dt, int64_t n_idx, int64_t row_words,
                                                           W* __restrict__ out) {
+    LG_PDL_TRIGGER();
     const int64_t total = n_idx * row_words;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
          w += (int64_t)gridDim.x * blockDim.x) {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) scatter_set_rows_kernel(W* __restrict__ d
                                                                int64_t row_stride_w, const void* __restrict__ idx,
                                                                int idx_dt, int64_t n_idx, int64_t row_words,
                                                                const W* __restrict__ src, W value) {
+    LG_PDL_TRIGGER();
     const int64_t total = n_idx * row_words;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
          w += (int64_t)gridDim.x * blockDim.x) {
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(T* __restrict__ d
                                                                int64_t row_stride, const void* __restrict__ idx,
                                                                int idx_dt, int64_t n_idx, int64_t row_len,
                                                                const T* __restrict__ src) {
+    LG_PDL_TRIGGER();
     const int64_t total = n_idx * row_len;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
          w += (int64_t)gridDim.x * blockDim.x) {
@@ -81,6 +84,7 @@ struct LinArgs {
 };
 
 __global__ void __launch_bounds__(256) linearize_kernel(LinArgs a, int64_t n, int64_t* __restrict__ lin) {
+    LG_PDL_TRIGGER();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t off = 0;
         for (int k = 0; k < a.n_arrays; ++k) {

@@ -17,6 +17,7 @@ namespace {
 
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ delta, int64_t n, float neg_lr, float mom) {
+    LG_PDL_TRIGGER();
     const int64_t nv = n / 4;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = tid; i < nv; i += nt) {
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
 // one CTA, so the counter can be advanced after every thread has read it
 __global__ void adam_prep_kernel(int n_seg, int64_t* __restrict__ t_dev, double b1, double b2,
                                  float* __restrict__ c1, float* __restrict__ c2) {
+    LG_PDL_TRIGGER();
     const int64_t t0 = *t_dev;
     for (int i = threadIdx.x; i < n_seg; i += blockDim.x) {
         const double t = (double)(t0 + i + 1);
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    const int64_t* __restrict__ seg_end, const float* __restrict__ c1,
                                                    const float* __restrict__ c2, float neg_lr, float b1, float b2,
                                                    float omb1, float omb2, float eps) {
+    LG_PDL_TRIGGER();
     const int64_t nv = n / 4;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
     int seg = 0;

@@ -42,6 +42,7 @@ __device__ __forceinline__ T warp_reduce(T v) {
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_rows_warp(const T* __restrict__ x, T* __restrict__ out, int64_t rows,
                                                      int64_t len, T scale, int acc_out) {
+    LG_PDL_TRIGGER();
     using VT = Vec<T, V>;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) red_rows_warp(const T* __restrict__ x, T*
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T* __restrict__ out, int64_t len,
                                                       int64_t chunk, int S, T scale, int acc_out) {
+    LG_PDL_TRIGGER();
     using VT = Vec<T, V>;
     __shared__ T sm[8];
     const int64_t row = blockIdx.x / S;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
                                                 int64_t inner, int64_t ld, int64_t chunk, int S, int64_t ntiles,
                                                 T scale, int acc_out, T* __restrict__ final_out,
                                                 unsigned int* __restrict__ tickets) {
+    LG_PDL_TRIGGER();
     // final_out != nullptr (S > 1): `out` holds the per-chunk partials and the LAST CTA to finish a column
     // tile (ticket counter) sums them in chunk order into final_out -- one launch, still deterministic
     using VT = Vec<T, V>;

@@ -159,6 +159,7 @@ namespace {
 // occupies the compute stream for `ns` nanoseconds: lets the host queue a whole step behind it, so that
 // CUDA events recorded between the queued kernels time the kernels and not the host's dispatch latency
 __global__ void spin_kernel(unsigned long long ns) {
+    LG_PDL_TRIGGER();
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {
