@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, '..', '..', 'lib', 'liblightgrad_b200.so'))
+LIB_PATH = os.environ.get('LG_LIB') or os.path.normpath(os.path.join(_HERE, '..', '..', 'lib', 'liblightgrad_b200.so'))
 
 # ---- enums mirrored from include/lightgrad_b200.h (tests/test_abi.py checks they agree) ----------
 F32, F64, I32, I64, I16, U8, I8, BF16 = range(8)

@@ -27,7 +27,9 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), lib=LIB, obj_dir=OBJ):
+    FLAGS_ = FLAGS + list(extra_flags)
+    OBJ, LIB = obj_dir, lib
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
@@ -41,7 +43,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC] + FLAGS + ['-c', src, '-o', obj]
+        cmd = [NVCC] + FLAGS_ + ['-c', src, '-o', obj]
         if verbose:
             print(' '.join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -29,6 +29,10 @@ int ew_dispatch2(int opc, int dtype, const void* a, const void* b, void* out, co
 int ew_dispatch3(int opc, int dtype, const void* a, const void* b, const void* c, void* out, const EwShape& s,
                  double alpha);
 
+// (evict-first ld/st.cs variants of the flat kernel were measured: no faster, 3-8 % slower for add/gelu)
+#define LG_EW_LD(p) (*(p))
+#define LG_EW_ST(p, v) (*(p) = (v))
+
 // ---- flat ---------------------------------------------------------------------------------------
 template <class Op, typename T, int NIN, int V>
 __global__ void __launch_bounds__(256) ew_flat_kernel(const T* __restrict__ a, const T* __restrict__ b,
@@ -49,9 +53,9 @@ __global__ void __launch_bounds__(256) ew_flat_kernel(const T* __restrict__ a, c
         VT ra[U], rb[U], rc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            ra[u] = av[i + u * nthreads];
-            if (NIN > 1) rb[u] = bv[i + u * nthreads];
-            if (NIN > 2) rc[u] = cv[i + u * nthreads];
+            ra[u] = LG_EW_LD(av + i + u * nthreads);
+            if (NIN > 1) rb[u] = LG_EW_LD(bv + i + u * nthreads);
+            if (NIN > 2) rc[u] = LG_EW_LD(cv + i + u * nthreads);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(256) ew_flat_kernel(const T* __restrict__ a, c
 #pragma unroll
             for (int k = 0; k < V; ++k)
                 r.v[k] = Op::apply(ra[u].v[k], NIN > 1 ? rb[u].v[k] : T(0), NIN > 2 ? rc[u].v[k] : T(0), alpha);
-            ov[i + u * nthreads] = r;
+            LG_EW_ST(ov + i + u * nthreads, r);
         }
     }
     for (; i < nv; i += nthreads) {
