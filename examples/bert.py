@@ -62,7 +62,12 @@ class BertSelfAttention(nn.Module):
         self.key = nn.Linear(hidden_size, hidden_size)
         self.value = nn.Linear(hidden_size, hidden_size)
 
-    def forward(self, hidden, attention_mask=None):
+    def forward(self, hidden, attention_mask=None, need_probs=True):
+        if attention_mask is None and not need_probs and hasattr(hidden, 'self_attention') \
+                and len(hidden.shape) == 3:
+            # whole block as one graph node: grouped QKV projection, per-head views, stacked gradients
+            q, k, v = self.query, self.key, self.value
+            return hidden.self_attention(q.weight, q.bias, k.weight, k.bias, v.weight, v.bias, heads=self.h), None
         Q, K, V = self.query(hidden), self.key(hidden), self.value(hidden)
         b, s, _ = K.shape
         Q = Q.reshape(b, s, self.h, self.d).transpose(0, 2, 1, 3)
@@ -93,8 +98,8 @@ class BertAttention(nn.Module):
         self.output.dense = nn.Linear(hidden_size, hidden_size)
         self.output.LayerNorm = nn.LayerNorm(hidden_size)
 
-    def forward(self, hidden_in, attention_mask=None):
-        hidden, attentions = self.self(hidden_in, attention_mask=attention_mask)
+    def forward(self, hidden_in, attention_mask=None, need_probs=True):
+        hidden, attentions = self.self(hidden_in, attention_mask=attention_mask, need_probs=need_probs)
         hidden = self.output.dense(hidden)
         return self.output.LayerNorm(hidden + hidden_in), attentions
 
@@ -112,8 +117,8 @@ class BertLayer(nn.Module):
     def mlp(self, x):
         return self.output.dense(gelu(self.intermediate.dense(x)))
 
-    def forward(self, hidden, attention_mask=None):
-        hidden, attentions = self.attention(hidden, attention_mask)
+    def forward(self, hidden, attention_mask=None, need_probs=True):
+        hidden, attentions = self.attention(hidden, attention_mask, need_probs=need_probs)
         hidden = hidden + self.mlp(hidden)
         return self.output.LayerNorm(hidden), attentions
 
@@ -131,7 +136,8 @@ class BertModel(nn.Module):
     def forward(self, input_ids, attention_mask=None, token_type_ids=None):
         hidden = self.embeddings(input_ids, token_type_ids=token_type_ids)
         for layer in self.encoder.layer:
-            hidden, _ = layer(hidden, attention_mask=attention_mask)
+            # the attention probabilities are not returned from here: layers may fuse the whole block
+            hidden, _ = layer(hidden, attention_mask=attention_mask, need_probs=False)
         return hidden
 
 

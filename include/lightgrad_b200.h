@@ -175,6 +175,11 @@ typedef struct LgGemmDesc {
 } LgGemmDesc;
 int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c,
             const void* bias, int accumulate);
+/* `groups` (1..4) problems that share one LgGemmDesc but have their own operand / result / bias pointers, as one
+ * launch (the Q, K and V projections of an attention block; their three dW).  Several groups may name the same
+ * C: with accumulate != 0 every group adds into it (dX = sum_g dY_g W_g). */
+int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const void* const* a, const void* const* b,
+                    void* const* c, const void* const* bias, int accumulate);
 /* measurement hooks for the matmul share of a step (off by default):
  * lg_prof_gemm(1): CUDA events on the compute stream around every lg_gemm launch;
  * lg_prof_gemm(2): lg_gemm launches NOTHING and only counts -- timing a captured step with and without its

@@ -865,6 +865,127 @@ class linear(Function):
         return dx, dw
 
 
+def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False):
+    """outs[g] (+)= As[g] @ Bs[g] (+ biases[g]) for up to 4 problems of identical shape and strides, as one
+    launch.  Naming the same tensor in every ``outs`` slot makes it one K-concatenated product
+    out = sum_g As[g] @ Bs[g].  Operands: 2-D, or N-D with batch dims that collapse to <= 2 strides."""
+    a, b, out = As[0], Bs[0], outs[0]
+    for x, y, o in zip(As, Bs, outs):
+        assert x._shape == a._shape and x._strides == a._strides and x._code == a._code
+        assert y._shape == b._shape and y._strides == b._strides and y._code == a._code
+        assert o._shape == out._shape and o._strides == out._strides and o._code == a._code
+    M, K = a._shape[-2:]
+    N = b._shape[-1]
+    assert b._shape[-2] == K and out._shape[-2:] == (M, N) and a._shape[:-2] == b._shape[:-2] == out._shape[:-2]
+    bshape = a._shape[:-2]
+    cshape, (csa, csb, csc) = _collapse_batch(bshape, [list(a._strides[:-2]), list(b._strides[:-2]),
+                                                       list(out._strides[:-2])])
+    assert len(cshape) <= 2, "grouped matmul: batch dims must collapse to two"
+    while len(cshape) < 2:
+        cshape.insert(0, 1)
+        csa.insert(0, 0)
+        csb.insert(0, 0)
+        csc.insert(0, 0)
+    d = rt.GemmDesc(M, N, K, cshape[0], cshape[1],
+                    csa[0], csa[1], a._strides[-2], a._strides[-1],
+                    csb[0], csb[1], b._strides[-2], b._strides[-1],
+                    csc[0], csc[1], out._strides[-2], out._strides[-1])
+    n = len(As)
+    arr = C.c_void_p * n
+    rt.api.gemm_grouped(_matmul_mode, a._code, C.byref(d), n, arr(*[t.ptr for t in As]), arr(*[t.ptr for t in Bs]),
+                        arr(*[t.ptr for t in outs]),
+                        arr(*[t.ptr for t in biases]) if biases is not None else None, 1 if accumulate else 0)
+    return outs
+
+
+def _direct_grad(p, code):
+    """The parameter's existing gradient buffer when a kernel may add into it in place, else None."""
+    g = p.grad if isinstance(p, CudaTensor) and p.requires_grad else None
+    if g is not None and g._contig and g._code == code == rt.F32 and g._shape == p._shape:
+        return g
+    return None
+
+
+@CudaTensor.register_op()
+class self_attention(Function):
+    """Multi-head self-attention without mask, heads merged: (b, s, H) -> (b, s, H)
+
+        Q, K, V = x Wq^T + bq, x Wk^T + bk, x Wv^T + bv ;  out = softmax(Q K^T / sqrt(d)) V   per head
+
+    i.e. BertSelfAttention.forward of the reference (examples/bert.py:60-93) as one graph node.  The three
+    projections are one grouped GEMM into a stacked (3, b*s, H) buffer whose per-head views feed the batched
+    score / context GEMMs without a copy; backward writes dQ, dK, dV into one stacked buffer, forms dX as ONE
+    K-concatenated GEMM (sum of the three dY_g W_g accumulated in tensor memory) and the three dW as one
+    grouped GEMM accumulating into the optimizer's gradient arena.
+    """
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, heads=1):
+        x = _float_like(x)
+        assert len(x._shape) == 3, "self_attention expects (batch, seq, hidden)"
+        b, s, H = x._shape
+        assert H % heads == 0 and wq._shape == wk._shape == wv._shape == (H, H)
+        dh = H // heads
+        rows = b * s
+        x2 = _fold_rows(x)
+        x2._mark_shared()
+        qkv = CudaTensor._new((3, rows, H), x._dtype)
+        parts = [qkv._view((rows, H), (H, 1), g * rows * H) for g in range(3)]
+        _gemm_grouped([x2] * 3, [_swap_last(w) for w in (wq, wk, wv)], parts, [bq, bk, bv])
+        hv = (b, heads, s, dh), (s * H, dh, H, 1)                      # per-head view of a (rows, H) matrix
+        q, k, v = (qkv._view(hv[0], hv[1], g * rows * H) for g in range(3))
+        scale = 1.0 / float(np.sqrt(dh))
+        scores = _gemm(q, _swap_last(k))
+        probs = CudaTensor._new(scores._shape, x._dtype)
+        rt.api.softmax_fwd(x._code, scores.ptr, probs.ptr, scores._numel // s, s, scale)
+        del scores
+        out = CudaTensor._new((b, s, H), x._dtype)
+        _gemm(probs, v, out=out._view(hv[0], hv[1]))
+        probs._temp = qkv._temp = False
+        ctx.save_for_backward(x2, qkv, probs, (b, s, H, heads, scale), x._shape)
+        return out
+
+    def backward(ctx, out_grad):
+        x2, qkv, probs, (b, s, H, heads, scale), xshape = ctx.get_saved_tensors()
+        wq, bq, wk, bk, wv, bv = ctx._parents[1:7]
+        dh, rows = H // heads, b * s
+        g = out_grad.contiguous()
+        if g._code != x2._code:
+            g = g.astype(x2._dtype)
+        hv = (b, heads, s, dh), (s * H, dh, H, 1)
+        q, k, v = (qkv._view(hv[0], hv[1], i * rows * H) for i in range(3))
+        go = g._view(hv[0], hv[1])
+        dqkv = CudaTensor._new((3, rows, H), x2._dtype)
+        dq, dk, dv = (dqkv._view(hv[0], hv[1], i * rows * H) for i in range(3))
+        _gemm(_swap_last(probs), go, out=dv)                            # dV = P^T dO
+        dp = _gemm(go, _swap_last(v))                                   # dP = dO V^T
+        ds = CudaTensor._new(probs._shape, x2._dtype)
+        rt.api.softmax_bwd(x2._code, probs.ptr, dp.ptr, ds.ptr, probs._numel // s, s, scale)
+        del dp
+        _gemm(ds, k, out=dq)                                            # dQ = dS K
+        _gemm(_swap_last(ds), q, out=dk)                                # dK = dS^T Q
+        parts = [dqkv._view((rows, H), (H, 1), i * rows * H) for i in range(3)]
+        ws = (wq, wk, wv)
+        dx = CudaTensor._new((rows, H), x2._dtype)
+        _gemm_grouped(parts, list(ws), [dx] * 3)                        # dX = sum_g dY_g W_g
+        dx = _with_shape(dx, xshape)
+        wgs = [_direct_grad(w, x2._code) for w in ws]
+        pt = [_swap_last(t) for t in parts]
+        if all(w is not None for w in wgs):
+            _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True)           # dW_g += dY_g^T X, straight into the arena
+            dws = [Function.ACCUMULATED] * 3
+        else:
+            dws = [CudaTensor._new((H, H), x2._dtype) for _ in range(3)]
+            _gemm_grouped(pt, [x2] * 3, dws)
+        dbs = []
+        for part, bias in zip(parts, (bq, bk, bv)):
+            bg = _direct_grad(bias, x2._code)
+            if bg is not None and H > 1:
+                rt.api.reduce_pitched(RED['SUM'], part._code, part.ptr, bg.ptr, 1, rows, H, H, 1.0, 1)
+                dbs.append(Function.ACCUMULATED)
+            else:
+                dbs.append(_reduce(RED['SUM'], part, (0,), False))
+        return dx, dws[0], dbs[0], dws[1], dbs[1], dws[2], dbs[2]
+
+
 # ---------------------------------------------------------------------------------------------------
 # indexing (cpu/ops.py:234-255, opencl/ops.py:292-331)
 def _is_index_array(v):

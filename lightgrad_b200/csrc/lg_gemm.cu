@@ -6,6 +6,8 @@ int gemm_simt(int dtype, const LgGemmDesc* d, const void* a, const void* b, void
               int accumulate);
 int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate);
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c);
+int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
+                    const void* const* bias, int accumulate);
 }  // namespace lg
 
 using namespace lg;
@@ -81,6 +83,42 @@ int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void*
         rc = gemm_tc(mode, d, a, b, c, bias, accumulate);
     else
         rc = gemm_simt(dtype, d, a, b, c, bias, accumulate);
+    if (g_prof_on) {
+        LG_CUDA(cudaEventRecord(pr.e1, stream()));
+        g_probes.push_back(pr);
+    }
+    return rc;
+}
+
+int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const void* const* a, const void* const* b,
+                    void* const* c, const void* const* bias, int accumulate) {
+    LG_INIT();
+    LG_REQUIRE(groups >= 1 && groups <= 4, "lg_gemm_grouped: 1..4 groups");
+    if (g_skip) {
+        g_skip_launches += 1;
+        g_skip_flops += 2.0 * (double)d->M * (double)d->N * (double)d->K * (double)(d->batch0 * d->batch1) * groups;
+        return 0;
+    }
+    bool tc = mode != LG_GEMM_FP32_SIMT && !(accumulate && bias);
+    for (int g = 0; g < groups && tc; ++g) tc = gemm_tc_supported(mode, dtype, d, a[g], b[g], c[g]) != 0;
+    GemmProbe pr;
+    if (g_prof_on) {
+        LG_CUDA(cudaEventCreate(&pr.e0));
+        LG_CUDA(cudaEventCreate(&pr.e1));
+        pr.flops = 2.0 * (double)d->M * (double)d->N * (double)d->K * (double)(d->batch0 * d->batch1) * groups;
+        LG_CUDA(cudaEventRecord(pr.e0, stream()));
+    }
+    int rc = 0;
+    if (tc) {
+        rc = gemm_tc_grouped(d, groups, a, b, c, bias, accumulate);
+    } else {
+        // exact path: one launch per group (a repeated C accumulates from the second group on)
+        for (int g = 0; g < groups && !rc; ++g) {
+            bool seen = false;
+            for (int h = 0; h < g; ++h) seen = seen || c[h] == c[g];
+            rc = gemm_simt(dtype, d, a[g], b[g], c[g], (bias && !seen) ? bias[g] : nullptr, (accumulate || seen) ? 1 : 0);
+        }
+    }
     if (g_prof_on) {
         LG_CUDA(cudaEventRecord(pr.e1, stream()));
         g_probes.push_back(pr);

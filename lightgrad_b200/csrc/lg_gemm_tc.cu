@@ -24,6 +24,7 @@ using namespace lg;
 
 namespace {
 
+constexpr int LG_MAX_GROUPS = 4;
 constexpr int BM = 128;
 constexpr int BK = 32;               // fp32 elements per K step = 128 bytes
 constexpr int A_STAGE_BYTES = BM * 128;
@@ -149,7 +150,13 @@ struct TcParams {
     int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
     int batch1, batches;      // batches = batch0 * batch1
     int reduce_out;           // 1: C += tile (TMA reduce-add): split-K partials and/or accumulate mode
-    const float* bias;
+    int groups;               // problems of identical shape served by this launch (1-CTA kernel only)
+    int kcat;                 // operand pairs concatenated along K into ONE result: C = sum_g A_g B_g (1-CTA kernel)
+    const float* bias[LG_MAX_GROUPS];
+};
+
+struct TcMaps {
+    CUtensorMap a[LG_MAX_GROUPS], b[LG_MAX_GROUPS], c[LG_MAX_GROUPS];
 };
 
 // CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on vertically adjacent output tiles
@@ -160,8 +167,7 @@ struct TcParams {
 // cta_group::2 kernel below, which really halves the B bytes per SM.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, TcParams p) {
+gemm_tf32_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
     LG_PDL_TRIGGER();
     constexpr int B_STAGE_BYTES = BN * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -181,7 +187,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // p.tiles_m counts groups of CL vertically adjacent tiles; work items are distributed over clusters
     const int items_per_batch = p.tiles_m * p.tiles_n * p.splits;
-    const int work_items = items_per_batch * p.batches;
+    // grouped launch: `groups` problems of identical shape (own operand / result maps), enumerated group-major
+    const int items_per_group = items_per_batch * p.batches;
+    const int work_items = items_per_group * p.groups;
     const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
     const int cluster_id = (int)blockIdx.x / CL, n_clusters = (int)gridDim.x / CL;
 
@@ -195,9 +203,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_init(&tempty[s], EPI_WARPS * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c));
+        for (int g = 0; g < p.groups * p.kcat; ++g) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[g]));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[g]));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.c[g]));
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -219,47 +229,53 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int w = cluster_id; w < work_items; w += n_clusters) {
-                const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+                const int grp = w / items_per_group, wg = w - grp * items_per_group;
+                const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
                 const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
                 const int tile = wi / p.splits, split = wi - tile * p.splits;
                 const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
                 const int kb0 = split * p.kblocks_per_split;
                 int kb1 = kb0 + p.kblocks_per_split;
                 if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
-                for (int kb = kb0; kb < kb1; ++kb) {
+                const int kspan = kb1 - kb0;
+                for (int it = 0; it < kspan * p.kcat; ++it) {
+                    // K-concatenated operands: chunk kc supplies k-blocks kb0..kb1 of its own (A, B) pair
+                    const int kc = it / kspan, kb = kb0 + (it - kc * kspan);
+                    const CUtensorMap* map_a = &maps.a[grp + kc];
+                    const CUtensorMap* map_b = &maps.b[grp + kc];
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     const int k0 = kb * BK;
                     if (!A_MN) {
-                        tma_load_4d(&map_a, &full[stage], sa, k0, m0, bc1, bc0);
+                        tma_load_4d(map_a, &full[stage], sa, k0, m0, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 32; ++j)
-                            tma_load_4d(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
+                            tma_load_4d(map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
                     }
                     if (CL == 1) {
                         if (!B_MN) {
-                            tma_load_4d(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
+                            tma_load_4d(map_b, &full[stage], sb, k0, n0, bc1, bc0);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BN / 32; ++j)
-                                tma_load_4d(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
+                                tma_load_4d(map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
                         }
                     } else {
                         // this CTA fetches its half of the B tile for the whole cluster
                         constexpr uint16_t kAll = (uint16_t)((1u << CL) - 1);
                         if (!B_MN) {
                             constexpr int HALF = BN / CL;   // rows of B per CTA (the map's box height)
-                            tma_load_4d_mc(&map_b, &full[stage], sb + crank * HALF * 128, k0, n0 + crank * HALF, bc1,
+                            tma_load_4d_mc(map_b, &full[stage], sb + crank * HALF * 128, k0, n0 + crank * HALF, bc1,
                                            bc0, kAll);
                         } else {
                             constexpr int PER = (BN / 32) / CL;
 #pragma unroll
                             for (int jj = 0; jj < PER; ++jj) {
                                 const int j = crank * PER + jj;
-                                tma_load_4d_mc(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0,
+                                tma_load_4d_mc(map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0,
                                                kAll);
                             }
                         }
@@ -280,14 +296,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int w = cluster_id; w < work_items; w += n_clusters) {
-                const int split = (w % items_per_batch) % p.splits;
+                const int split = ((w % items_per_group) % items_per_batch) % p.splits;
                 const int kb0 = split * p.kblocks_per_split;
                 int kb1 = kb0 + p.kblocks_per_split;
                 if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                const int n_it = (kb1 - kb0) * p.kcat;
+                for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -301,7 +318,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                                  : umma_desc(sa + ks * 32, 16, 1024, 2);
                         const uint64_t db = B_MN ? umma_desc(sb + ks * 1024, BK * 128, 512, 1)
                                                  : umma_desc(sb + ks * 32, 16, 1024, 2);
-                        const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        const uint32_t accum = (it > 0 || ks > 0) ? 1u : 0u;
                         asm volatile(
                             "{\n\t"
                             ".reg .pred p;\n\t"
@@ -347,7 +364,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t acc_phase = 0;
         int flip = 0;
         for (int w = cluster_id; w < work_items; w += n_clusters) {
-            const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+            const int grp = w / items_per_group, wg = w - grp * items_per_group;
+            const CUtensorMap* map_c = &maps.c[grp];
+            const float* bias = p.bias[grp];
+            const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
             const int tile = wi / p.splits, split = wi - tile * p.splits;
             const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
@@ -376,7 +396,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     // the TMA store that last read this buffer (two chunks ago) must have drained
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
-                    const bool add_bias = p.bias != nullptr && split == 0;
+                    const bool add_bias = bias != nullptr && split == 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 o;
@@ -387,12 +407,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (add_bias) {
                             const int cn = col0 + 4 * j;
                             if (cn + 3 < p.N) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cn);
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias + cn);
                                 o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                             } else {
-                                if (cn + 0 < p.N) o.x += p.bias[cn + 0];
-                                if (cn + 1 < p.N) o.y += p.bias[cn + 1];
-                                if (cn + 2 < p.N) o.z += p.bias[cn + 2];
+                                if (cn + 0 < p.N) o.x += bias[cn + 0];
+                                if (cn + 1 < p.N) o.y += bias[cn + 1];
+                                if (cn + 2 < p.N) o.z += bias[cn + 2];
                             }
                         }
                         // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
@@ -401,8 +421,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.reduce_out) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
-                        else tma_store_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        if (p.reduce_out) tma_reduce_add_4d(map_c, buf, col0, m0 + 32 * q, bc1, bc0);
+                        else tma_store_4d(map_c, buf, col0, m0 + 32 * q, bc1, bc0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     flip ^= 1;
@@ -632,7 +652,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     uint8_t* buf = buf0 + flip * EPI_BUF_BYTES;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
-                    const bool add_bias = p.bias != nullptr && split == 0;
+                    const float* bias = p.bias[0];
+                    const bool add_bias = bias != nullptr && split == 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 o;
@@ -643,12 +664,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if (add_bias) {
                             const int cn = col0 + 4 * j;
                             if (cn + 3 < p.N) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + cn);
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias + cn);
                                 o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                             } else {
-                                if (cn + 0 < p.N) o.x += p.bias[cn + 0];
-                                if (cn + 1 < p.N) o.y += p.bias[cn + 1];
-                                if (cn + 2 < p.N) o.z += p.bias[cn + 2];
+                                if (cn + 0 < p.N) o.x += bias[cn + 0];
+                                if (cn + 1 < p.N) o.y += bias[cn + 1];
+                                if (cn + 2 < p.N) o.z += bias[cn + 2];
                             }
                         }
                         *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
@@ -785,7 +806,7 @@ int launch_2cta_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMa
 }
 
 template <int BN, bool A_MN, bool B_MN, int CL>
-int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, int grid) {
+int launch_cfg(const TcMaps& maps, const TcParams& p, int grid) {
     constexpr int ST = stages_for<BN>();
     constexpr size_t smem = smem_for<BN>();
     auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, ST, CL>;
@@ -808,18 +829,17 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    LG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
+    LG_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
     LG_CHECK_LAUNCH();
     return 0;
 }
 
 template <int BN, int CL>
-int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
-              const TcParams& p, int grid) {
-    if (!a_mn && !b_mn) return launch_cfg<BN, false, false, CL>(ma, mb, mc, p, grid);
-    if (!a_mn && b_mn) return launch_cfg<BN, false, true, CL>(ma, mb, mc, p, grid);
-    if (a_mn && !b_mn) return launch_cfg<BN, true, false, CL>(ma, mb, mc, p, grid);
-    return launch_cfg<BN, true, true, CL>(ma, mb, mc, p, grid);
+int launch_bn(bool a_mn, bool b_mn, const TcMaps& maps, const TcParams& p, int grid) {
+    if (!a_mn && !b_mn) return launch_cfg<BN, false, false, CL>(maps, p, grid);
+    if (!a_mn && b_mn) return launch_cfg<BN, false, true, CL>(maps, p, grid);
+    if (a_mn && !b_mn) return launch_cfg<BN, true, false, CL>(maps, p, grid);
+    return launch_cfg<BN, true, true, CL>(maps, p, grid);
 }
 
 bool k_major(int64_t s_mn, int64_t s_k, int64_t extent_mn) { return s_k == 1 && (s_mn % 4 == 0 || extent_mn == 1); }
@@ -829,7 +849,7 @@ struct Plan {
     int bn, splits, tiles_m, tiles_n, kblocks, kper;
 };
 
-Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches) {
+Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split) {
     const int sms = sm_count();
     const int kblocks = (int)((K + BK - 1) / BK);
     Plan best{};
@@ -843,14 +863,14 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches) {
         const int tm = (int)((M + BM - 1) / BM), tn = (int)((N + bn - 1) / bn);
         const int tiles = tm * tn * (int)batches;
         int splits = 1;
-        if (tiles < sms && batches == 1) {
+        if (tiles < sms && allow_split) {
             splits = sms / tiles;
             const int max_splits = kblocks / 8 > 0 ? kblocks / 8 : 1;   // >= 8 k-blocks (256 of K) per split
             if (splits > max_splits) splits = max_splits;
             if (splits > 16) splits = 16;
             if (splits < 1) splits = 1;
         }
-        if (force_splits && batches == 1) splits = force_splits < kblocks ? force_splits : kblocks;
+        if (force_splits && allow_split) splits = force_splits < kblocks ? force_splits : kblocks;
         int kper = (kblocks + splits - 1) / splits;
         splits = (kblocks + kper - 1) / kper;
         const int items = tiles * splits;
@@ -894,35 +914,56 @@ int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, c
     return 1;
 }
 
-int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate) {
-    (void)mode;
+// `groups` problems sharing one LgGemmDesc (shape, strides) but with their own operand / result / bias
+// pointers run as ONE launch of the 1-CTA kernel (e.g. the Q, K and V projections of an attention block:
+// 3 x 128 tiles instead of three one-wave launches).  Several groups may name the same C: with
+// accumulate they all reduce-add into it (dX = sum_g dY_g W_g).
+int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
+                    const void* const* bias, int accumulate) {
     if (load_encode()) return 1;
+    LG_REQUIRE(groups >= 1 && groups <= LG_MAX_GROUPS, "gemm_tc: 1..%d groups per launch", LG_MAX_GROUPS);
     const int64_t M = d->M, N = d->N, K = d->K;
     const bool a_mn = !k_major(d->sa_m, d->sa_k, M);
     const bool b_mn = !k_major(d->sb_n, d->sb_k, N);
     const int64_t batches = d->batch0 * d->batch1;
-    Plan pl = choose_plan(M, N, K, batches);
-    CUtensorMap ma, mb, mc;
+    // every group naming the same C: one K-concatenated product C (+)= sum_g A_g B_g, accumulated in TMEM
+    bool same_c = groups > 1;
+    for (int g = 1; g < groups; ++g) same_c = same_c && c[g] == c[0];
+    if (!same_c)
+        for (int g = 0; g < groups; ++g)
+            for (int h = 0; h < g; ++h) LG_REQUIRE(c[g] != c[h], "gemm_tc: groups must share ONE result or none");
+    if (same_c)
+        for (int g = 1; g < groups; ++g)
+            LG_REQUIRE(!bias || bias[g] == bias[0], "gemm_tc: K-concatenated groups share one bias");
+    const int n_problems = same_c ? 1 : groups;
+    // split-K partials meet in C by reduce-add: C must be zeroed first (done below for one plain matrix) or
+    // already hold the value being accumulated into
+    Plan pl = choose_plan(M, N, K, batches * n_problems, accumulate || batches * n_problems == 1);
     int rc;
     const BatchDims ba{d->batch1, d->sa_b1, d->batch0, d->sa_b0}, bb{d->batch1, d->sb_b1, d->batch0, d->sb_b0},
         bc{d->batch1, d->sc_b1, d->batch0, d->sc_b0};
-    // operand maps: K-major -> (inner = K, outer = rows); MN-major -> (inner = rows, outer = K)
-    if (!a_mn) rc = make_map(&ma, a, K, M, d->sa_m, ba, BK, BM);
-    else rc = make_map(&ma, a, M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
     // CTA pairs (cta_group::2) take 256-row tiles and split the B tile between the two SMs; needs >= 2 tile rows
     // (measured: +5..8 % on >= 2-wave problems such as 4096^3 or the 30522-wide decoder, but slower than
     //  independent CTAs on the one-wave BERT projections, which therefore keep cta_group::1)
     static const int force_pair = getenv("LG_GEMM_PAIR") ? atoi(getenv("LG_GEMM_PAIR")) : -1;
     const bool big = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits >= 2 * (int64_t)sm_count();
-    const bool pair_mma = batches == 1 && pl.tiles_m >= 2 && (force_pair < 0 ? big : force_pair == 1);
+    const bool pair_mma = groups == 1 && batches == 1 && pl.tiles_m >= 2 && (force_pair < 0 ? big : force_pair == 1);
     const int cl = pair_mma ? 2 : 1;
-    if (!b_mn) rc = make_map(&mb, b, K, N, d->sb_n, bb, BK, pl.bn / cl);
-    else rc = make_map(&mb, b, N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
-    rc = make_map(&mc, c, N, M, d->sc_m, bc, 32, 32);
-    if (rc) return rc;
+    TcMaps maps;
     TcParams p;
+    for (int g = 0; g < groups; ++g) {
+        // operand maps: K-major -> (inner = K, outer = rows); MN-major -> (inner = rows, outer = K)
+        if (!a_mn) rc = make_map(&maps.a[g], a[g], K, M, d->sa_m, ba, BK, BM);
+        else rc = make_map(&maps.a[g], a[g], M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+        if (!b_mn) rc = make_map(&maps.b[g], b[g], K, N, d->sb_n, bb, BK, pl.bn / cl);
+        else rc = make_map(&maps.b[g], b[g], N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+        rc = make_map(&maps.c[g], c[g], N, M, d->sc_m, bc, 32, 32);
+        if (rc) return rc;
+        p.bias[g] = bias ? (const float*)bias[g] : nullptr;
+    }
+    for (int g = groups; g < LG_MAX_GROUPS; ++g) p.bias[g] = nullptr;
     p.M = (int)M;
     p.N = (int)N;
     p.K = (int)K;
@@ -933,35 +974,45 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     p.kblocks_total = pl.kblocks;
     p.batch1 = (int)d->batch1;
     p.batches = (int)batches;
-    p.bias = (const float*)bias;
+    p.groups = n_problems;
+    p.kcat = same_c ? groups : 1;
     p.reduce_out = (pl.splits > 1 || accumulate) ? 1 : 0;
     if (pl.splits > 1 && !accumulate) {
-        // split-K partials are summed by TMA reduce-add into a zeroed C
+        // split-K partials are summed by TMA reduce-add into a zeroed C (single group here)
         if (d->sc_m == N) {
-            LG_CUDA(cudaMemsetAsync(c, 0, (size_t)M * N * 4, stream()));
+            LG_CUDA(cudaMemsetAsync(c[0], 0, (size_t)M * N * 4, stream()));
         } else {
-            LG_CUDA(cudaMemset2DAsync(c, (size_t)d->sc_m * 4, 0, (size_t)N * 4, (size_t)M, stream()));
+            LG_CUDA(cudaMemset2DAsync(c[0], (size_t)d->sc_m * 4, 0, (size_t)N * 4, (size_t)M, stream()));
         }
     }
-    const int64_t items64 = (int64_t)p.tiles_m * pl.tiles_n * pl.splits * batches;   // cluster work items
+    const int64_t items64 = (int64_t)p.tiles_m * pl.tiles_n * pl.splits * batches * n_problems;   // cluster work items
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
     const int max_clusters = sm_count() / cl;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
     if (pair_mma) {
         switch (pl.bn) {
-            case 256: return launch_2cta_bn<256>(a_mn, b_mn, ma, mb, mc, p, grid);
-            case 192: return launch_2cta_bn<192>(a_mn, b_mn, ma, mb, mc, p, grid);
-            case 128: return launch_2cta_bn<128>(a_mn, b_mn, ma, mb, mc, p, grid);
-            default: return launch_2cta_bn<64>(a_mn, b_mn, ma, mb, mc, p, grid);
+            case 256: return launch_2cta_bn<256>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
+            case 192: return launch_2cta_bn<192>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
+            case 128: return launch_2cta_bn<128>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
+            default: return launch_2cta_bn<64>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
         }
     }
     switch (pl.bn) {
-        case 256: return launch_bn<256, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
-        case 192: return launch_bn<192, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
-        case 128: return launch_bn<128, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
-        default: return launch_bn<64, 1>(a_mn, b_mn, ma, mb, mc, p, grid);
+        case 256: return launch_bn<256, 1>(a_mn, b_mn, maps, p, grid);
+        case 192: return launch_bn<192, 1>(a_mn, b_mn, maps, p, grid);
+        case 128: return launch_bn<128, 1>(a_mn, b_mn, maps, p, grid);
+        default: return launch_bn<64, 1>(a_mn, b_mn, maps, p, grid);
     }
+}
+
+int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate) {
+    (void)mode;
+    const void* av[1] = {a};
+    const void* bv[1] = {b};
+    void* cv[1] = {c};
+    const void* biasv[1] = {bias};
+    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate);
 }
 
 }  // namespace lg

@@ -209,6 +209,14 @@ class FakeDevice(object):
             r = r + Cm
         Cm[...] = r
 
+    def gemm_grouped(self, mode, dt, dref, groups, a, b, c, bias, accumulate):
+        seen = []
+        for g in range(groups):
+            again = c[g] in seen          # groups naming one result: C = sum_g A_g B_g (+ bias once)
+            self.gemm(mode, dt, dref, a[g], b[g], c[g], bias[g] if bias and not again else None,
+                      1 if (accumulate or again) else 0)
+            seen.append(c[g])
+
     def gemm_tc_supported(self, mode, dt, dref):
         return 1 if mode != rt.GEMM_FP32_SIMT and dt == rt.F32 else 0
 

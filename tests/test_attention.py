@@ -1,0 +1,161 @@
+"""Grouped matmul (lg_gemm_grouped) and the fused self-attention node against the oracle.
+
+The node replaces BertSelfAttention.forward of the reference (examples/bert.py:60-93): the oracle side
+below spells that forward with the reference's own operators on the CPU tensor, so output and every
+gradient are compared op-for-op.  Exact mode: <= 1e-5 (fp32 matmul bound); tf32 mode: <= 5e-3.
+"""
+import ctypes as C
+import math
+import numpy as np
+import pytest
+from lightgrad_b200 import CudaTensor
+from lightgrad_b200.autograd.cuda import ops, runtime as rt
+from lightgrad_b200.autograd.cuda.ops import _gemm_grouped, _swap_last
+from oracle import CpuTensor
+
+
+@pytest.fixture(params=["fake", pytest.param("gpu", marks=pytest.mark.gpu)])
+def device(request):
+    request.getfixturevalue("fake_device" if request.param == "fake" else "cuda")
+    return request.param
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def mode(request, device):
+    prev = ops.set_matmul_mode(request.param)
+    yield request.param
+    ops.set_matmul_mode(prev)
+
+
+def rel(got, want):
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
+
+
+def _tol(mode):
+    return 1e-5 if mode == 'fp32' else 5e-3
+
+
+@pytest.mark.parametrize("shape", [(256, 192, 128), (512, 768, 256), (100, 132, 72)])
+def test_grouped_independent_results(mode, shape):
+    M, N, K = shape
+    rs = np.random.RandomState(3)
+    a = [rs.uniform(-1, 1, (M, K)).astype(np.float32) for _ in range(3)]
+    w = [rs.uniform(-1, 1, (N, K)).astype(np.float32) for _ in range(3)]        # used transposed (MN-major B)
+    bias = [rs.uniform(-1, 1, (N,)).astype(np.float32) for _ in range(3)]
+    A, W, B = ([CudaTensor.from_numpy(v) for v in vs] for vs in (a, w, bias))
+    out = CudaTensor.empty((3, M, N))
+    parts = [out._view((M, N), (N, 1), g * M * N) for g in range(3)]
+    _gemm_grouped(A, [_swap_last(t) for t in W], parts, B)
+    got = out.numpy()
+    for g in range(3):
+        want = a[g].astype(np.float64) @ w[g].T.astype(np.float64) + bias[g]
+        assert rel(got[g], want) <= _tol(mode), (shape, g)
+    # accumulate: every group adds into what its result already holds
+    _gemm_grouped(A, [_swap_last(t) for t in W], parts, accumulate=True)
+    got2 = out.numpy()
+    for g in range(3):
+        want = 2 * (a[g].astype(np.float64) @ w[g].T.astype(np.float64)) + bias[g]
+        assert rel(got2[g], want) <= _tol(mode), (shape, g, 'acc')
+
+
+@pytest.mark.parametrize("shape", [(256, 192, 128), (384, 768, 768), (100, 132, 72)])
+@pytest.mark.parametrize("groups", [2, 3, 4])
+def test_grouped_shared_result_is_k_concatenation(mode, shape, groups):
+    M, N, K = shape
+    rs = np.random.RandomState(4)
+    a = [rs.uniform(-1, 1, (M, K)).astype(np.float32) for _ in range(groups)]
+    b = [rs.uniform(-1, 1, (K, N)).astype(np.float32) for _ in range(groups)]
+    A, B = ([CudaTensor.from_numpy(v) for v in vs] for vs in (a, b))
+    out = CudaTensor.empty((M, N))
+    _gemm_grouped(A, B, [out] * groups)
+    want = sum(x.astype(np.float64) @ y.astype(np.float64) for x, y in zip(a, b))
+    assert rel(out.numpy(), want) <= _tol(mode)
+    _gemm_grouped(A, B, [out] * groups, accumulate=True)
+    assert rel(out.numpy(), 2 * want) <= _tol(mode)
+
+
+def test_grouped_rejects_partially_shared_results(device):
+    if device == 'fake':
+        pytest.skip("argument check lives in the CUDA library")
+    prev = ops.set_matmul_mode('tf32')
+    try:
+        A = [CudaTensor.zeros((128, 128)) for _ in range(3)]
+        o1, o2 = CudaTensor.zeros((128, 128)), CudaTensor.zeros((128, 128))
+        with pytest.raises(RuntimeError):
+            _gemm_grouped(A, A, [o1, o1, o2])
+    finally:
+        ops.set_matmul_mode(prev)
+
+
+def _oracle_attention(T, x, wq, bq, wk, bk, wv, bv, heads):
+    # BertSelfAttention.forward with the reference's operator set (examples/bert.py:60-93)
+    b, s, H = x.shape
+    d = H // heads
+    Q = x @ wq.transpose(1, 0) + bq
+    K = x @ wk.transpose(1, 0) + bk
+    V = x @ wv.transpose(1, 0) + bv
+    Q = Q.reshape(b, s, heads, d).transpose(0, 2, 1, 3)
+    K = K.reshape(b, s, heads, d).transpose(0, 2, 3, 1)
+    V = V.reshape(b, s, heads, d).transpose(0, 2, 1, 3)
+    P = (Q @ K / math.sqrt(d)).softmax(axis=-1)
+    return (P @ V).transpose(0, 2, 1, 3).reshape(b, s, H)
+
+
+@pytest.mark.parametrize("cfg", [(2, 16, 64, 4), (3, 128, 256, 4), (2, 24, 96, 3)])
+@pytest.mark.parametrize("preset_grads", [False, True])
+def test_self_attention_matches_oracle(mode, cfg, preset_grads):
+    b, s, H, heads = cfg
+    rs = np.random.RandomState(5)
+    x = rs.uniform(-1, 1, (b, s, H)).astype(np.float32)
+    ws = [(rs.uniform(-1, 1, (H, H)) / math.sqrt(H)).astype(np.float32) for _ in range(3)]
+    bs = [rs.uniform(-0.1, 0.1, (H,)).astype(np.float32) for _ in range(3)]
+    up = rs.uniform(-1, 1, (b, s, H)).astype(np.float32)
+
+    def run(T):
+        X = T.from_numpy(x)
+        W = [T.from_numpy(w) for w in ws]
+        B = [T.from_numpy(v) for v in bs]
+        if T is CudaTensor:
+            if preset_grads:
+                # gradients already allocated (optimizer arena): the node adds into them in place
+                for p in W + B:
+                    p.zero_grad()
+            out = X.self_attention(W[0], B[0], W[1], B[1], W[2], B[2], heads=heads)
+        else:
+            out = _oracle_attention(T, X, W[0], B[0], W[1], B[1], W[2], B[2], heads)
+        (out * T.from_numpy(up, requires_grad=False)).sum().backward()
+        return out.numpy(), [X.grad.numpy()] + [p.grad.numpy() for p in W + B]
+
+    want_out, want_g = run(CpuTensor)
+    got_out, got_g = run(CudaTensor)
+    tol = _tol(mode) * (10 if mode == 'fp32' else 1)       # composite of ~8 fp32 matmuls + softmax
+    assert rel(got_out, want_out) <= tol
+    names = ['x', 'wq', 'wk', 'wv', 'bq', 'bk', 'bv']
+    gmax = max(float(np.abs(g).max()) for g in want_g)
+    for n, g, w in zip(names, got_g, want_g):
+        assert g.shape == w.shape, n
+        # key.bias has a mathematically zero gradient (softmax is shift invariant): compare on the common scale
+        assert float(np.abs(g - w).max()) <= tol * max(float(np.abs(w).max()), 1e-3 * gmax), n
+
+
+def test_bert_layer_uses_fused_node_and_matches_unfused(device):
+    import lightgrad_b200.nn as nn
+    from examples.bert import BertSelfAttention
+    with nn.use_tensor(CudaTensor):
+        np.random.seed(7)
+        att = BertSelfAttention(64, 4)
+    x = np.random.uniform(-1, 1, (2, 16, 64)).astype(np.float32)
+    X1, X2 = CudaTensor.from_numpy(x), CudaTensor.from_numpy(x)
+    fused, none = att(X1, need_probs=False)
+    assert none is None and fused.ctx.__class__.__name__ == 'self_attention'
+    plain, probs = att(X2)
+    assert probs is not None and probs.shape == (2, 4, 16, 16)
+    np.testing.assert_allclose(fused.numpy(), plain.numpy(), rtol=1e-5, atol=1e-6)
+    fused.sum().backward()
+    g1 = {k: p.grad.numpy().copy() for k, p in att.named_parameters()}
+    for _, p in att.named_parameters():
+        p.zero_grad()
+    plain.sum().backward()
+    for k, p in att.named_parameters():
+        np.testing.assert_allclose(g1[k], p.grad.numpy(), rtol=1e-4, atol=1e-5, err_msg=k)
+    np.testing.assert_allclose(X1.grad.numpy(), X2.grad.numpy(), rtol=1e-4, atol=1e-5)
