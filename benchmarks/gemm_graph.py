@@ -1,0 +1,169 @@
+"""Per-shape tensor-core GEMM time INSIDE a CUDA graph (no python / launch latency between kernels).
+
+opbench's eager loop is bound by interpreter dispatch below ~30 us per call, which hides what the BERT
+step's one-wave GEMMs really cost.  Here each shape is captured `reps` times back-to-back into one graph
+(rotating over enough operand sets to exceed L2, like the step does) and the replay is timed with events.
+
+    python benchmarks/gemm_graph.py [--reps 24]
+"""
+import argparse
+import json
+import os
+import sys
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lightgrad_b200 import CudaTensor                                  # noqa: E402
+from lightgrad_b200.autograd.cuda import ops, runtime as rt            # noqa: E402
+from lightgrad_b200.autograd.cuda.graph import StepGraph               # noqa: E402
+from lightgrad_b200.autograd.cuda.ops import _gemm, _gemm_grouped, _swap_last   # noqa: E402
+
+R, H, F, V = 4096, 768, 3072, 30522          # rows = batch 32 x seq 128
+
+
+def rand(*shape):
+    return CudaTensor.from_numpy(np.random.uniform(-1, 1, shape).astype(np.float32))
+
+
+def cases():
+    # name, builder -> (callable issuing ONE launch on operand set i, flops per launch)
+    def fwd(n_in, n_out):
+        def make(sets):
+            X = [rand(R, n_in) for _ in range(sets)]
+            W = [rand(n_out, n_in) for _ in range(sets)]
+            b = rand(n_out)
+            O = [CudaTensor.empty((R, n_out)) for _ in range(sets)]
+            return (lambda i: _gemm(X[i], _swap_last(W[i]), out=O[i], bias=b)), 2.0 * R * n_in * n_out
+        return make
+
+    def dx(n_in, n_out):
+        def make(sets):
+            G = [rand(R, n_out) for _ in range(sets)]
+            W = [rand(n_out, n_in) for _ in range(sets)]
+            O = [CudaTensor.empty((R, n_in)) for _ in range(sets)]
+            return (lambda i: _gemm(G[i], W[i], out=O[i])), 2.0 * R * n_in * n_out
+        return make
+
+    def dw(n_in, n_out):
+        def make(sets):
+            G = [rand(R, n_out) for _ in range(sets)]
+            X = [rand(R, n_in) for _ in range(sets)]
+            O = [CudaTensor.zeros((n_out, n_in)) for _ in range(sets)]
+            return (lambda i: _gemm(_swap_last(G[i]), X[i], out=O[i], accumulate=True)), 2.0 * R * n_in * n_out
+        return make
+
+    def qkv_fwd():
+        def make(sets):
+            X = [rand(R, H) for _ in range(sets)]
+            W = [[rand(H, H) for _ in range(3)] for _ in range(sets)]
+            b = [rand(H) for _ in range(3)]
+            O = [CudaTensor.empty((3, R, H)) for _ in range(sets)]
+            def go(i):
+                parts = [O[i]._view((R, H), (H, 1), g * R * H) for g in range(3)]
+                _gemm_grouped([X[i]] * 3, [_swap_last(w) for w in W[i]], parts, b)
+            return go, 3 * 2.0 * R * H * H
+        return make
+
+    def qkv_dx():
+        def make(sets):
+            G = [rand(3, R, H) for _ in range(sets)]
+            W = [[rand(H, H) for _ in range(3)] for _ in range(sets)]
+            O = [CudaTensor.empty((R, H)) for _ in range(sets)]
+            def go(i):
+                parts = [G[i]._view((R, H), (H, 1), g * R * H) for g in range(3)]
+                _gemm_grouped(parts, W[i], [O[i]] * 3)
+            return go, 3 * 2.0 * R * H * H
+        return make
+
+    def qkv_dw():
+        def make(sets):
+            G = [rand(3, R, H) for _ in range(sets)]
+            X = [rand(R, H) for _ in range(sets)]
+            O = [[CudaTensor.zeros((H, H)) for _ in range(3)] for _ in range(sets)]
+            def go(i):
+                parts = [_swap_last(G[i]._view((R, H), (H, 1), g * R * H)) for g in range(3)]
+                _gemm_grouped(parts, [X[i]] * 3, O[i], accumulate=True)
+            return go, 3 * 2.0 * R * H * H
+        return make
+
+    def att(kind):
+        b, h, s, d = 32, 12, 128, 64
+        def make(sets):
+            Q = [rand(b, h, s, d) for _ in range(sets)]
+            K = [rand(b, h, s, d) for _ in range(sets)]
+            P = [rand(b, h, s, s) for _ in range(sets)]
+            if kind == 'qk':
+                return (lambda i: _gemm(Q[i], _swap_last(K[i]), out=P[i])), 2.0 * b * h * s * s * d
+            O = [CudaTensor.empty((b, h, s, d)) for _ in range(sets)]
+            if kind == 'pv':
+                return (lambda i: _gemm(P[i], K[i], out=O[i])), 2.0 * b * h * s * s * d
+            return (lambda i: _gemm(_swap_last(P[i]), K[i], out=O[i])), 2.0 * b * h * s * s * d
+        return make
+
+    def layout(M, N, K, a_mn, b_mn, bias):
+        def make(sets):
+            A = [rand(K, M) if a_mn else rand(M, K) for _ in range(sets)]
+            B = [rand(K, N) if b_mn else rand(N, K) for _ in range(sets)]
+            bv = rand(N) if bias else None
+            O = [CudaTensor.empty((M, N)) for _ in range(sets)]
+            return (lambda i: _gemm(_swap_last(A[i]) if a_mn else A[i], B[i] if b_mn else _swap_last(B[i]),
+                                    out=O[i], bias=bv)), 2.0 * M * N * K
+        return make
+
+    if os.environ.get('GEMM_GRAPH_SUITE') == 'layout':
+        out = []
+        for (M, N, K) in [(4096, 3072, 768), (4096, 768, 3072), (4096, 768, 768), (4096, 4096, 4096)]:
+            for a_mn in (0, 1):
+                for b_mn in (0, 1):
+                    for bias in ((0, 1) if (a_mn, b_mn) == (0, 0) else (0,)):
+                        out.append(('%dx%dx%d A_%s B_%s%s' % (M, N, K, 'mn' if a_mn else 'k', 'mn' if b_mn else 'k',
+                                                            ' +bias' if bias else ''),
+                                    layout(M, N, K, a_mn, b_mn, bias)))
+        return out
+
+    return [
+        ('proj fwd 4096x768x768', fwd(H, H)), ('proj dX', dx(H, H)), ('proj dW (acc)', dw(H, H)),
+        ('ffn1 fwd 4096x3072x768', fwd(H, F)), ('ffn1 dX', dx(H, F)), ('ffn1 dW (acc)', dw(H, F)),
+        ('ffn2 fwd 4096x768x3072', fwd(F, H)), ('ffn2 dX', dx(F, H)), ('ffn2 dW (acc)', dw(F, H)),
+        ('qkv grouped fwd', qkv_fwd()), ('qkv k-concat dX', qkv_dx()), ('qkv grouped dW (acc)', qkv_dw()),
+        ('attn QK^T 384x128x128x64', att('qk')), ('attn PV', att('pv')), ('attn P^T dO', att('ptv')),
+        ('decoder fwd 4096x30522x768', fwd(H, V)), ('decoder dX', dx(H, V)), ('decoder dW (acc)', dw(H, V)),
+    ]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--reps', type=int, default=24)
+    ap.add_argument('--sets', type=int, default=6)
+    ap.add_argument('--only', default='')
+    a = ap.parse_args()
+    api = rt.ensure_device()
+    ops.set_matmul_mode('tf32')
+    for name, make in cases():
+        if a.only and a.only not in name:
+            continue
+        sets = 2 if ('decoder' in name or '4096x4096' in name) else a.sets
+        go, flops = make(sets)
+
+        def body():
+            for r in range(a.reps):
+                go(r % sets)
+        g = StepGraph(body, warmup=1)
+        for _ in range(2):
+            g.replay()
+        e0, e1 = rt.Event(), rt.Event()
+        n = 5
+        e0.record()
+        for _ in range(n):
+            g.replay()
+        e1.record()
+        e1.synchronize()
+        us = e0.elapsed_ms(e1) * 1e3 / (n * a.reps)
+        print(json.dumps({'case': name, 'us_per_launch': round(us, 2), 'tflops': round(flops / us * 1e-6, 1),
+                          'launches_in_graph': g.n_kernels}), flush=True)
+        del g, go
+        api.empty_cache()
+
+
+if __name__ == '__main__':
+    main()

@@ -69,6 +69,18 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// MN-major operands whose row pitch covers the extent rounded up to 32 use a rank-5 "chunked" map
+// (32 contiguous elements, k rows, 32-element chunk index, batch1, batch0): ONE box fills the whole stage in the
+// [chunk][k][32] order the UMMA descriptor expects, instead of one 4 KB box per chunk (the producer thread
+// and the TMA unit were the bottleneck of the MN-major kernels with 5..10 small boxes per k-block).
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 // same load, delivered to the same shared-memory offset (and signalling the same mbarrier offset) in every
 // CTA of the cluster named by `mask`
 __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
@@ -88,6 +100,14 @@ __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
         "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                                int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 // arrive on the barrier at the same offset in CTA `rank` of the cluster
@@ -151,6 +171,7 @@ struct TcParams {
     int batch1, batches;      // batches = batch0 * batch1
     int reduce_out;           // 1: C += tile (TMA reduce-add): split-K partials and/or accumulate mode
     int groups;               // problems of identical shape served by this launch (1-CTA kernel only)
+    int a_chunked, b_chunked; // MN-major operand addressed through a rank-5 chunked map (one box per stage)
     int kcat;                 // operand pairs concatenated along K into ONE result: C = sum_g A_g B_g (1-CTA kernel)
     const float* bias[LG_MAX_GROUPS];
 };
@@ -158,6 +179,103 @@ struct TcParams {
 struct TcMaps {
     CUtensorMap a[LG_MAX_GROUPS], b[LG_MAX_GROUPS], c[LG_MAX_GROUPS];
 };
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x BN accumulator tile, run by the four epilogue warps (warp q owns TMEM lanes 32q..32q+31,
+// i.e. 32 output rows; thread = row).  Per 32-column chunk: tcgen05.ld (the NEXT chunk's load is in flight while
+// this one is staged), + bias, 128B-swizzled staging buffer, TMA store / reduce-add.  The bias slice of a chunk
+// is fetched one chunk ahead with one coalesced load per warp and broadcast by shuffles, so no global-memory
+// latency sits between the TMEM read and the store.
+__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ float bias_slice(const float* bias, int col, int N) {
+    return (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+}
+
+struct EpiTile {
+    const CUtensorMap* map_c;
+    const float* bias;      // nullptr: none (also for split-K partials other than the first)
+    int row0, n0, N;        // first output row of this warp, first column of the tile, columns of C
+    int bc1, bc0;           // batch coordinates
+    int reduce_out;
+    bool rows_live;
+};
+
+__device__ __forceinline__ void epi_emit(const EpiTile& t, const uint32_t (&v)[32], float bcur, int col0, uint8_t* buf,
+                                         int lane) {
+    // the TMA store that last read this buffer (two chunks ago) must have drained
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = __uint_as_float(v[4 * j + 0]);
+        o.y = __uint_as_float(v[4 * j + 1]);
+        o.z = __uint_as_float(v[4 * j + 2]);
+        o.w = __uint_as_float(v[4 * j + 3]);
+        if (t.bias != nullptr) {
+            o.x += __shfl_sync(0xffffffffu, bcur, 4 * j + 0);
+            o.y += __shfl_sync(0xffffffffu, bcur, 4 * j + 1);
+            o.z += __shfl_sync(0xffffffffu, bcur, 4 * j + 2);
+            o.w += __shfl_sync(0xffffffffu, bcur, 4 * j + 3);
+        }
+        // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        if (t.reduce_out) tma_reduce_add_4d(t.map_c, buf, col0, t.row0, t.bc1, t.bc0);
+        else tma_store_4d(t.map_c, buf, col0, t.row0, t.bc1, t.bc0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
+// `bfirst` = bias_slice of the tile's first chunk, loaded by the caller BEFORE it waited for the accumulator
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, uint32_t taddr0, uint8_t* buf0, int& flip,
+                                              int lane) {
+    constexpr int NC = BN / 32;
+    static_assert(NC % 2 == 0, "chunks are processed in pairs");
+    uint32_t va[32], vb[32];
+    tmem_ld32(va, taddr0);
+    float bnext = bfirst;
+#pragma unroll 1
+    for (int c = 0; c < NC; c += 2) {
+        const int col0 = t.n0 + c * 32;
+        if (col0 >= t.N) break;
+        const bool has_b = col0 + 32 < t.N;                   // chunk c + 1 exists
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (has_b) tmem_ld32(vb, taddr0 + (uint32_t)((c + 1) * 32));
+        float bcur = bnext;
+        bnext = bias_slice(t.bias, col0 + 32 + lane, t.N);
+        if (t.rows_live) {
+            epi_emit(t, va, bcur, col0, buf0 + flip * EPI_BUF_BYTES, lane);
+            flip ^= 1;
+        }
+        if (!has_b) break;
+        const bool has_a = c + 2 < NC && col0 + 64 < t.N;     // chunk c + 2 exists
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (has_a) tmem_ld32(va, taddr0 + (uint32_t)((c + 2) * 32));
+        bcur = bnext;
+        bnext = bias_slice(t.bias, col0 + 64 + lane, t.N);
+        if (t.rows_live) {
+            epi_emit(t, vb, bcur, col0 + 32, buf0 + flip * EPI_BUF_BYTES, lane);
+            flip ^= 1;
+        }
+    }
+}
 
 // CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on vertically adjacent output tiles
 // (same N block): each loads its own A tile and HALF of the shared B tile, multicast to both; a stage may be
@@ -167,7 +285,7 @@ struct TcMaps {
 // cta_group::2 kernel below, which really halves the B bytes per SM.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
-gemm_tf32_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
+gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     LG_PDL_TRIGGER();
     constexpr int B_STAGE_BYTES = BN * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -250,6 +368,8 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
                     const int k0 = kb * BK;
                     if (!A_MN) {
                         tma_load_4d(map_a, &full[stage], sa, k0, m0, bc1, bc0);
+                    } else if (p.a_chunked) {
+                        tma_load_5d(map_a, &full[stage], sa, 0, k0, m0 >> 5, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 32; ++j)
@@ -258,6 +378,8 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
                     if (CL == 1) {
                         if (!B_MN) {
                             tma_load_4d(map_b, &full[stage], sb, k0, n0, bc1, bc0);
+                        } else if (p.b_chunked) {
+                            tma_load_5d(map_b, &full[stage], sb, 0, k0, n0 >> 5, bc1, bc0);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BN / 32; ++j)
@@ -371,63 +493,20 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
             const int tile = wi / p.splits, split = wi - tile * p.splits;
             const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
+            EpiTile t;
+            t.map_c = map_c;
+            t.bias = split == 0 ? bias : nullptr;
+            t.row0 = m0 + 32 * q;
+            t.n0 = n0;
+            t.N = p.N;
+            t.bc1 = bc1;
+            t.bc0 = bc0;
+            t.reduce_out = p.reduce_out;
+            t.rows_live = t.row0 < p.M;
+            const float bfirst = bias_slice(t.bias, n0 + lane, p.N);
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool rows_live = (m0 + 32 * q) < p.M;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= p.N) break;
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (rows_live) {
-                    uint8_t* buf = buf0 + flip * EPI_BUF_BYTES;
-                    // the TMA store that last read this buffer (two chunks ago) must have drained
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                    const bool add_bias = bias != nullptr && split == 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o;
-                        o.x = __uint_as_float(v[4 * j + 0]);
-                        o.y = __uint_as_float(v[4 * j + 1]);
-                        o.z = __uint_as_float(v[4 * j + 2]);
-                        o.w = __uint_as_float(v[4 * j + 3]);
-                        if (add_bias) {
-                            const int cn = col0 + 4 * j;
-                            if (cn + 3 < p.N) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bias + cn);
-                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                            } else {
-                                if (cn + 0 < p.N) o.x += bias[cn + 0];
-                                if (cn + 1 < p.N) o.y += bias[cn + 1];
-                                if (cn + 2 < p.N) o.z += bias[cn + 2];
-                            }
-                        }
-                        // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
-                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (p.reduce_out) tma_reduce_add_4d(map_c, buf, col0, m0 + 32 * q, bc1, bc0);
-                        else tma_store_4d(map_c, buf, col0, m0 + 32 * q, bc1, bc0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    flip ^= 1;
-                }
-            }
+            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, flip, lane);
             // this warp is done reading the accumulator stage
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty[acc]);
@@ -538,6 +617,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const int k0 = kb * BK;
                     if (!A_MN) {
                         tma_load_4d_2sm(&map_a, &full[stage], sa, k0, m0, bc1, bc0);
+                    } else if (p.a_chunked) {
+                        tma_load_5d_2sm(&map_a, &full[stage], sa, 0, k0, m0 >> 5, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 32; ++j)
@@ -545,6 +626,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                     if (!B_MN) {
                         tma_load_4d_2sm(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
+                    } else if (p.b_chunked) {
+                        tma_load_5d_2sm(&map_b, &full[stage], sb, 0, k0, n0 >> 5, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < HB / 32; ++j)
@@ -628,62 +711,20 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
             const int tile = wi / p.splits, split = wi - tile * p.splits;
             const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM, n0 = (tile / p.tiles_m) * BN;
+            EpiTile t;
+            t.map_c = &map_c;
+            t.bias = split == 0 ? p.bias[0] : nullptr;
+            t.row0 = m0 + 32 * q;
+            t.n0 = n0;
+            t.N = p.N;
+            t.bc1 = bc1;
+            t.bc0 = bc0;
+            t.reduce_out = p.reduce_out;
+            t.rows_live = t.row0 < p.M;
+            const float bfirst = bias_slice(t.bias, n0 + lane, p.N);
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool rows_live = (m0 + 32 * q) < p.M;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= p.N) break;
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN + c * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (rows_live) {
-                    uint8_t* buf = buf0 + flip * EPI_BUF_BYTES;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                    const float* bias = p.bias[0];
-                    const bool add_bias = bias != nullptr && split == 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o;
-                        o.x = __uint_as_float(v[4 * j + 0]);
-                        o.y = __uint_as_float(v[4 * j + 1]);
-                        o.z = __uint_as_float(v[4 * j + 2]);
-                        o.w = __uint_as_float(v[4 * j + 3]);
-                        if (add_bias) {
-                            const int cn = col0 + 4 * j;
-                            if (cn + 3 < p.N) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bias + cn);
-                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                            } else {
-                                if (cn + 0 < p.N) o.x += bias[cn + 0];
-                                if (cn + 1 < p.N) o.y += bias[cn + 1];
-                                if (cn + 2 < p.N) o.z += bias[cn + 2];
-                            }
-                        }
-                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (p.reduce_out) tma_reduce_add_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
-                        else tma_store_4d(&map_c, buf, col0, m0 + 32 * q, bc1, bc0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    flip ^= 1;
-                }
-            }
+            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, flip, lane);
             // one arrival per warp on the LEADER's barrier: the accumulator stage of this CTA is drained
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -740,6 +781,31 @@ int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, i
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
+}
+
+// rank-5 map of an MN-major operand (k rows of `mn` contiguous elements, row pitch `ld`):
+// (32, k, ceil(mn/32), batch1, batch0) with element strides (1, ld, 32, s1, s0); box = (32, BK, chunks, 1, 1)
+int make_map_chunked(CUtensorMap* map, const void* base, int64_t mn, int64_t k, int64_t ld, const BatchDims& bd,
+                     int box_chunks) {
+    const int64_t chunks = (mn + 31) / 32;
+    cuuint64_t dims[5] = {32, (cuuint64_t)k, (cuuint64_t)chunks, (cuuint64_t)bd.n1, (cuuint64_t)bd.n0};
+    const int64_t s_k = k > 1 ? ld : chunks * 32;
+    const int64_t dflt = s_k * (k > 0 ? k : 1);
+    cuuint64_t strides[4] = {(cuuint64_t)s_k * 4, 128, (cuuint64_t)(bd.n1 > 1 ? bd.s1 : dflt) * 4,
+                             (cuuint64_t)(bd.n0 > 1 ? bd.s0 : dflt * (bd.n1 > 0 ? bd.n1 : 1)) * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)BK, (cuuint32_t)box_chunks, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (chunked) failed with CUresult %d", (int)r);
+    return 0;
+}
+// chunks must tile a row exactly: a partial last chunk would read past the end of the row (and, for the last
+// row of a view, possibly past the end of the allocation), which the tensor map cannot clip
+inline bool chunkable(int64_t mn) {
+    static const bool off = getenv("LG_GEMM_NO_CHUNKED") != nullptr;
+    return !off && mn % 32 == 0;
 }
 
 template <int BN>
@@ -951,12 +1017,17 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int cl = pair_mma ? 2 : 1;
     TcMaps maps;
     TcParams p;
+    const bool a_ch = a_mn && chunkable(M), b_ch = b_mn && chunkable(N);
+    p.a_chunked = a_ch ? 1 : 0;
+    p.b_chunked = b_ch ? 1 : 0;
     for (int g = 0; g < groups; ++g) {
         // operand maps: K-major -> (inner = K, outer = rows); MN-major -> (inner = rows, outer = K)
         if (!a_mn) rc = make_map(&maps.a[g], a[g], K, M, d->sa_m, ba, BK, BM);
+        else if (a_ch) rc = make_map_chunked(&maps.a[g], a[g], M, K, d->sa_k, ba, BM / 32);
         else rc = make_map(&maps.a[g], a[g], M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
         if (!b_mn) rc = make_map(&maps.b[g], b[g], K, N, d->sb_n, bb, BK, pl.bn / cl);
+        else if (b_ch) rc = make_map_chunked(&maps.b[g], b[g], N, K, d->sb_k, bb, pl.bn / cl / 32);
         else rc = make_map(&maps.b[g], b[g], N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc) return rc;
         rc = make_map(&maps.c[g], c[g], N, M, d->sc_m, bc, 32, 32);
