@@ -110,6 +110,74 @@ def cases():
                                     out=O[i], bias=bv)), 2.0 * M * N * K
         return make
 
+    if os.environ.get('GEMM_GRAPH_SUITE') == 'fused':
+        # the non-matmul kernels of the BERT step at their step shapes; "flops" slot carries BYTES here
+        import lightgrad_b200 as light
+        RED, EW = rt.RED, rt.EW
+
+        def ln(bwd):
+            def make(sets):
+                X = [rand(R, H) for _ in range(sets)]
+                G = [rand(R, H) for _ in range(sets)]
+                w, b = rand(H), rand(H)
+                wg = CudaTensor.zeros((2, H))
+                Y = [CudaTensor.empty((R, H)) for _ in range(sets)]
+                mean, rstd = CudaTensor.empty((R,)), CudaTensor.empty((R,))
+                rt.api.layernorm_fwd(rt.F32, X[0].ptr, w.ptr, b.ptr, Y[0].ptr, mean.ptr, rstd.ptr, R, H, 1e-5)
+                if not bwd:
+                    return (lambda i: rt.api.layernorm_fwd(rt.F32, X[i].ptr, w.ptr, b.ptr, Y[i].ptr, mean.ptr, rstd.ptr,
+                                                           R, H, 1e-5)), 2.0 * R * H * 4
+                return (lambda i: rt.api.layernorm_bwd(rt.F32, X[i].ptr, w.ptr, mean.ptr, rstd.ptr, G[i].ptr, Y[i].ptr,
+                                                       wg.ptr, wg.ptr + 4 * H, R, H, 1)), 3.0 * R * H * 4
+            return make
+
+        def colsum(n):
+            def make(sets):
+                G = [rand(R, n) for _ in range(sets)]
+                bg = CudaTensor.zeros((n,))
+                return (lambda i: rt.api.reduce_pitched(RED['SUM'], rt.F32, G[i].ptr, bg.ptr, 1, R, n, n, 1.0, 1)), \
+                    1.0 * R * n * 4
+            return make
+
+        def ew(op, n_in, n):
+            def make(sets):
+                A = [rand(R, n) for _ in range(sets)]
+                B = [rand(R, n) for _ in range(sets)]
+                O = [CudaTensor.empty((R, n)) for _ in range(sets)]
+                return (lambda i: rt.api.ew_flat(EW[op], rt.F32, A[i].ptr, B[i].ptr if n_in > 1 else None, None,
+                                                 O[i].ptr, R * n, 0.0)), (n_in + 1.0) * R * n * 4
+            return make
+
+        def softmax(bwd):
+            rows, cols = 32 * 12 * 128, 128
+            def make(sets):
+                Xs = [rand(rows, cols) for _ in range(sets)]
+                Gs = [rand(rows, cols) for _ in range(sets)]
+                Ys = [CudaTensor.empty((rows, cols)) for _ in range(sets)]
+                if not bwd:
+                    return (lambda i: rt.api.softmax_fwd(rt.F32, Xs[i].ptr, Ys[i].ptr, rows, cols, 0.125)), \
+                        2.0 * rows * cols * 4
+                return (lambda i: rt.api.softmax_bwd(rt.F32, Xs[i].ptr, Gs[i].ptr, Ys[i].ptr, rows, cols, 0.125)), \
+                    3.0 * rows * cols * 4
+            return make
+
+        def adam():
+            def make(sets):
+                n = 110 * 1000 * 1000 // 64 * 64
+                ps = [CudaTensor.zeros((n,))]
+                opt = light.optim.Adam(ps, lr=1e-4)
+                ps[0].zero_grad()
+                opt.step()
+                return (lambda i: opt.step()), 7.0 * n * 4
+            return make
+
+        return [('layernorm fwd 4096x768', ln(False)), ('layernorm bwd 4096x768 (+partials reduce)', ln(True)),
+                ('bias grad colsum 4096x768', colsum(H)), ('bias grad colsum 4096x3072', colsum(F)),
+                ('add 4096x768', ew('ADD', 2, H)), ('gelu 4096x3072', ew('GELU', 1, F)),
+                ('gelu_bwd 4096x3072', ew('GELU_BWD', 2, F)),
+                ('softmax fwd 49152x128', softmax(False)), ('softmax bwd 49152x128', softmax(True)),
+                ('adam 110M', adam())]
+
     if os.environ.get('GEMM_GRAPH_SUITE') == 'layout':
         out = []
         for (M, N, K) in [(4096, 3072, 768), (4096, 768, 3072), (4096, 768, 768), (4096, 4096, 4096)]:
@@ -142,7 +210,7 @@ def main():
     for name, make in cases():
         if a.only and a.only not in name:
             continue
-        sets = 2 if ('decoder' in name or '4096x4096' in name) else a.sets
+        sets = 2 if ('decoder' in name or '4096x4096' in name) else (12 if '768' in name and 'x3072' not in name and os.environ.get('GEMM_GRAPH_SUITE') == 'fused' else a.sets)
         go, flops = make(sets)
 
         def body():
@@ -159,7 +227,8 @@ def main():
         e1.record()
         e1.synchronize()
         us = e0.elapsed_ms(e1) * 1e3 / (n * a.reps)
-        print(json.dumps({'case': name, 'us_per_launch': round(us, 2), 'tflops': round(flops / us * 1e-6, 1),
+        unit = 'gbps' if os.environ.get('GEMM_GRAPH_SUITE') == 'fused' else 'tflops'
+        print(json.dumps({'case': name, 'us_per_launch': round(us, 2), unit: round(flops / us * (1e-3 if unit == 'gbps' else 1e-6), 1),
                           'launches_in_graph': g.n_kernels}), flush=True)
         del g, go
         api.empty_cache()

@@ -339,47 +339,60 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
 // dx per row; dgamma / dbeta accumulate in registers over the rows a warp owns, are combined per CTA in
 // shared memory and written as one partial row per CTA ([gridDim.x, cols], reduced afterwards).
 template <int NV>
-__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                         const float* __restrict__ mean,
-                                                         const float* __restrict__ rstd, const float* __restrict__ g,
-                                                         float* __restrict__ dx, float* __restrict__ dgamma_part,
-                                                         float* __restrict__ dbeta_part, int64_t rows, int cols,
-                                                         int64_t part_ld) {
+__global__ void __launch_bounds__(256, (NV <= 6 ? 2 : 1))
+ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const float* __restrict__ g, float* __restrict__ dx,
+                  float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows, int cols,
+                  int64_t part_ld) {
     LG_PDL_TRIGGER();
-    // 8 warps x cols floats: every warp parks its register partials here, then columns are summed over warps
+    // [gamma : cols floats][8 warps x cols floats]: gamma is re-read from here every row (keeps it out of the
+    // register file so two CTAs fit on an SM); every warp parks its register partials in its slot at the end
     extern __shared__ unsigned char smem_raw[];
-    float* stage = reinterpret_cast<float*>(smem_raw);
+    float* sgamma = reinterpret_cast<float*>(smem_raw);
+    float* stage = sgamma + cols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inv = 1.0f / (float)cols;
     const int nchunks = cols >> 2;
-    float4 gm[NV], ag[NV], ab[NV];
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x)
+        reinterpret_cast<float4*>(sgamma)[c] = reinterpret_cast<const float4*>(gamma)[c];
+    float4 ag[NV], ab[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        const int c = lane + 32 * j;
         ag[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < nchunks) gm[j] = reinterpret_cast<const float4*>(gamma)[c];
     }
+    __syncthreads();
     for (; row < rows; row += row_step) {
         const float4* px = reinterpret_cast<const float4*>(x + row * cols);
         const float4* pg = reinterpret_cast<const float4*>(g + row * cols);
-        const float mu = mean[row], rs = rstd[row];
         float4 xh[NV], gv[NV];
+        // all loads of the row are issued before anything depends on them
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) {
+                xh[j] = px[c];
+                gv[j] = pg[c];
+            }
+        }
+        const float mu = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int c = lane + 32 * j;
             if (c < nchunks) {
-                float4 xv = px[c];
-                gv[j] = pg[c];
-                xh[j].x = (xv.x - mu) * rs; xh[j].y = (xv.y - mu) * rs;
-                xh[j].z = (xv.z - mu) * rs; xh[j].w = (xv.w - mu) * rs;
-                const float d0 = gv[j].x * gm[j].x, d1 = gv[j].y * gm[j].y, d2 = gv[j].z * gm[j].z,
-                            d3 = gv[j].w * gm[j].w;
-                s1 += (d0 + d1) + (d2 + d3);
-                s2 += (d0 * xh[j].x + d1 * xh[j].y) + (d2 * xh[j].z + d3 * xh[j].w);
+                const float4 gm = reinterpret_cast<const float4*>(sgamma)[c];
+                xh[j].x = (xh[j].x - mu) * rs; xh[j].y = (xh[j].y - mu) * rs;
+                xh[j].z = (xh[j].z - mu) * rs; xh[j].w = (xh[j].w - mu) * rs;
+                ag[j].x += gv[j].x * xh[j].x; ag[j].y += gv[j].y * xh[j].y;
+                ag[j].z += gv[j].z * xh[j].z; ag[j].w += gv[j].w * xh[j].w;
+                ab[j].x += gv[j].x; ab[j].y += gv[j].y; ab[j].z += gv[j].z; ab[j].w += gv[j].w;
+                // from here on gv holds g * gamma
+                gv[j].x *= gm.x; gv[j].y *= gm.y; gv[j].z *= gm.z; gv[j].w *= gm.w;
+                s1 += (gv[j].x + gv[j].y) + (gv[j].z + gv[j].w);
+                s2 += (gv[j].x * xh[j].x + gv[j].y * xh[j].y) + (gv[j].z * xh[j].z + gv[j].w * xh[j].w);
             }
         }
         s1 = warp_sum(s1) * inv;
@@ -390,14 +403,11 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
             const int c = lane + 32 * j;
             if (c < nchunks) {
                 float4 r;
-                r.x = rs * (gv[j].x * gm[j].x - s1 - xh[j].x * s2);
-                r.y = rs * (gv[j].y * gm[j].y - s1 - xh[j].y * s2);
-                r.z = rs * (gv[j].z * gm[j].z - s1 - xh[j].z * s2);
-                r.w = rs * (gv[j].w * gm[j].w - s1 - xh[j].w * s2);
+                r.x = rs * (gv[j].x - s1 - xh[j].x * s2);
+                r.y = rs * (gv[j].y - s1 - xh[j].y * s2);
+                r.z = rs * (gv[j].z - s1 - xh[j].z * s2);
+                r.w = rs * (gv[j].w - s1 - xh[j].w * s2);
                 pd[c] = r;
-                ag[j].x += gv[j].x * xh[j].x; ag[j].y += gv[j].y * xh[j].y;
-                ag[j].z += gv[j].z * xh[j].z; ag[j].w += gv[j].w * xh[j].w;
-                ab[j].x += gv[j].x; ab[j].y += gv[j].y; ab[j].z += gv[j].z; ab[j].w += gv[j].w;
             }
         }
     }
@@ -699,7 +709,7 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
     void* pg = part;
     void* pb = (char*)part + (size_t)cols * es;
     if (fast) {
-        const size_t smem_fast = 8 * (size_t)cols * sizeof(float);   // <= 32 KB for cols <= 1024
+        const size_t smem_fast = 9 * (size_t)cols * sizeof(float);   // gamma + 8 warp slots: <= 36 KB for cols <= 1024
 #define LN_B(NV_)                                                                                              \
     ln_bwd_vec_kernel<NV_><<<grid, 256, smem_fast, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean, \
                                                           (const float*)rstd, (const float*)g, (float*)dx,     \

@@ -108,6 +108,22 @@ __global__ void __launch_bounds__(256) red_rows_block(const T* __restrict__ x, T
 }
 
 // ---- inner > 1 -----------------------------------------------------------------------------------
+// L2-coherent (L1-bypassing) vector load of partials written by other CTAs of the same launch
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> ldcg_vec(const T* p) {
+    Vec<T, V> r;
+    if constexpr (sizeof(Vec<T, V>) == 16) {
+        const float4 raw = __ldcg(reinterpret_cast<const float4*>(p));
+        memcpy(&r, &raw, 16);
+    } else if constexpr (sizeof(Vec<T, V>) == 8) {
+        const float2 raw = __ldcg(reinterpret_cast<const float2*>(p));
+        memcpy(&r, &raw, 8);
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) r.v[k] = __ldcg(p + k);
+    }
+    return r;
+}
 template <class R, typename T, int V>
 __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __restrict__ out, int64_t rlen,
                                                 int64_t inner, int64_t ld, int64_t chunk, int S, int64_t ntiles,
@@ -186,11 +202,38 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // final pass over the S partial rows of this column tile: warp ty takes partials ty, ty+8, ... (their loads
+    // are independent, so the whole pass costs about one L2 round trip), then the 8 warp sums are combined in
+    // a fixed order -- the result does not depend on which CTA happened to finish last
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = R::template init<T>();
+    if (col < inner) {
+        const T* q = out + o * S * inner + col;
+        int pp = ty;
+        for (; pp + 24 < S; pp += 32) {
+            VT w0 = ldcg_vec<T, V>(q + (int64_t)pp * inner), w1 = ldcg_vec<T, V>(q + (int64_t)(pp + 8) * inner),
+               w2 = ldcg_vec<T, V>(q + (int64_t)(pp + 16) * inner), w3 = ldcg_vec<T, V>(q + (int64_t)(pp + 24) * inner);
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                acc[k] = R::template comb<T>(R::template comb<T>(R::template comb<T>(acc[k], w0.v[k]), w1.v[k]),
+                                             R::template comb<T>(w2.v[k], w3.v[k]));
+        }
+        for (; pp < S; pp += 8) {
+            VT w0 = ldcg_vec<T, V>(q + (int64_t)pp * inner);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = R::template comb<T>(acc[k], w0.v[k]);
+        }
+    }
+    __syncthreads();   // everyone is done reading sm from the first pass
+#pragma unroll
+    for (int k = 0; k < V; ++k) sm[ty][tx * V + k] = acc[k];
+    __syncthreads();
     for (int c = threadIdx.x; c < 32 * V; c += 256) {
         int64_t gc = tile * 32 * V + c;
         if (gc >= inner) continue;
-        T v = R::template init<T>();
-        for (int pp = 0; pp < S; ++pp) v = R::template comb<T>(v, __ldcg(out + (o * S + pp) * inner + gc));
+        T v = sm[0][c];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) v = R::template comb<T>(v, sm[j][c]);
         T* dst = final_out + o * inner + gc;
         *dst = acc_out ? *dst + v * scale : v * scale;
     }
