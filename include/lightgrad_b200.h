@@ -124,6 +124,15 @@ int lg_profiler_range(int start);
 /* keeps the compute stream busy for `us` microseconds (measurement aid: work queued behind it runs back
  * to back on the device, so events between kernels are free of host dispatch latency) */
 int lg_stream_delay_us(uint64_t us);
+/* Side stream.  Launches issued between lg_side_begin and lg_side_end go to a second stream that is ordered
+ * after everything issued on the compute stream so far and runs concurrently with what follows (weight / bias
+ * gradients, which nothing else in backward waits for, backfill the SMs a one-wave GEMM leaves idle; the
+ * reference has a single in-order OpenCL queue, opencl/device.py:58-60).  lg_side_join makes the compute stream
+ * wait for them; lg_sync, lg_memcpy_d2h, lg_graph_begin/end and lg_nccl_fork join / order implicitly.  The caller
+ * keeps every buffer those launches touch alive until the join. */
+int lg_side_begin(void);
+int lg_side_end(void);
+int lg_side_join(void);
 /* whole-step CUDA graphs: everything enqueued between begin and end (kernels, memsets, NCCL calls)
  * is recorded instead of executed; allocations made meanwhile come from a pool private to the
  * graph (*pool_id: 0 = create one, reused by later re-captures).  lg_graph_launch replays the step

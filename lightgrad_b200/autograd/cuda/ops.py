@@ -16,6 +16,7 @@ from ..func import Function
 from ..tensor import AbstractTensor
 from .tensor import CudaTensor, i64arr, contiguous_strides, _prod
 from . import runtime as rt
+from ..grads import Gradients
 
 EW, RED = rt.EW, rt.RED
 _SCALARS = (int, float, np.integer, np.floating, bool, np.bool_)
@@ -24,6 +25,9 @@ _SCALARS = (int, float, np.integer, np.floating, bool, np.bool_)
 # matmul arithmetic mode: 'fp32' (exact FFMA, default), 'tf32' or 'bf16' (tcgen05 tensor cores)
 _MODES = {'fp32': rt.GEMM_FP32_SIMT, 'tf32': rt.GEMM_TF32_TC, 'bf16': rt.GEMM_BF16_TC}
 _matmul_mode = _MODES[os.environ.get('LG_MATMUL_MODE', 'fp32').lower()]
+
+
+Gradients.after_backward.append(rt.side_join)
 
 
 def set_matmul_mode(name):
@@ -455,6 +459,7 @@ class pow(Function):
 def _inplace(op, s_op, negate=False):
     class _Op(Function):
         def forward(ctx, t, other):
+            rt.side_join_if_written(t)
             if _is_scalar(other):
                 v = -float(other) if negate else float(other)
                 if t._code not in (rt.F32, rt.F64):
@@ -844,23 +849,27 @@ class linear(Function):
         x2, weight, xshape, has_bias = ctx.get_saved_tensors()
         g2 = _fold_rows(out_grad)
         dx = _with_shape(_gemm(g2, weight), xshape)
-        wg = weight.grad
-        if weight.requires_grad and wg is not None and wg._contig and wg._code == g2._code == rt.F32 \
-                and wg._shape == weight._shape:
-            # dW += dY^T X straight into the existing gradient (the optimizer's arena): no temporary, no add pass
+        wg = _direct_grad(weight, g2._code)
+        bias = ctx._parents[2] if has_bias else None
+        bg = _direct_grad(bias, g2._code) if has_bias else None
+        if bg is not None and not (bg._shape == (g2._shape[1],) and g2._strides[1] == 1 and g2._shape[1] > 1):
+            bg = None
+        if wg is not None and (bg is not None or not has_bias):
+            # dW += dY^T X and db += column sums of dY go straight into the existing gradients (the optimizer's
+            # arena: no temporary, no add pass).  Nothing else in backward waits for them, so they are issued on
+            # the side stream and overlap the dX chain.
+            with rt.side_stream(g2, x2, writes=(wg,) if bg is None else (wg, bg)):
+                _gemm(_swap_last(g2), x2, out=wg, accumulate=True)
+                if bg is not None:
+                    rt.api.reduce_pitched(RED['SUM'], g2._code, g2.ptr, bg.ptr, 1, g2._shape[0], g2._shape[1],
+                                          g2._strides[0], 1.0, 1)
+            return (dx, Function.ACCUMULATED, Function.ACCUMULATED) if has_bias else (dx, Function.ACCUMULATED)
+        if wg is not None:
             _gemm(_swap_last(g2), x2, out=wg, accumulate=True)
             dw = Function.ACCUMULATED
         else:
             dw = _gemm(_swap_last(g2), x2)
         if has_bias:
-            bias = ctx._parents[2]
-            bg = bias.grad if isinstance(bias, CudaTensor) and bias.requires_grad else None
-            if bg is not None and bg._contig and bg._code == g2._code and bg._shape == (g2._shape[1],) \
-                    and g2._strides[1] == 1 and g2._shape[1] > 1:
-                # db += column sums of dY, reduced straight into the existing gradient
-                rt.api.reduce_pitched(RED['SUM'], g2._code, g2.ptr, bg.ptr, 1, g2._shape[0], g2._shape[1],
-                                      g2._strides[0], 1.0, 1)
-                return dx, dw, Function.ACCUMULATED
             return dx, dw, _reduce(RED['SUM'], g2, (0,), False)
         return dx, dw
 
@@ -968,16 +977,23 @@ class self_attention(Function):
         _gemm_grouped(parts, list(ws), [dx] * 3)                        # dX = sum_g dY_g W_g
         dx = _with_shape(dx, xshape)
         wgs = [_direct_grad(w, x2._code) for w in ws]
+        bgs = [_direct_grad(bias, x2._code) for bias in (bq, bk, bv)]
         pt = [_swap_last(t) for t in parts]
+        if all(w is not None for w in wgs) and all(b is not None for b in bgs) and H > 1:
+            # dW_g += dY_g^T X and db_g += colsum(dY_g), straight into the arena, on the side stream
+            with rt.side_stream(dqkv, x2, writes=tuple(wgs) + tuple(bgs)):
+                _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True)
+                for part, bg in zip(parts, bgs):
+                    rt.api.reduce_pitched(RED['SUM'], part._code, part.ptr, bg.ptr, 1, rows, H, H, 1.0, 1)
+            return (dx,) + (Function.ACCUMULATED,) * 6
         if all(w is not None for w in wgs):
-            _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True)           # dW_g += dY_g^T X, straight into the arena
+            _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True)
             dws = [Function.ACCUMULATED] * 3
         else:
             dws = [CudaTensor._new((H, H), x2._dtype) for _ in range(3)]
             _gemm_grouped(pt, [x2] * 3, dws)
         dbs = []
-        for part, bias in zip(parts, (bq, bk, bv)):
-            bg = _direct_grad(bias, x2._code)
+        for part, bg in zip(parts, bgs):
             if bg is not None and H > 1:
                 rt.api.reduce_pitched(RED['SUM'], part._code, part.ptr, bg.ptr, 1, rows, H, H, 1.0, 1)
                 dbs.append(Function.ACCUMULATED)

@@ -65,6 +65,9 @@ _SIGNATURES = {
     'lg_graph_begin': [C.POINTER(C.c_int)],
     'lg_graph_end': [C.POINTER(_vp), C.POINTER(C.c_uint64)],
     'lg_graph_abort': [],
+    'lg_side_begin': [],
+    'lg_side_end': [],
+    'lg_side_join': [],
     'lg_graph_launch': [_vp, C.c_uint64],
     'lg_graph_destroy': [_vp],
     'lg_ew_flat': [C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_double],
@@ -168,6 +171,45 @@ def ensure_device(device=-1):
 
 def synchronize():
     ensure_device().sync()
+    _side_held.clear()
+    _side_dirty.clear()
+
+
+# ---- side stream (lg_side_begin / end / join) ----------------------------------------------------------
+_side_held = []          # tensors the side stream's launches touch: kept alive until the join
+_side_dirty = set()      # device addresses of gradients the side stream accumulates into
+
+
+class side_stream(object):
+    """``with side_stream(x, g): ...`` issues the block's launches on the side stream (they run concurrently
+    with whatever the compute stream does next) and keeps the given tensors alive until ``side_join``."""
+
+    def __init__(self, *hold, writes=()):
+        self.hold, self.writes = hold, writes
+
+    def __enter__(self):
+        api.side_begin()
+        _side_held.extend(self.hold)
+        _side_held.extend(self.writes)
+        for t in self.writes:
+            _side_dirty.add(t.ptr)
+
+    def __exit__(self, *exc):
+        api.side_end()
+
+
+def side_join():
+    """Compute stream waits for the side stream (no-op when nothing is outstanding)."""
+    if api is not None and _ready:
+        api.side_join()      # cheap when nothing is outstanding (the library tracks it)
+    _side_held.clear()
+    _side_dirty.clear()
+
+
+def side_join_if_written(t):
+    """Called before the compute stream updates ``t`` in place: orders it after side-stream writes to ``t``."""
+    if _side_dirty and t.ptr in _side_dirty:
+        side_join()
 
 
 def launch_count():

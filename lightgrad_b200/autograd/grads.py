@@ -47,6 +47,9 @@ class Gradients(object):
     # gradient contribution (lets the data-parallel wrapper start reducing finished gradients while the
     # rest of backward is still running)
     leaf_hook = None
+    # callables run when the OUTERMOST walk is over (a backend joins work it issued asynchronously, e.g. weight
+    # gradients computed on a second stream)
+    after_backward = []
     _walking = 0
 
     @staticmethod
@@ -140,3 +143,6 @@ class Gradients(object):
             Gradients._walking -= 1
             d = Gradients._depth - 1
             Gradients._depth = d if d > 0 else 0
+            if Gradients._walking == 0:
+                for fn in Gradients.after_backward:
+                    fn()

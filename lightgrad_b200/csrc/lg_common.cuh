@@ -17,7 +17,10 @@ namespace lg {
 
 // ---- error plumbing ---------------------------------------------------------------------------
 int set_error(const char* fmt, ...);
-cudaStream_t stream();        // compute stream
+cudaStream_t stream();        // stream kernels launch on: the compute stream, or the side stream inside lg_side_begin/end
+bool on_side_stream();
+int side_join();
+int side_order_before(cudaStream_t other);
 cudaStream_t comm_stream();   // collective stream
 int sm_count();
 void count_launch(int n = 1);

@@ -731,6 +731,12 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
         return set_error("ln_bwd launch failed: %s", cudaGetErrorString(e));
     }
     count_launch();
+    // the per-CTA partials are summed into d(gamma), d(beta) on the side stream: only the optimizer needs them
+    const bool side = accumulate && !on_side_stream();
+    if (side && lg_side_begin()) {
+        tmp_free(part);
+        return 1;
+    }
     int rc;
     if (cols <= 1) rc = set_error("lg_layernorm_bwd: cols must be > 1");
     else if ((char*)dbeta == (char*)dgamma + (size_t)cols * es)
@@ -739,7 +745,8 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
         rc = lg_reduce_pitched(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, part_ld, 1.0, accumulate);
         if (!rc) rc = lg_reduce_pitched(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, part_ld, 1.0, accumulate);
     }
-    tmp_free(part);
+    tmp_free(part);      // deferred until the join while on the side stream
+    if (side) lg_side_end();
     return rc;
 }
 

@@ -84,6 +84,8 @@ int lg_nccl_fork(void) {
     LG_REQUIRE(g_comm_nccl, "lg_nccl_fork: communicator not initialised");
     LG_CUDA(cudaEventRecord(g_ev_fork, stream()));
     LG_CUDA(cudaStreamWaitEvent(comm_stream(), g_ev_fork, 0));
+    // weight gradients are accumulated on the side stream: the collective must see those writes too
+    if (side_order_before(comm_stream())) return 1;
     return 0;
 }
 

@@ -16,6 +16,13 @@ namespace lg {
 static thread_local char g_err[1024] = "";
 static int g_device = -1;
 static cudaStream_t g_stream = nullptr, g_comm = nullptr;
+// side stream: work that nothing on the critical path of backward waits for (weight / bias gradients) is
+// issued here between lg_side_begin / lg_side_end and runs concurrently with the main stream, backfilling
+// the SMs a one-wave GEMM leaves idle.  g_cur is the stream every kernel wrapper launches on.
+static cudaStream_t g_side = nullptr, g_cur = nullptr;
+static cudaEvent_t g_ev_side_fork = nullptr, g_ev_side_join = nullptr;
+static bool g_side_mode = false, g_side_pending = false;
+static std::vector<void*> g_side_deferred;   // blocks freed in side mode: reusable only after the join
 static int g_sms = 148;
 static std::atomic<uint64_t> g_launches{0};
 
@@ -26,7 +33,8 @@ int set_error(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
-cudaStream_t stream() { return g_stream; }
+cudaStream_t stream() { return g_cur; }
+bool on_side_stream() { return g_side_mode; }
 cudaStream_t comm_stream() { return g_comm; }
 int sm_count() { return g_sms; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
@@ -114,7 +122,27 @@ bool capturing() { return g_capturing; }
 
 void* tmp_alloc(size_t nbytes) { return g_cache->get(nbytes ? nbytes : 1); }
 void tmp_free(void* p) {
-    if (p) g_cache->put(p);
+    if (!p) return;
+    if (g_side_mode) g_side_deferred.push_back(p);
+    else g_cache->put(p);
+}
+
+// main stream waits for everything issued on the side stream so far; deferred blocks become reusable
+int side_join() {
+    if (!g_side_pending) return 0;
+    LG_CUDA(cudaEventRecord(g_ev_side_join, g_side));
+    LG_CUDA(cudaStreamWaitEvent(g_stream, g_ev_side_join, 0));
+    for (void* p : g_side_deferred) g_cache->put(p);
+    g_side_deferred.clear();
+    g_side_pending = false;
+    return 0;
+}
+// `other` (the collective stream) must also see side-stream writes issued so far
+int side_order_before(cudaStream_t other) {
+    if (!g_side_pending) return 0;
+    LG_CUDA(cudaEventRecord(g_ev_side_join, g_side));
+    LG_CUDA(cudaStreamWaitEvent(other, g_ev_side_join, 0));
+    return 0;
 }
 
 static int do_init(int device) {
@@ -144,6 +172,10 @@ static int do_init(int device) {
     g_sms = prop.multiProcessorCount;
     LG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     LG_CUDA(cudaStreamCreateWithFlags(&g_comm, cudaStreamNonBlocking));
+    LG_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+    LG_CUDA(cudaEventCreateWithFlags(&g_ev_side_fork, cudaEventDisableTiming));
+    LG_CUDA(cudaEventCreateWithFlags(&g_ev_side_join, cudaEventDisableTiming));
+    g_cur = g_stream;
     g_cache = new Cache();
     g_device = device;
     return 0;
@@ -213,6 +245,7 @@ int lg_device_props(int* sm_count_, int* cc_major, int* cc_minor, size_t* total_
 int lg_sync(void) {
     LG_INIT();
     LG_REQUIRE(!g_capturing, "lg_sync: cannot synchronise while a step is being captured into a CUDA graph");
+    if (side_join()) return 1;
     LG_CUDA(cudaStreamSynchronize(g_stream));
     LG_CUDA(cudaStreamSynchronize(g_comm));
     return 0;
@@ -228,11 +261,45 @@ int lg_alloc(size_t nbytes, void** ptr) {
 
 int lg_free(void* ptr) {
     if (!ptr || !g_cache) return 0;
+    if (g_side_mode) {
+        g_side_deferred.push_back(ptr);
+        return 0;
+    }
     return g_cache->put(ptr);
+}
+
+// ---- side stream ---------------------------------------------------------------------------------
+// lg_side_begin .. lg_side_end brackets launches that go to the side stream (ordered after everything issued
+// on the main stream so far); lg_side_join makes the main stream wait for them.  The CALLER keeps every
+// buffer those launches touch alive until the join.  LG_NO_SIDE_STREAM=1 turns the bracket into a no-op.
+int lg_side_begin(void) {
+    LG_INIT();
+    static const bool off = getenv("LG_NO_SIDE_STREAM") != nullptr;
+    if (off) return 0;
+    LG_REQUIRE(!g_side_mode, "lg_side_begin: already on the side stream");
+    LG_CUDA(cudaEventRecord(g_ev_side_fork, g_stream));
+    LG_CUDA(cudaStreamWaitEvent(g_side, g_ev_side_fork, 0));
+    g_cur = g_side;
+    g_side_mode = true;
+    g_side_pending = true;
+    return 0;
+}
+
+int lg_side_end(void) {
+    g_cur = g_stream;
+    g_side_mode = false;
+    return 0;
+}
+
+int lg_side_join(void) {
+    LG_INIT();
+    LG_REQUIRE(!g_side_mode, "lg_side_join: still inside lg_side_begin / lg_side_end");
+    return side_join();
 }
 
 int lg_empty_cache(void) {
     LG_INIT();
+    if (side_join()) return 1;
     LG_CUDA(cudaStreamSynchronize(g_stream));
     std::lock_guard<std::mutex> lk(g_cache->mu);
     g_cache->release_all();
@@ -261,6 +328,7 @@ int lg_memcpy_d2h(void* dst, const void* src, size_t nbytes) {
     LG_INIT();
     LG_REQUIRE(!g_capturing, "lg_memcpy_d2h: reading a tensor back (numpy()/item()) is not possible while a step is "
                              "being captured into a CUDA graph");
+    if (side_join()) return 1;
     if (nbytes) LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
     LG_CUDA(cudaStreamSynchronize(g_stream));
     return 0;
@@ -326,6 +394,7 @@ void* lg_stream_handle(void) { return (void*)g_stream; }
 int lg_graph_begin(int* pool_id) {
     LG_INIT();
     LG_REQUIRE(!g_capturing, "lg_graph_begin: a capture is already in progress");
+    if (side_join()) return 1;
     LG_CUDA(cudaStreamSynchronize(g_stream));
     {
         std::lock_guard<std::mutex> lk(g_cache->mu);
@@ -343,6 +412,10 @@ int lg_graph_begin(int* pool_id) {
 
 int lg_graph_end(void** graph_exec, uint64_t* n_nodes) {
     LG_REQUIRE(g_capturing, "lg_graph_end: no capture in progress");
+    // a forked side stream must rejoin the capturing stream before the capture can end
+    g_cur = g_stream;
+    g_side_mode = false;
+    if (side_join()) return 1;
     g_capturing = false;
     {
         std::lock_guard<std::mutex> lk(g_cache->mu);
@@ -367,6 +440,9 @@ int lg_graph_end(void** graph_exec, uint64_t* n_nodes) {
 
 int lg_graph_abort(void) {
     if (!g_capturing) return 0;
+    g_cur = g_stream;
+    g_side_mode = false;
+    side_join();
     g_capturing = false;
     g_cache->cur_pool = 0;
     cudaGraph_t graph = nullptr;

@@ -217,6 +217,12 @@ class FakeDevice(object):
                       1 if (accumulate or again) else 0)
             seen.append(c[g])
 
+    def side_begin(self): pass
+
+    def side_end(self): pass
+
+    def side_join(self): pass
+
     def gemm_tc_supported(self, mode, dt, dref):
         return 1 if mode != rt.GEMM_FP32_SIMT and dt == rt.F32 else 0
 
