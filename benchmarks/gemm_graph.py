@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lightgrad_b200 import CudaTensor                                  # noqa: E402
 from lightgrad_b200.autograd.cuda import ops, runtime as rt            # noqa: E402
 from lightgrad_b200.autograd.cuda.graph import StepGraph               # noqa: E402
-from lightgrad_b200.autograd.cuda.ops import _gemm, _gemm_grouped, _swap_last   # noqa: E402
+from lightgrad_b200.autograd.cuda.ops import _gemm, _gemm_grouped, _gemm_epilogue, _swap_last   # noqa: E402
 
 R, H, F, V = 4096, 768, 3072, 30522          # rows = batch 32 x seq 128
 
@@ -84,6 +84,22 @@ def cases():
                 parts = [_swap_last(G[i]._view((R, H), (H, 1), g * R * H)) for g in range(3)]
                 _gemm_grouped(parts, [X[i]] * 3, O[i], accumulate=True)
             return go, 3 * 2.0 * R * H * H
+        return make
+
+    def epi(kind):
+        def make(sets):
+            if kind == 1:      # h = x W1^T + b1, act = gelu(h)
+                X = [rand(R, H) for _ in range(sets)]
+                W = [rand(F, H) for _ in range(sets)]
+                b = rand(F)
+                O = [CudaTensor.empty((R, F)) for _ in range(sets)]
+                A = [CudaTensor.empty((R, F)) for _ in range(sets)]
+                return (lambda i: _gemm_epilogue(X[i], _swap_last(W[i]), O[i], b, 1, A[i])), 2.0 * R * H * F
+            G = [rand(R, H) for _ in range(sets)]
+            W = [rand(H, F) for _ in range(sets)]
+            Hh = [rand(R, F) for _ in range(sets)]
+            O = [CudaTensor.empty((R, F)) for _ in range(sets)]
+            return (lambda i: _gemm_epilogue(G[i], W[i], O[i], None, 2, Hh[i])), 2.0 * R * H * F
         return make
 
     def att(kind):
@@ -193,6 +209,7 @@ def cases():
         ('proj fwd 4096x768x768', fwd(H, H)), ('proj dX', dx(H, H)), ('proj dW (acc)', dw(H, H)),
         ('ffn1 fwd 4096x3072x768', fwd(H, F)), ('ffn1 dX', dx(H, F)), ('ffn1 dW (acc)', dw(H, F)),
         ('ffn2 fwd 4096x768x3072', fwd(F, H)), ('ffn2 dX', dx(F, H)), ('ffn2 dW (acc)', dw(F, H)),
+        ('ffn1 fwd + gelu epilogue (2 results)', epi(1)), ('ffn2 dX * gelu\' epilogue', epi(2)),
         ('qkv grouped fwd', qkv_fwd()), ('qkv k-concat dX', qkv_dx()), ('qkv grouped dW (acc)', qkv_dw()),
         ('attn QK^T 384x128x128x64', att('qk')), ('attn PV', att('pv')), ('attn P^T dO', att('ptv')),
         ('decoder fwd 4096x30522x768', fwd(H, V)), ('decoder dX', dx(H, V)), ('decoder dW (acc)', dw(H, V)),

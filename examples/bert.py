@@ -115,6 +115,10 @@ class BertLayer(nn.Module):
         self.output.LayerNorm = nn.LayerNorm(hidden_size)
 
     def mlp(self, x):
+        if hasattr(x, 'mlp_gelu'):
+            # both GEMMs, the bias adds and the GELU (forward and derivative) as one graph node
+            d1, d2 = self.intermediate.dense, self.output.dense
+            return x.mlp_gelu(d1.weight, d1.bias, d2.weight, d2.bias)
         return self.output.dense(gelu(self.intermediate.dense(x)))
 
     def forward(self, hidden, attention_mask=None, need_probs=True):

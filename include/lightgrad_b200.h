@@ -189,6 +189,14 @@ int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void*
  * C: with accumulate != 0 every group adds into it (dX = sum_g dY_g W_g). */
 int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const void* const* a, const void* const* b,
                     void* const* c, const void* const* bias, int accumulate);
+/* One plain (unbatched) product with an activation fused into its epilogue -- the two halves of
+ * gelu(x W1^T + b1) in BertLayer (examples/bert.py:12,150-153 of the reference):
+ *   LG_EPI_GELU_FWD: c = a b + bias (kept for backward) and aux = gelu(c), both written by the epilogue;
+ *   LG_EPI_GELU_BWD: c = (a b) * gelu'(aux), aux = the pre-activation saved by the forward call.
+ * aux has c's shape, row pitch aux_ld elements. */
+typedef enum { LG_EPI_NONE = 0, LG_EPI_GELU_FWD = 1, LG_EPI_GELU_BWD = 2 } LgGemmEpilogue;
+int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias,
+                     int epi_op, void* aux, int64_t aux_ld);
 /* measurement hooks for the matmul share of a step (off by default):
  * lg_prof_gemm(1): CUDA events on the compute stream around every lg_gemm launch;
  * lg_prof_gemm(2): lg_gemm launches NOTHING and only counts -- timing a captured step with and without its

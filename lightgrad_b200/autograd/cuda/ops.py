@@ -848,7 +848,15 @@ class linear(Function):
     def backward(ctx, out_grad):
         x2, weight, xshape, has_bias = ctx.get_saved_tensors()
         g2 = _fold_rows(out_grad)
-        dx = _with_shape(_gemm(g2, weight), xshape)
+        xin = ctx._parents[0]
+        xg = _direct_grad(xin, g2._code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
+        if xg is not None:
+            # x already holds a gradient from another consumer (residual branch): dX is reduce-added into it by
+            # the GEMM epilogue instead of being materialised and added by a separate pass
+            _gemm(g2, weight, out=_fold_rows(xg), accumulate=True)
+            dx = Function.ACCUMULATED
+        else:
+            dx = _with_shape(_gemm(g2, weight), xshape)
         wg = _direct_grad(weight, g2._code)
         bias = ctx._parents[2] if has_bias else None
         bg = _direct_grad(bias, g2._code) if has_bias else None
@@ -905,6 +913,77 @@ def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False):
                         arr(*[t.ptr for t in outs]),
                         arr(*[t.ptr for t in biases]) if biases is not None else None, 1 if accumulate else 0)
     return outs
+
+
+def _gemm_epilogue(a, b, out, bias, epi, aux):
+    """One plain 2-D product with an activation fused into the GEMM epilogue (lg_gemm_epilogue):
+    epi 1: out = a @ b + bias and aux = gelu(out);   epi 2: out = (a @ b) * gelu'(aux)."""
+    M, K = a._shape
+    N = b._shape[1]
+    assert b._shape[0] == K and out._shape == (M, N) == aux._shape and out._strides[1] == 1 == aux._strides[1]
+    d = rt.GemmDesc(M, N, K, 1, 1, 0, 0, a._strides[0], a._strides[1], 0, 0, b._strides[0], b._strides[1],
+                    0, 0, out._strides[0], 1)
+    rt.api.gemm_epilogue(_matmul_mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr,
+                         bias.ptr if bias is not None else None, epi, aux.ptr, aux._strides[0])
+    return out
+
+
+@CudaTensor.register_op()
+class mlp_gelu(Function):
+    """y = gelu(x W1^T + b1) W2^T + b2 -- the feed-forward block of BertLayer (examples/bert.py:150-153 of the
+    reference: output.dense(gelu(intermediate.dense(x)))) as one graph node.
+
+    Forward: the first GEMM's epilogue adds the bias and writes both the pre-activation h (kept for backward)
+    and gelu(h); backward: the GEMM that forms d(gelu(h)) = dY W2 multiplies by gelu'(h) in its epilogue, so the
+    (rows x intermediate) activation gradient is never written un-multiplied; weight / bias gradients go to the
+    side stream and into the optimizer's arena; dX is added into x's gradient when the residual branch already
+    delivered one.
+    """
+    def forward(ctx, x, w1, b1, w2, b2):
+        x = _float_like(x)
+        x2 = _fold_rows(x)
+        if not x2._contig and x2._strides[1] != 1:
+            x2 = x2.contiguous()
+        x2._mark_shared()
+        rows, F = x2._shape[0], w1._shape[0]
+        h = CudaTensor._new((rows, F), x._dtype)
+        act = CudaTensor._new((rows, F), x._dtype)
+        _gemm_epilogue(x2, _swap_last(w1), h, b1, 1, act)
+        y = _gemm(act, _swap_last(w2), bias=b2)
+        h._temp = act._temp = False
+        ctx.save_for_backward(x2, h, act, x._shape)
+        return _with_shape(y, x._shape[:-1] + (w2._shape[0],))
+
+    def backward(ctx, out_grad):
+        x2, h, act, xshape = ctx.get_saved_tensors()
+        xin, w1, b1, w2, b2 = ctx._parents[:5]
+        g2 = _fold_rows(out_grad)
+        if g2._code != x2._code:
+            g2 = g2.astype(x2._dtype)
+        if g2._strides[1] != 1:
+            g2 = g2.contiguous()
+        code = x2._code
+        dh = CudaTensor._new(h._shape, h._dtype)
+        _gemm_epilogue(g2, w2, dh, None, 2, h)                     # dh = (dY W2) * gelu'(h)
+        xg = _direct_grad(xin, code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
+        if xg is not None:
+            _gemm(dh, w1, out=_fold_rows(xg), accumulate=True)
+            dx = Function.ACCUMULATED
+        else:
+            dx = _with_shape(_gemm(dh, w1), xshape)
+        grads = [_direct_grad(p, code) for p in (w1, b1, w2, b2)]
+        if all(g is not None for g in grads) and min(w1._shape[0], w2._shape[0]) > 1:
+            w1g, b1g, w2g, b2g = grads
+            with rt.side_stream(g2, dh, act, x2, writes=tuple(grads)):
+                _gemm(_swap_last(g2), act, out=w2g, accumulate=True)
+                rt.api.reduce_pitched(RED['SUM'], code, g2.ptr, b2g.ptr, 1, g2._shape[0], g2._shape[1],
+                                      g2._strides[0], 1.0, 1)
+                _gemm(_swap_last(dh), x2, out=w1g, accumulate=True)
+                rt.api.reduce_pitched(RED['SUM'], code, dh.ptr, b1g.ptr, 1, dh._shape[0], dh._shape[1],
+                                      dh._strides[0], 1.0, 1)
+            return (dx,) + (Function.ACCUMULATED,) * 4
+        return (dx, _gemm(_swap_last(dh), x2), _reduce(RED['SUM'], dh, (0,), False),
+                _gemm(_swap_last(g2), act), _reduce(RED['SUM'], g2, (0,), False))
 
 
 def _direct_grad(p, code):
@@ -973,9 +1052,16 @@ class self_attention(Function):
         _gemm(_swap_last(ds), q, out=dk)                                # dK = dS^T Q
         parts = [dqkv._view((rows, H), (H, 1), i * rows * H) for i in range(3)]
         ws = (wq, wk, wv)
-        dx = CudaTensor._new((rows, H), x2._dtype)
-        _gemm_grouped(parts, list(ws), [dx] * 3)                        # dX = sum_g dY_g W_g
-        dx = _with_shape(dx, xshape)
+        xin = ctx._parents[0]
+        xg = _direct_grad(xin, x2._code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
+        if xg is not None:
+            # dX = sum_g dY_g W_g added into the gradient x already received through the residual branch
+            _gemm_grouped(parts, list(ws), [_fold_rows(xg)] * 3, accumulate=True)
+            dx = Function.ACCUMULATED
+        else:
+            dx = CudaTensor._new((rows, H), x2._dtype)
+            _gemm_grouped(parts, list(ws), [dx] * 3)                    # dX = sum_g dY_g W_g
+            dx = _with_shape(dx, xshape)
         wgs = [_direct_grad(w, x2._code) for w in ws]
         bgs = [_direct_grad(bias, x2._code) for bias in (bq, bk, bv)]
         pt = [_swap_last(t) for t in parts]

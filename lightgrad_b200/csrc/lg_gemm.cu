@@ -7,7 +7,9 @@ int gemm_simt(int dtype, const LgGemmDesc* d, const void* a, const void* b, void
 int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate);
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c);
 int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
-                    const void* const* bias, int accumulate);
+                    const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld);
+int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
+                     int64_t aux_ld);
 }  // namespace lg
 
 using namespace lg;
@@ -110,7 +112,7 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
     }
     int rc = 0;
     if (tc) {
-        rc = gemm_tc_grouped(d, groups, a, b, c, bias, accumulate);
+        rc = gemm_tc_grouped(d, groups, a, b, c, bias, accumulate, 0, nullptr, 0);
     } else {
         // exact path: one launch per group (a repeated C accumulates from the second group on)
         for (int g = 0; g < groups && !rc; ++g) {
@@ -118,6 +120,45 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
             for (int h = 0; h < g; ++h) seen = seen || c[h] == c[g];
             rc = gemm_simt(dtype, d, a[g], b[g], c[g], (bias && !seen) ? bias[g] : nullptr, (accumulate || seen) ? 1 : 0);
         }
+    }
+    if (g_prof_on) {
+        LG_CUDA(cudaEventRecord(pr.e1, stream()));
+        g_probes.push_back(pr);
+    }
+    return rc;
+}
+
+int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias,
+                     int epi_op, void* aux, int64_t aux_ld) {
+    LG_INIT();
+    LG_REQUIRE(epi_op == LG_EPI_GELU_FWD || epi_op == LG_EPI_GELU_BWD, "lg_gemm_epilogue: unknown epilogue %d", epi_op);
+    LG_REQUIRE(d->batch0 == 1 && d->batch1 == 1 && d->sc_n == 1, "lg_gemm_epilogue: one plain row-major result");
+    LG_REQUIRE(aux && aux_ld >= d->N, "lg_gemm_epilogue: aux operand missing");
+    if (g_skip) {
+        g_skip_launches += 1;
+        g_skip_flops += 2.0 * (double)d->M * (double)d->N * (double)d->K;
+        return 0;
+    }
+    const bool tc = mode != LG_GEMM_FP32_SIMT && gemm_tc_supported(mode, dtype, d, a, b, c) &&
+                    (((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0 && d->N % 4 == 0;
+    GemmProbe pr;
+    if (g_prof_on) {
+        LG_CUDA(cudaEventCreate(&pr.e0));
+        LG_CUDA(cudaEventCreate(&pr.e1));
+        pr.flops = 2.0 * (double)d->M * (double)d->N * (double)d->K;
+        LG_CUDA(cudaEventRecord(pr.e0, stream()));
+    }
+    int rc;
+    if (tc) {
+        rc = gemm_tc_epilogue(d, a, b, c, bias, epi_op, aux, aux_ld);
+    } else {
+        // exact path: the product, then the activation as a strided elementwise pass over the same buffers
+        rc = gemm_simt(dtype, d, a, b, c, bias, 0);
+        const int64_t shape[2] = {d->M, d->N}, sc[2] = {d->sc_m, 1}, sx[2] = {aux_ld, 1};
+        if (!rc && epi_op == LG_EPI_GELU_FWD)
+            rc = lg_ew(LG_EW_GELU, dtype, 2, shape, c, sc, nullptr, nullptr, nullptr, nullptr, aux, sx, 0.0);
+        else if (!rc)
+            rc = lg_ew(LG_EW_GELU_BWD, dtype, 2, shape, aux, sx, c, sc, nullptr, nullptr, c, sc, 0.0);
     }
     if (g_prof_on) {
         LG_CUDA(cudaEventRecord(pr.e1, stream()));

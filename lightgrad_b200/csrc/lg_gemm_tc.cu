@@ -12,7 +12,7 @@
 //   warp 0        TMA producer          (ring of kStages {A,B} stages, full/empty mbarriers)
 //   warp 1        TMEM allocator + MMA issuer (one elected lane; 4 x tcgen05.mma m128nBNk8 per stage;
 //                                       tcgen05.commit releases the stage / publishes the accumulator)
-//   warps 2..5    epilogue: tcgen05.ld 32x32b.x32 -> (+bias) -> swizzled smem -> TMA store
+//   warps 2..9    epilogue (two per TMEM lane quarter, alternate 32-column chunks): tcgen05.ld 32x32b.x32 -> (+bias) -> swizzled smem -> TMA store
 //                 (cp.reduce.async.bulk.tensor .add when the K range is split across CTAs)
 //   two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 // Roofline: tensor pipe (TF32 dense = half the bf16 rate).  Algorithmic flops 2*M*N*K.
@@ -28,7 +28,8 @@ constexpr int LG_MAX_GROUPS = 4;
 constexpr int BM = 128;
 constexpr int BK = 32;               // fp32 elements per K step = 128 bytes
 constexpr int A_STAGE_BYTES = BM * 128;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, taking alternate 32-column chunks
+constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
 constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 32 fp32, per warp, double buffered
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,12 +173,16 @@ struct TcParams {
     int reduce_out;           // 1: C += tile (TMA reduce-add): split-K partials and/or accumulate mode
     int groups;               // problems of identical shape served by this launch (1-CTA kernel only)
     int a_chunked, b_chunked; // MN-major operand addressed through a rank-5 chunked map (one box per stage)
+    int epi_op;               // LgGemmEpilogue: 0 none, 1 aux = gelu(C) as a second result, 2 C = acc * gelu'(aux)
+    const float* aux;         // epi_op 2: pre-activation matrix (same shape as C), row pitch aux_ld elements
+    long long aux_ld;
     int kcat;                 // operand pairs concatenated along K into ONE result: C = sum_g A_g B_g (1-CTA kernel)
     const float* bias[LG_MAX_GROUPS];
 };
 
 struct TcMaps {
     CUtensorMap a[LG_MAX_GROUPS], b[LG_MAX_GROUPS], c[LG_MAX_GROUPS];
+    CUtensorMap aux;          // epi_op 1: second result, same geometry as c[0]
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -203,77 +208,104 @@ __device__ __forceinline__ float bias_slice(const float* bias, int col, int N) {
     return (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
 }
 
+// GELU in the epilogue: only 4 warps per SM do this work, so tanh is formed as 1 - 2 / (exp(2u) + 1) from
+// ex2.approx and rcp.approx (abs. error ~2e-7, well inside the tf32 result's own rounding) instead of tanhf
+__device__ __forceinline__ float epi_tanh(float u) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * 2.885390081777927f));   // exp(2u) = 2^(2u log2 e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+__device__ __forceinline__ float epi_gelu(float x) {
+    const float inner = (x * 0.7978845608f) * (1.0f + (0.044715f * x) * x);
+    return (0.5f * x) * (1.0f + epi_tanh(inner));
+}
+__device__ __forceinline__ float epi_gelu_bwd(float x, float g) {
+    const float c1 = 0.7978845608f, c2 = 0.044715f;
+    const float x2 = x * x;
+    const float t = epi_tanh((x * c1) * (1.0f + c2 * x2));
+    const float du = c1 * (1.0f + 3.0f * c2 * x2);
+    return (0.5f * (1.0f + t) + (0.5f * x) * (1.0f - t * t) * du) * g;
+}
+
 struct EpiTile {
     const CUtensorMap* map_c;
+    const CUtensorMap* map_aux;   // epi_op 1
     const float* bias;      // nullptr: none (also for split-K partials other than the first)
+    const float* aux;       // epi_op 2: row `row0 + lane` of the pre-activation matrix, or nullptr past the last row
+    int epi_op;
     int row0, n0, N;        // first output row of this warp, first column of the tile, columns of C
     int bc1, bc0;           // batch coordinates
     int reduce_out;
     bool rows_live;
 };
 
-__device__ __forceinline__ void epi_emit(const EpiTile& t, const uint32_t (&v)[32], float bcur, int col0, uint8_t* buf,
-                                         int lane) {
-    // the TMA store that last read this buffer (two chunks ago) must have drained
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+// stage one 32 x 32 chunk (thread = row) in the 128B-swizzled buffer and hand it to the TMA unit
+__device__ __forceinline__ void epi_store(const CUtensorMap* map, const uint32_t (&v)[32], uint8_t* buf, int col0,
+                                          int row0, int bc1, int bc0, int reduce_out, int lane) {
+    // the TMA store that last read this warp's staging buffer must have drained
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float4 o;
-        o.x = __uint_as_float(v[4 * j + 0]);
-        o.y = __uint_as_float(v[4 * j + 1]);
-        o.z = __uint_as_float(v[4 * j + 2]);
-        o.w = __uint_as_float(v[4 * j + 3]);
-        if (t.bias != nullptr) {
-            o.x += __shfl_sync(0xffffffffu, bcur, 4 * j + 0);
-            o.y += __shfl_sync(0xffffffffu, bcur, 4 * j + 1);
-            o.z += __shfl_sync(0xffffffffu, bcur, 4 * j + 2);
-            o.w += __shfl_sync(0xffffffffu, bcur, 4 * j + 3);
-        }
-        // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
-        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
-    }
+    for (int j = 0; j < 8; ++j)   // 128-byte swizzle: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-        if (t.reduce_out) tma_reduce_add_4d(t.map_c, buf, col0, t.row0, t.bc1, t.bc0);
-        else tma_store_4d(t.map_c, buf, col0, t.row0, t.bc1, t.bc0);
+        if (reduce_out) tma_reduce_add_4d(map, buf, col0, row0, bc1, bc0);
+        else tma_store_4d(map, buf, col0, row0, bc1, bc0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 }
 
-// `bfirst` = bias_slice of the tile's first chunk, loaded by the caller BEFORE it waited for the accumulator
+// v: this thread's 32 accumulator values of the chunk (as raw bits), finished and stored in place
+__device__ __forceinline__ void epi_emit(const EpiTile& t, uint32_t (&v)[32], float bcur, int col0, uint8_t* buf,
+                                         int lane) {
+    if (t.bias != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __shfl_sync(0xffffffffu, bcur, k));
+    }
+    if (!t.rows_live) return;
+    if (t.epi_op == 2) {
+        // pre-activation values of this thread's row (one 128-byte line; columns past N are never stored)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 h = (t.aux != nullptr && col0 + 4 * j + 3 < t.N)
+                                 ? __ldg(reinterpret_cast<const float4*>(t.aux + col0 + 4 * j))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * j + 0] = __float_as_uint(epi_gelu_bwd(h.x, __uint_as_float(v[4 * j + 0])));
+            v[4 * j + 1] = __float_as_uint(epi_gelu_bwd(h.y, __uint_as_float(v[4 * j + 1])));
+            v[4 * j + 2] = __float_as_uint(epi_gelu_bwd(h.z, __uint_as_float(v[4 * j + 2])));
+            v[4 * j + 3] = __float_as_uint(epi_gelu_bwd(h.w, __uint_as_float(v[4 * j + 3])));
+        }
+    }
+    epi_store(t.map_c, v, buf, col0, t.row0, t.bc1, t.bc0, t.reduce_out, lane);
+    if (t.epi_op == 1) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(epi_gelu(__uint_as_float(v[k])));
+        epi_store(t.map_aux, v, buf, col0, t.row0, t.bc1, t.bc0, 0, lane);
+    }
+}
+
+// This warp takes chunks half, half + 2, ... of the tile (its partner on the same TMEM lane quarter takes the
+// others; eight epilogue warps keep enough TMEM loads / stores in flight without software pipelining).
+// `bfirst` = bias_slice of its first chunk, loaded by the caller BEFORE it waited for the accumulator.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, uint32_t taddr0, uint8_t* buf0, int& flip,
+__device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, uint32_t taddr0, uint8_t* buf, int half,
                                               int lane) {
     constexpr int NC = BN / 32;
-    static_assert(NC % 2 == 0, "chunks are processed in pairs");
-    uint32_t va[32], vb[32];
-    tmem_ld32(va, taddr0);
     float bnext = bfirst;
 #pragma unroll 1
-    for (int c = 0; c < NC; c += 2) {
+    for (int c = half; c < NC; c += 2) {
         const int col0 = t.n0 + c * 32;
         if (col0 >= t.N) break;
-        const bool has_b = col0 + 32 < t.N;                   // chunk c + 1 exists
+        uint32_t v[32];
+        tmem_ld32(v, taddr0 + (uint32_t)(c * 32));
+        const float bcur = bnext;
+        bnext = (c + 2 < NC) ? bias_slice(t.bias, col0 + 64 + lane, t.N) : 0.f;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (has_b) tmem_ld32(vb, taddr0 + (uint32_t)((c + 1) * 32));
-        float bcur = bnext;
-        bnext = bias_slice(t.bias, col0 + 32 + lane, t.N);
-        if (t.rows_live) {
-            epi_emit(t, va, bcur, col0, buf0 + flip * EPI_BUF_BYTES, lane);
-            flip ^= 1;
-        }
-        if (!has_b) break;
-        const bool has_a = c + 2 < NC && col0 + 64 < t.N;     // chunk c + 2 exists
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (has_a) tmem_ld32(va, taddr0 + (uint32_t)((c + 2) * 32));
-        bcur = bnext;
-        bnext = bias_slice(t.bias, col0 + 64 + lane, t.N);
-        if (t.rows_live) {
-            epi_emit(t, vb, bcur, col0 + 32, buf0 + flip * EPI_BUF_BYTES, lane);
-            flip ^= 1;
-        }
+        epi_emit(t, v, bcur, col0, buf, lane);
     }
 }
 
@@ -284,7 +316,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, ui
 // every CTA still stages the whole B tile), so only CL = 1 is instantiated; CTA pairs use the
 // cta_group::2 kernel below, which really halves the B bytes per SM.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     LG_PDL_TRIGGER();
     constexpr int B_STAGE_BYTES = BN * 128;
@@ -295,7 +327,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* stage_base = smem;
     uint8_t* epi_base = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = (uint64_t*)(epi_base + EPI_WARPS * 2 * EPI_BUF_BYTES);
+    uint64_t* bars = (uint64_t*)(epi_base + EPI_WARPS * EPI_BUF_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
@@ -481,10 +513,10 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
         // ===================================== epilogue ==========================================
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
         const int ew = warp - 2;                // staging slot
-        uint8_t* buf0 = epi_base + ew * 2 * EPI_BUF_BYTES;
+        const int half = ew >> 2;               // which of the two warps on this lane quarter
+        uint8_t* buf0 = epi_base + ew * EPI_BUF_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
-        int flip = 0;
         for (int w = cluster_id; w < work_items; w += n_clusters) {
             const int grp = w / items_per_group, wg = w - grp * items_per_group;
             const CUtensorMap* map_c = &maps.c[grp];
@@ -495,18 +527,21 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
             EpiTile t;
             t.map_c = map_c;
+            t.map_aux = &maps.aux;
+            t.epi_op = p.epi_op;
             t.bias = split == 0 ? bias : nullptr;
             t.row0 = m0 + 32 * q;
+            t.aux = (p.epi_op == 2 && t.row0 + lane < p.M) ? p.aux + (long long)(t.row0 + lane) * p.aux_ld : nullptr;
             t.n0 = n0;
             t.N = p.N;
             t.bc1 = bc1;
             t.bc0 = bc0;
             t.reduce_out = p.reduce_out;
             t.rows_live = t.row0 < p.M;
-            const float bfirst = bias_slice(t.bias, n0 + lane, p.N);
+            const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, flip, lane);
+            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, half, lane);
             // this warp is done reading the accumulator stage
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty[acc]);
@@ -534,15 +569,17 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
 // 6 stages instead of 4 at BN = 256 -- what the fp32-operand (tf32) GEMM needs to cover L2 latency.
 //   both CTAs : warp 0 = TMA producer (completion credited to the leader's `full` barrier)
 //               warp 1 = collective TMEM allocation; in the leader also the single MMA-issuing thread
-//               warps 2..5 = epilogue on the CTA's own 128 accumulator rows
+//               warps 2..9 = epilogue on the CTA's own 128 accumulator rows
 //   leader    : waits `full`, issues m256 nBN k8 MMAs, tcgen05.commit(multicast) -> `empty` of both CTAs,
-//               and `tfull` of both CTAs when a tile is complete; waits `tempty` (8 warp arrivals: 4 local,
+//               and `tfull` of both CTAs when a tile is complete; waits `tempty` (16 warp arrivals: 8 local,
 //               4 remote) before overwriting an accumulator stage.
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_c, TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     LG_PDL_TRIGGER();
+    const CUtensorMap& map_a = maps.a[0];
+    const CUtensorMap& map_b = maps.b[0];
+    const CUtensorMap& map_c = maps.c[0];
     constexpr int HB = BN / 2;                          // B rows staged per CTA
     constexpr int B_STAGE_BYTES = HB * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -551,7 +588,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* stage_base = smem;
     uint8_t* epi_base = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = (uint64_t*)(epi_base + EPI_WARPS * 2 * EPI_BUF_BYTES);
+    uint64_t* bars = (uint64_t*)(epi_base + EPI_WARPS * EPI_BUF_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
@@ -702,10 +739,10 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ===================================== epilogue (both CTAs, own 128 rows) ==================
         const int q = warp & 3;
         const int ew = warp - 2;
-        uint8_t* buf0 = epi_base + ew * 2 * EPI_BUF_BYTES;
+        const int half = ew >> 2;
+        uint8_t* buf0 = epi_base + ew * EPI_BUF_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
-        int flip = 0;
         for (int w = cluster_id; w < work_items; w += n_clusters) {
             const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
@@ -713,18 +750,21 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM, n0 = (tile / p.tiles_m) * BN;
             EpiTile t;
             t.map_c = &map_c;
+            t.map_aux = &maps.aux;
+            t.epi_op = p.epi_op;
             t.bias = split == 0 ? p.bias[0] : nullptr;
             t.row0 = m0 + 32 * q;
+            t.aux = (p.epi_op == 2 && t.row0 + lane < p.M) ? p.aux + (long long)(t.row0 + lane) * p.aux_ld : nullptr;
             t.n0 = n0;
             t.N = p.N;
             t.bc1 = bc1;
             t.bc0 = bc0;
             t.reduce_out = p.reduce_out;
             t.rows_live = t.row0 < p.M;
-            const float bfirst = bias_slice(t.bias, n0 + lane, p.N);
+            const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, flip, lane);
+            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, half, lane);
             // one arrival per warp on the LEADER's barrier: the accumulator stage of this CTA is drained
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -813,7 +853,7 @@ constexpr int stages_for() { return BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 
 
 template <int BN>
 constexpr size_t smem_for() {
-    return (size_t)stages_for<BN>() * (A_STAGE_BYTES + BN * 128) + EPI_WARPS * 2 * EPI_BUF_BYTES +
+    return (size_t)stages_for<BN>() * (A_STAGE_BYTES + BN * 128) + EPI_WARPS * EPI_BUF_BYTES +
            (2 * stages_for<BN>() + 4) * 8 + 16 + 1024;
 }
 
@@ -829,12 +869,12 @@ constexpr int stages2_for() {
 }
 template <int BN>
 constexpr size_t smem2_for() {
-    return (size_t)stages2_for<BN>() * (A_STAGE_BYTES + BN * 64) + EPI_WARPS * 2 * EPI_BUF_BYTES +
+    return (size_t)stages2_for<BN>() * (A_STAGE_BYTES + BN * 64) + EPI_WARPS * EPI_BUF_BYTES +
            (2 * stages2_for<BN>() + 4) * 8 + 16 + 1024;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, int grid) {
+int launch_2cta(const TcMaps& maps, const TcParams& p, int grid) {
     constexpr int ST = stages2_for<BN>();
     constexpr size_t smem = smem2_for<BN>();
     auto kern = gemm_tf32_2cta_kernel<BN, A_MN, B_MN, ST>;
@@ -845,7 +885,7 @@ int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream();
     cudaLaunchAttribute attr[2];
@@ -857,18 +897,18 @@ int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    LG_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
+    LG_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
     LG_CHECK_LAUNCH();
     return 0;
 }
 
 template <int BN>
-int launch_2cta_bn(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+int launch_2cta_bn(bool a_mn, bool b_mn, const TcMaps& maps,
                    const TcParams& p, int grid) {
-    if (!a_mn && !b_mn) return launch_2cta<BN, false, false>(ma, mb, mc, p, grid);
-    if (!a_mn && b_mn) return launch_2cta<BN, false, true>(ma, mb, mc, p, grid);
-    if (a_mn && !b_mn) return launch_2cta<BN, true, false>(ma, mb, mc, p, grid);
-    return launch_2cta<BN, true, true>(ma, mb, mc, p, grid);
+    if (!a_mn && !b_mn) return launch_2cta<BN, false, false>(maps, p, grid);
+    if (!a_mn && b_mn) return launch_2cta<BN, false, true>(maps, p, grid);
+    if (a_mn && !b_mn) return launch_2cta<BN, true, false>(maps, p, grid);
+    return launch_2cta<BN, true, true>(maps, p, grid);
 }
 
 template <int BN, bool A_MN, bool B_MN, int CL>
@@ -883,7 +923,7 @@ int launch_cfg(const TcMaps& maps, const TcParams& p, int grid) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream();
     cudaLaunchAttribute attr[2];
@@ -985,8 +1025,13 @@ int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, c
 // 3 x 128 tiles instead of three one-wave launches).  Several groups may name the same C: with
 // accumulate they all reduce-add into it (dX = sum_g dY_g W_g).
 int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
-                    const void* const* bias, int accumulate) {
+                    const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld) {
     if (load_encode()) return 1;
+    if (epi_op) {
+        LG_REQUIRE(groups == 1 && d->batch0 * d->batch1 == 1 && !accumulate, "gemm_tc: epilogue ops need one plain GEMM");
+        LG_REQUIRE(aux && (((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0 && aux_ld >= d->N && d->N % 4 == 0,
+                   "gemm_tc: epilogue operand must be 16-byte aligned with a row pitch that is a multiple of 4");
+    }
     LG_REQUIRE(groups >= 1 && groups <= LG_MAX_GROUPS, "gemm_tc: 1..%d groups per launch", LG_MAX_GROUPS);
     const int64_t M = d->M, N = d->N, K = d->K;
     const bool a_mn = !k_major(d->sa_m, d->sa_k, M);
@@ -1004,7 +1049,7 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int n_problems = same_c ? 1 : groups;
     // split-K partials meet in C by reduce-add: C must be zeroed first (done below for one plain matrix) or
     // already hold the value being accumulated into
-    Plan pl = choose_plan(M, N, K, batches * n_problems, accumulate || batches * n_problems == 1);
+    Plan pl = choose_plan(M, N, K, batches * n_problems, !epi_op && (accumulate || batches * n_problems == 1));
     int rc;
     const BatchDims ba{d->batch1, d->sa_b1, d->batch0, d->sa_b0}, bb{d->batch1, d->sb_b1, d->batch0, d->sb_b0},
         bc{d->batch1, d->sc_b1, d->batch0, d->sc_b0};
@@ -1046,6 +1091,16 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     p.batch1 = (int)d->batch1;
     p.batches = (int)batches;
     p.groups = n_problems;
+    p.epi_op = epi_op;
+    p.aux = (const float*)aux;
+    p.aux_ld = aux_ld;
+    if (epi_op == 1) {
+        // second result: same geometry as C, its own row pitch
+        rc = make_map(&maps.aux, aux, N, M, aux_ld, BatchDims{1, 0, 1, 0}, 32, 32);
+        if (rc) return rc;
+    } else {
+        maps.aux = maps.c[0];
+    }
     p.kcat = same_c ? groups : 1;
     p.reduce_out = (pl.splits > 1 || accumulate) ? 1 : 0;
     if (pl.splits > 1 && !accumulate) {
@@ -1063,10 +1118,10 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int grid = cl * (items < max_clusters ? items : max_clusters);
     if (pair_mma) {
         switch (pl.bn) {
-            case 256: return launch_2cta_bn<256>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
-            case 192: return launch_2cta_bn<192>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
-            case 128: return launch_2cta_bn<128>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
-            default: return launch_2cta_bn<64>(a_mn, b_mn, maps.a[0], maps.b[0], maps.c[0], p, grid);
+            case 256: return launch_2cta_bn<256>(a_mn, b_mn, maps, p, grid);
+            case 192: return launch_2cta_bn<192>(a_mn, b_mn, maps, p, grid);
+            case 128: return launch_2cta_bn<128>(a_mn, b_mn, maps, p, grid);
+            default: return launch_2cta_bn<64>(a_mn, b_mn, maps, p, grid);
         }
     }
     switch (pl.bn) {
@@ -1083,7 +1138,16 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     const void* bv[1] = {b};
     void* cv[1] = {c};
     const void* biasv[1] = {bias};
-    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate);
+    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate, 0, nullptr, 0);
+}
+
+int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
+                     int64_t aux_ld) {
+    const void* av[1] = {a};
+    const void* bv[1] = {b};
+    void* cv[1] = {c};
+    const void* biasv[1] = {bias};
+    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, 0, epi_op, aux, aux_ld);
 }
 
 }  // namespace lg

@@ -217,6 +217,22 @@ class FakeDevice(object):
                       1 if (accumulate or again) else 0)
             seen.append(c[g])
 
+    def gemm_epilogue(self, mode, dt, dref, a, b, c, bias, epi, aux, aux_ld):
+        d = dref._obj
+        self.gemm(mode, dt, dref, a, b, c, bias, 0)
+        Cm = _arr(c, dt, [d.M, d.N], [d.sc_m, 1])
+        X = _arr(aux, dt, [d.M, d.N], [aux_ld, 1])
+        f = NP[dt]
+        c1, c2 = f(0.7978845608), f(0.044715)
+        if epi == 1:
+            inner = (Cm * c1) * (f(1.0) + (c2 * Cm) * Cm)
+            X[...] = (f(0.5) * Cm) * (f(1.0) + np.tanh(inner))
+        else:
+            x2 = X * X
+            t = np.tanh((X * c1) * (f(1.0) + c2 * x2))
+            du = c1 * (f(1.0) + f(3.0) * c2 * x2)
+            Cm[...] = (f(0.5) * (f(1.0) + t) + (f(0.5) * X) * (f(1.0) - t * t) * du) * Cm
+
     def side_begin(self): pass
 
     def side_end(self): pass

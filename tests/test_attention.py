@@ -159,3 +159,45 @@ def test_bert_layer_uses_fused_node_and_matches_unfused(device):
     for k, p in att.named_parameters():
         np.testing.assert_allclose(g1[k], p.grad.numpy(), rtol=1e-4, atol=1e-5, err_msg=k)
     np.testing.assert_allclose(X1.grad.numpy(), X2.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def _oracle_mlp(T, x, w1, b1, w2, b2):
+    # BertLayer's feed-forward with the reference's operators (examples/bert.py:12,150-153)
+    h = x @ w1.transpose(1, 0) + b1
+    a = 0.5 * h * (1.0 + (h * 0.7978845608 * (1.0 + 0.044715 * h * h)).tanh())
+    return a @ w2.transpose(1, 0) + b2
+
+
+@pytest.mark.parametrize("cfg", [(2, 16, 64, 256), (4, 128, 256, 1024), (3, 20, 96, 200)])
+@pytest.mark.parametrize("preset_grads", [False, True])
+def test_mlp_gelu_matches_oracle(mode, cfg, preset_grads):
+    b, s, H, F = cfg
+    rs = np.random.RandomState(6)
+    x = rs.uniform(-1, 1, (b, s, H)).astype(np.float32)
+    w1 = (rs.uniform(-1, 1, (F, H)) * 2 / math.sqrt(H)).astype(np.float32)
+    w2 = (rs.uniform(-1, 1, (H, F)) * 2 / math.sqrt(F)).astype(np.float32)
+    b1 = rs.uniform(-0.5, 0.5, (F,)).astype(np.float32)
+    b2 = rs.uniform(-0.5, 0.5, (H,)).astype(np.float32)
+    up = rs.uniform(-1, 1, (b, s, H)).astype(np.float32)
+
+    def run(T):
+        X = T.from_numpy(x)
+        P = [T.from_numpy(v) for v in (w1, b1, w2, b2)]
+        if T is CudaTensor:
+            if preset_grads:
+                for p in P:
+                    p.zero_grad()
+                X.zero_grad()               # dX is then reduce-added into the existing gradient
+            out = X.mlp_gelu(*P)
+        else:
+            out = _oracle_mlp(T, X, *P)
+        (out * T.from_numpy(up, requires_grad=False)).sum().backward()
+        return out.numpy(), [X.grad.numpy()] + [p.grad.numpy() for p in P]
+
+    want_out, want_g = run(CpuTensor)
+    got_out, got_g = run(CudaTensor)
+    tol = _tol(mode) * (10 if mode == 'fp32' else 1)
+    assert rel(got_out, want_out) <= tol
+    for n, g, w in zip(['x', 'w1', 'b1', 'w2', 'b2'], got_g, want_g):
+        assert g.shape == w.shape, n
+        assert rel(g, w) <= tol, n
