@@ -26,8 +26,19 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+# stdout carries exactly one JSON line.  Libraries write there behind python's back (NCCL prints its version
+# banner to fd 1 whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and the JSON
+# line goes to a private duplicate of the original stdout.
 os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + '\n')
+    _REAL_STDOUT.flush()
+
 
 import numpy as np  # noqa: E402
 
@@ -182,7 +193,7 @@ def main():
                 'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 'e2e': {'value': res['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ------------------------------------------------------------------------------------ our arm
@@ -356,7 +367,7 @@ def main():
     if args.gpus == 1 and not args.no_cpu_baseline:
         res = cpu_reference_leg(2, 1, args.cpu_sample_batch or 4, budget_s=90.0)
         line['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
-    print(json.dumps(line), flush=True)
+    emit(line)
     finish(comm)
 
 
