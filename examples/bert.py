@@ -101,7 +101,7 @@ class BertAttention(nn.Module):
     def forward(self, hidden_in, attention_mask=None, need_probs=True):
         hidden, attentions = self.self(hidden_in, attention_mask=attention_mask, need_probs=need_probs)
         hidden = self.output.dense(hidden)
-        return self.output.LayerNorm(hidden + hidden_in), attentions
+        return self.output.LayerNorm(hidden, residual=hidden_in), attentions
 
 
 class BertLayer(nn.Module):
@@ -123,8 +123,7 @@ class BertLayer(nn.Module):
 
     def forward(self, hidden, attention_mask=None, need_probs=True):
         hidden, attentions = self.attention(hidden, attention_mask, need_probs=need_probs)
-        hidden = hidden + self.mlp(hidden)
-        return self.output.LayerNorm(hidden), attentions
+        return self.output.LayerNorm(self.mlp(hidden), residual=hidden), attentions
 
 
 class BertModel(nn.Module):

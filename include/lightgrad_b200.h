@@ -238,6 +238,10 @@ int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, int64_t l
 int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y,
                      void* mean, void* rstd, int64_t rows, int64_t cols, double eps);
 /* accumulate != 0: dgamma / dbeta are added to the buffers (existing .grad) instead of overwriting them */
+/* y = layernorm(a + b): the residual add of BertAttention / BertLayer (examples/bert.py:113,158 of the reference)
+ * folded into the normalisation; the sum is written to sum_out (it is the x that lg_layernorm_bwd needs). */
+int lg_add_layernorm_fwd(int dtype, const void* a, const void* b, void* sum_out, const void* gamma, const void* beta,
+                         void* y, void* mean, void* rstd, int64_t rows, int64_t cols, double eps);
 int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd,
                      const void* g, void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols,
                      int accumulate);

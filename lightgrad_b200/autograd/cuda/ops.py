@@ -29,6 +29,9 @@ _matmul_mode = _MODES[os.environ.get('LG_MATMUL_MODE', 'fp32').lower()]
 
 Gradients.after_backward.append(rt.side_join)
 
+# A/B switch for measurements: LG_DISABLE=add_ln,mlp,attn,dx_acc turns the named fusions off
+_DISABLED = set(filter(None, os.environ.get('LG_DISABLE', '').split(',')))
+
 
 def set_matmul_mode(name):
     """Select how float32 matmuls are computed: 'fp32' | 'tf32' | 'bf16'.  Returns the previous mode name."""
@@ -988,6 +991,8 @@ class mlp_gelu(Function):
 
 def _direct_grad(p, code):
     """The parameter's existing gradient buffer when a kernel may add into it in place, else None."""
+    if 'dx_acc' in _DISABLED and p.ctx is not None:
+        return None
     g = p.grad if isinstance(p, CudaTensor) and p.requires_grad else None
     if g is not None and g._contig and g._code == code == rt.F32 and g._shape == p._shape:
         return g
@@ -1352,20 +1357,55 @@ class layernorm(Function):
 
     def backward(ctx, out_grad):
         x, w, mean, rstd = ctx.get_saved_tensors()
-        g = out_grad.contiguous()
-        cols = x._shape[-1]
-        rows = x._numel // cols
-        dx = CudaTensor._new(x._shape, x._dtype)
-        weight, bias = ctx._parents[1], ctx._parents[2]
-        wg, bg = weight.grad, bias.grad
-        if weight.requires_grad and bias.requires_grad and wg is not None and bg is not None and wg._contig \
-                and bg._contig and wg._code == bg._code == x._code and wg._shape == bg._shape == (cols,):
-            # d(gamma), d(beta) are added straight into the existing gradients
-            rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, wg.ptr, bg.ptr, rows, cols, 1)
-            return dx, Function.ACCUMULATED, Function.ACCUMULATED
-        dw, db = CudaTensor._new((cols,), x._dtype), CudaTensor._new((cols,), x._dtype)
-        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols, 0)
-        return dx, dw, db
+        return _ln_backward(x, w, mean, rstd, ctx._parents[1], ctx._parents[2], out_grad)
+
+
+def _ln_backward(x, w, mean, rstd, weight, bias, out_grad):
+    """(dx, d(gamma), d(beta)) of a layer norm over the last axis; the parameter gradients are added straight
+    into existing gradient buffers when there are any."""
+    g = out_grad.contiguous()
+    cols = x._shape[-1]
+    rows = x._numel // cols
+    dx = CudaTensor._new(x._shape, x._dtype)
+    wg, bg = weight.grad, bias.grad
+    if weight.requires_grad and bias.requires_grad and wg is not None and bg is not None and wg._contig \
+            and bg._contig and wg._code == bg._code == x._code and wg._shape == bg._shape == (cols,):
+        # d(gamma), d(beta) are added straight into the existing gradients
+        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, wg.ptr, bg.ptr, rows, cols, 1)
+        return dx, Function.ACCUMULATED, Function.ACCUMULATED
+    dw, db = CudaTensor._new((cols,), x._dtype), CudaTensor._new((cols,), x._dtype)
+    rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols, 0)
+    return dx, dw, db
+
+
+@CudaTensor.register_op()
+class add_layernorm(Function):
+    """layernorm(a + b) over the last axis: the residual connections of BertAttention / BertLayer
+    (examples/bert.py:113,158 of the reference: LayerNorm(hidden + hidden_in)) with the add folded into the
+    normalisation kernel (one pass writes the sum, which backward needs, and the normalised result)."""
+    def forward(ctx, a, b, weight, bias, eps=1e-5):
+        a, b = _float_like(a), _float_like(b)
+        if a._shape != b._shape or a._code != b._code:
+            raise ValueError("add_layernorm: operands must share one shape and dtype (%s %s / %s %s)"
+                             % (a._shape, a._dtype, b._shape, b._dtype))
+        a, b = a.contiguous(), b.contiguous()
+        cols = a._shape[-1]
+        assert weight._shape == (cols,) and bias._shape == (cols,)
+        rows = a._numel // cols
+        s = CudaTensor._new(a._shape, a._dtype)
+        y = CudaTensor._new(a._shape, a._dtype)
+        mean, rstd = CudaTensor._new((rows,), a._dtype), CudaTensor._new((rows,), a._dtype)
+        w, bb = weight.contiguous(), bias.contiguous()
+        rt.api.add_layernorm_fwd(a._code, a.ptr, b.ptr, s.ptr, w.ptr, bb.ptr, y.ptr, mean.ptr, rstd.ptr, rows, cols,
+                                 float(eps))
+        s._temp = False
+        ctx.save_for_backward(s, w, mean, rstd)
+        return y
+
+    def backward(ctx, out_grad):
+        s, w, mean, rstd = ctx.get_saved_tensors()
+        dx, dw, db = _ln_backward(s, w, mean, rstd, ctx._parents[2], ctx._parents[3], out_grad)
+        return dx, dx, dw, db       # the sum's gradient goes to both addends
 
 
 def cross_entropy_forward(logits, labels):
@@ -1387,6 +1427,9 @@ def cross_entropy_forward(logits, labels):
 
 
 def cross_entropy_backward(saved, out_grad):
+    # (forming this gradient inside the forward kernel, while each row is cache resident, was measured slower
+    #  than the two separate sweeps: 8.63 vs 8.55 ms per BERT step -- the forward grid has to shrink to keep
+    #  the rows in flight inside L2)
     x, lab, lse = saved
     rows, cols = x._shape
     g = out_grad.contiguous()
@@ -1460,3 +1503,9 @@ class conv(Function):
             _ewn(EW['ADD'], (dst, _basic_view(src, list(sel))), out=dst)
         x_grad._temp = True
         return x_grad, w_grad
+
+
+# measurement switch (see _DISABLED above): drop fused nodes so that models fall back to the composed path
+for _n, _attr in (('add_ln', 'add_layernorm'), ('mlp', 'mlp_gelu'), ('attn', 'self_attention')):
+    if _n in _DISABLED and hasattr(CudaTensor, _attr):
+        delattr(CudaTensor, _attr)

@@ -92,6 +92,7 @@ _SIGNATURES = {
     'lg_cross_entropy_fwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int64],
     'lg_cross_entropy_bwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64],
     'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
+    'lg_add_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
     'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp,

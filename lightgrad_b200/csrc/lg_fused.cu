@@ -273,10 +273,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
 // ---- float32 fast path: one warp per row, the row lives in registers (NV float4 per lane), 128-bit accesses.
 // Valid for cols % 4 == 0 and cols <= NV*128 (BERT: 768 -> NV = 6).
 template <int NV>
-__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                         float* __restrict__ sum_out, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ y,
                                                          float* __restrict__ mean, float* __restrict__ rstd,
                                                          int64_t rows, int cols, float eps) {
+    // res != nullptr: the normalised input is x + res (residual connection), written to sum_out for backward
     LG_PDL_TRIGGER();
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -299,10 +301,25 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int c = lane + 32 * j;
-            if (c < nchunks) {
-                v[j] = p[c];
-                s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            if (c < nchunks) v[j] = p[c];
+        }
+        if (res != nullptr) {
+            const float4* pr = reinterpret_cast<const float4*>(res + row * cols);
+            float4* ps = reinterpret_cast<float4*>(sum_out + row * cols);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int c = lane + 32 * j;
+                if (c < nchunks) {
+                    const float4 r = pr[c];
+                    v[j].x += r.x; v[j].y += r.y; v[j].z += r.z; v[j].w += r.w;
+                    ps[c] = v[j];
+                }
             }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            if (c < nchunks) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
         }
         const float mu = warp_sum(s) * inv;
         float q = 0.f;
@@ -652,23 +669,46 @@ int lg_cross_entropy_bwd(int dtype, int idx_dtype, const void* logits, int64_t l
     return set_error("lg_cross_entropy_bwd: unsupported dtype %d", dtype);
 }
 
+static int layernorm_fwd_impl(int dtype, const void* x, const void* res, void* sum_out, const void* gamma,
+                              const void* beta, void* y, void* mean, void* rstd, int64_t rows, int64_t cols,
+                              double eps);
+
 int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y, void* mean, void* rstd,
                      int64_t rows, int64_t cols, double eps) {
+    return layernorm_fwd_impl(dtype, x, nullptr, nullptr, gamma, beta, y, mean, rstd, rows, cols, eps);
+}
+
+int lg_add_layernorm_fwd(int dtype, const void* a, const void* b, void* sum_out, const void* gamma, const void* beta,
+                         void* y, void* mean, void* rstd, int64_t rows, int64_t cols, double eps) {
+    LG_REQUIRE(a && b && sum_out, "lg_add_layernorm_fwd: operands missing");
+    return layernorm_fwd_impl(dtype, a, b, sum_out, gamma, beta, y, mean, rstd, rows, cols, eps);
+}
+
+static int layernorm_fwd_impl(int dtype, const void* x, const void* res, void* sum_out, const void* gamma,
+                              const void* beta, void* y, void* mean, void* rstd, int64_t rows, int64_t cols,
+                              double eps) {
     LG_INIT();
     if (rows * cols == 0) return 0;
     int64_t blocks = (rows + 7) / 8, cap = (int64_t)sm_count() * 16;
     int grid = (int)(blocks < cap ? blocks : cap);
     const int nv = ln_nv(cols);
-    if (dtype == LG_F32 && nv && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta)) {
+    if (dtype == LG_F32 && nv && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
+        aligned16(res) && aligned16(sum_out)) {
         int64_t cap2 = (int64_t)sm_count() * 4;
         int g2 = (int)(blocks < cap2 ? blocks : cap2);
 #define LN_F(NV_)                                                                                           \
-    ln_fwd_vec_kernel<NV_><<<g2, 256, 0, stream()>>>((const float*)x, (const float*)gamma, (const float*)beta, \
-                                                     (float*)y, (float*)mean, (float*)rstd, rows, (int)cols, (float)eps)
+    ln_fwd_vec_kernel<NV_><<<g2, 256, 0, stream()>>>((const float*)x, (const float*)res, (float*)sum_out,           \
+                                                     (const float*)gamma, (const float*)beta, (float*)y,            \
+                                                     (float*)mean, (float*)rstd, rows, (int)cols, (float)eps)
         if (nv == 2) LN_F(2); else if (nv == 4) LN_F(4); else if (nv == 6) LN_F(6); else LN_F(8);
 #undef LN_F
         LG_CHECK_LAUNCH();
         return 0;
+    }
+    if (res != nullptr) {
+        // generic shapes: form the sum with the elementwise engine, then normalise it
+        if (lg_ew_flat(LG_EW_ADD, dtype, x, res, nullptr, sum_out, rows * cols, 0.0)) return 1;
+        x = sum_out;
     }
     if (dtype == LG_F32)
         ln_fwd_kernel<float><<<grid, 256, 0, stream()>>>((const float*)x, (const float*)gamma, (const float*)beta,

@@ -154,9 +154,14 @@ class LayerNorm(Module):
         self.weight = T.ones(self.shape)
         self.bias = T.zeros(self.shape)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """``residual``: normalise ``x + residual`` (backends with a fused add + layer norm do it in one pass)."""
         k = len(self.shape)
         assert x.shape[-k:] == self.shape, "Shape mismatch in layer norm! (%s <-> %s)" % (x.shape, self.shape)
+        if residual is not None:
+            if k == 1 and hasattr(x, 'add_layernorm') and x.shape == residual.shape and x.dtype == residual.dtype:
+                return x.add_layernorm(residual, self.weight, self.bias, eps=self.eps)
+            x = x + residual
         if k == 1 and hasattr(x, 'layernorm'):
             return x.layernorm(self.weight, self.bias, eps=self.eps)
         axes = tuple(range(len(x.shape) - k, len(x.shape)))

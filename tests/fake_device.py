@@ -319,6 +319,10 @@ class FakeDevice(object):
         _arr(mean, dt, [rows])[...] = mu[:, 0]
         _arr(rstd, dt, [rows])[...] = rs[:, 0]
 
+    def add_layernorm_fwd(self, dt, a, b, s, w, bias, y, mean, rstd, rows, cols, eps):
+        _arr(s, dt, [rows, cols])[...] = _arr(a, dt, [rows, cols]) + _arr(b, dt, [rows, cols])
+        self.layernorm_fwd(dt, s, w, bias, y, mean, rstd, rows, cols, eps)
+
     def layernorm_bwd(self, dt, x, w, mean, rstd, g, dx, dw, db, rows, cols, accumulate):
         self.launches += 1
         X, G, W = _arr(x, dt, [rows, cols]), _arr(g, dt, [rows, cols]), _arr(w, dt, [cols])

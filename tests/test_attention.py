@@ -201,3 +201,37 @@ def test_mlp_gelu_matches_oracle(mode, cfg, preset_grads):
     for n, g, w in zip(['x', 'w1', 'b1', 'w2', 'b2'], got_g, want_g):
         assert g.shape == w.shape, n
         assert rel(g, w) <= tol, n
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 64), (2, 128, 768), (3, 7, 100)])
+@pytest.mark.parametrize("preset_grads", [False, True])
+def test_add_layernorm_matches_oracle(device, shape, preset_grads):
+    # LayerNorm(hidden + residual) of BertAttention / BertLayer (examples/bert.py:113,158) with the reference's
+    # own composition on the CPU tensor as the oracle (nn.py:109-124)
+    rs = np.random.RandomState(8)
+    a = rs.uniform(-1, 1, shape).astype(np.float32)
+    b = rs.uniform(-1, 1, shape).astype(np.float32)
+    w = rs.uniform(0.5, 1.5, shape[-1:]).astype(np.float32)
+    bias = rs.uniform(-0.5, 0.5, shape[-1:]).astype(np.float32)
+    up = rs.uniform(-1, 1, shape).astype(np.float32)
+
+    def run(T):
+        A, B, W, Bi = (T.from_numpy(v) for v in (a, b, w, bias))
+        if T is CudaTensor:
+            if preset_grads:
+                W.zero_grad()
+                Bi.zero_grad()
+            out = A.add_layernorm(B, W, Bi, eps=1e-5)
+        else:
+            x = A + B
+            D = x - x.mean(axis=-1, keepdims=True)
+            V = (D * D).mean(axis=-1, keepdims=True)
+            out = D / (V + 1e-5).pow(1 / 2) * W + Bi
+        (out * T.from_numpy(up, requires_grad=False)).sum().backward()
+        return out.numpy(), [t.grad.numpy() for t in (A, B, W, Bi)]
+
+    want_out, want_g = run(CpuTensor)
+    got_out, got_g = run(CudaTensor)
+    np.testing.assert_allclose(got_out, want_out, rtol=3e-5, atol=3e-6)
+    for n, g, wv in zip('abwB', got_g, want_g):
+        np.testing.assert_allclose(g, wv, rtol=2e-4, atol=2e-5 * max(1.0, float(np.abs(wv).max())), err_msg=n)
