@@ -328,6 +328,41 @@ def main():
                     'same captured step with the lg_gemm launches removed (%.3f ms), both timed with CUDA events on '
                     'the compute stream right after the timed region' % (k_c, step_ms_c, k_c, nogemm_ms))
     rt.gemm_profile(False)
+
+    # ---- multi-GPU only: the gradient exchange on its own and what of it stays exposed
+    comm_info = None
+    if world > 1 and dp is not None and getattr(dp, '_nccl', False):
+        a = dp.arena
+        nbytes = a.total * 4
+        for _ in range(2):
+            rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
+        barrier()
+        c0 = rt.Event().record()
+        for _ in range(5):
+            rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
+        c1 = rt.Event().record()
+        c1.synchronize()
+        ar_ms = comm.max_float(c0.elapsed_ms(c1)) / 5
+        # the same local step without any exchange (captured separately): step time minus this = exposed communication
+        local_step = make_step(model, opt, None, light)
+        if args.eager:
+            run_local = lambda: local_step(ids_d, lab_d)  # noqa: E731
+        else:
+            sg_local = StepGraph(lambda: local_step(ids_d, lab_d), warmup=0)
+            run_local = sg_local.replay
+        run_local()
+        barrier()
+        l0 = rt.Event().record()
+        for _ in range(k_c if not args.eager else 3):
+            run_local()
+        l1 = rt.Event().record()
+        l1.synchronize()
+        local_ms = comm.max_float(l0.elapsed_ms(l1)) / (k_c if not args.eager else 3)
+        comm_info = {'allreduce_bytes': int(nbytes), 'allreduce_ms_alone': round(ar_ms, 3),
+                     'allreduce_busbw_gbps': round(2.0 * (world - 1) / world * nbytes / (ar_ms / 1e3) / 1e9, 1),
+                     'step_ms_without_exchange': round(local_ms, 3),
+                     'exposed_comm_ms': round(max(ms_a - local_ms, 0.0), 3),
+                     'note': 'bucketed all-reduce (64 MB buckets) overlapped with backward on the communication stream'}
     if rank != 0:
         finish(comm)
 
@@ -364,6 +399,9 @@ def main():
                      'how': roof_how},
         'mfu_vs_measured_bf16': round(GEMM_FLOPS_PER_SAMPLE * value / 1e12 / peaks['bf16_tflops'], 4),
     }
+    if comm_info is not None:
+        line['comm'] = comm_info
+    line['config']['per_gpu_batch'] = int(local)
     if args.gpus == 1 and not args.no_cpu_baseline:
         res = cpu_reference_leg(2, 1, args.cpu_sample_batch or 4, budget_s=90.0)
         line['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

@@ -197,6 +197,10 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
 typedef enum { LG_EPI_NONE = 0, LG_EPI_GELU_FWD = 1, LG_EPI_GELU_BWD = 2 } LgGemmEpilogue;
 int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias,
                      int epi_op, void* aux, int64_t aux_ld);
+/* Persistent tensor-core GEMM grids use at most n_sms SMs (0 = all).  The data-parallel wrapper lowers it while
+ * gradient all-reduces overlap backward, so the collective's CTAs do not push a one-CTA-per-SM grid into a
+ * second wave. */
+int lg_gemm_sm_limit(int n_sms);
 /* measurement hooks for the matmul share of a step (off by default):
  * lg_prof_gemm(1): CUDA events on the compute stream around every lg_gemm launch;
  * lg_prof_gemm(2): lg_gemm launches NOTHING and only counts -- timing a captured step with and without its

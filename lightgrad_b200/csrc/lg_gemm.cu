@@ -8,6 +8,7 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c);
 int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
                     const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld);
+int gemm_set_sm_limit(int n);
 int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
                      int64_t aux_ld);
 }  // namespace lg
@@ -165,6 +166,12 @@ int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, co
         g_probes.push_back(pr);
     }
     return rc;
+}
+
+int lg_gemm_sm_limit(int n_sms) {
+    LG_INIT();
+    LG_REQUIRE(n_sms >= 0, "lg_gemm_sm_limit: negative SM count");
+    return gemm_set_sm_limit(n_sms);
 }
 
 }  // extern "C"

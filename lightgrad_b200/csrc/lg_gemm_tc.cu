@@ -166,6 +166,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool a_mn, 
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// SMs the persistent GEMM grids may occupy (lg_gemm_sm_limit): a data-parallel step leaves a few SMs to the
+// collective's CTAs, so that a one-CTA-per-SM grid is never forced into a second wave by them
+static int g_gemm_sm_limit = 0;
+inline int gemm_sms() {
+    const int n = lg::sm_count();
+    return (g_gemm_sm_limit > 0 && g_gemm_sm_limit < n) ? g_gemm_sm_limit : n;
+}
+
 struct TcParams {
     int M, N, K;
     int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
@@ -956,7 +964,7 @@ struct Plan {
 };
 
 Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split) {
-    const int sms = sm_count();
+    const int sms = gemm_sms();
     const int kblocks = (int)((K + BK - 1) / BK);
     Plan best{};
     double best_score = -1.0;
@@ -1057,7 +1065,7 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     // (measured: +5..8 % on >= 2-wave problems such as 4096^3 or the 30522-wide decoder, but slower than
     //  independent CTAs on the one-wave BERT projections, which therefore keep cta_group::1)
     static const int force_pair = getenv("LG_GEMM_PAIR") ? atoi(getenv("LG_GEMM_PAIR")) : -1;
-    const bool big = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits >= 2 * (int64_t)sm_count();
+    const bool big = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits >= 2 * (int64_t)gemm_sms();
     const bool pair_mma = groups == 1 && batches == 1 && pl.tiles_m >= 2 && (force_pair < 0 ? big : force_pair == 1);
     const int cl = pair_mma ? 2 : 1;
     TcMaps maps;
@@ -1114,7 +1122,7 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int64_t items64 = (int64_t)p.tiles_m * pl.tiles_n * pl.splits * batches * n_problems;   // cluster work items
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
-    const int max_clusters = sm_count() / cl;
+    const int max_clusters = gemm_sms() / cl;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
     if (pair_mma) {
         switch (pl.bn) {
@@ -1148,6 +1156,11 @@ int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c,
     void* cv[1] = {c};
     const void* biasv[1] = {bias};
     return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, 0, epi_op, aux, aux_ld);
+}
+
+int gemm_set_sm_limit(int n) {
+    g_gemm_sm_limit = n;
+    return 0;
 }
 
 }  // namespace lg

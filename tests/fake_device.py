@@ -233,6 +233,8 @@ class FakeDevice(object):
             du = c1 * (f(1.0) + f(3.0) * c2 * x2)
             Cm[...] = (f(0.5) * (f(1.0) + t) + (f(0.5) * X) * (f(1.0) - t * t) * du) * Cm
 
+    def gemm_sm_limit(self, n): pass
+
     def side_begin(self): pass
 
     def side_end(self): pass
