@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lightgrad_b200 import CudaTensor                                  # noqa: E402
 from lightgrad_b200.autograd.cuda import ops, runtime as rt            # noqa: E402
 from lightgrad_b200.autograd.cuda.graph import StepGraph               # noqa: E402
-from lightgrad_b200.autograd.cuda.ops import _gemm, _gemm_grouped, _gemm_epilogue, _swap_last   # noqa: E402
+from lightgrad_b200.autograd.cuda.ops import _gemm, _gemm_grouped, _gemm_epilogue, _attention_gemm, _swap_last   # noqa: E402
 
 R, H, F, V = 4096, 768, 3072, 30522          # rows = batch 32 x seq 128
 
@@ -110,6 +110,12 @@ def cases():
             P = [rand(b, h, s, s) for _ in range(sets)]
             if kind == 'qk':
                 return (lambda i: _gemm(Q[i], _swap_last(K[i]), out=P[i])), 2.0 * b * h * s * s * d
+            if kind == 'qk_softmax':
+                return (lambda i: _attention_gemm(Q[i], _swap_last(K[i]), P[i], 3, 0.125)), 2.0 * b * h * s * s * d
+            if kind == 'dp_softmax_bwd':
+                D = [CudaTensor.empty((b, h, s, s)) for _ in range(sets)]
+                return (lambda i: _attention_gemm(Q[i], _swap_last(K[i]), D[i], 4, 0.125, aux=P[i])), \
+                    2.0 * b * h * s * s * d
             O = [CudaTensor.empty((b, h, s, d)) for _ in range(sets)]
             if kind == 'pv':
                 return (lambda i: _gemm(P[i], K[i], out=O[i])), 2.0 * b * h * s * s * d
@@ -211,7 +217,8 @@ def cases():
         ('ffn2 fwd 4096x768x3072', fwd(F, H)), ('ffn2 dX', dx(F, H)), ('ffn2 dW (acc)', dw(F, H)),
         ('ffn1 fwd + gelu epilogue (2 results)', epi(1)), ('ffn2 dX * gelu\' epilogue', epi(2)),
         ('qkv grouped fwd', qkv_fwd()), ('qkv k-concat dX', qkv_dx()), ('qkv grouped dW (acc)', qkv_dw()),
-        ('attn QK^T 384x128x128x64', att('qk')), ('attn PV', att('pv')), ('attn P^T dO', att('ptv')),
+        ('attn QK^T 384x128x128x64', att('qk')), ('attn QK^T + softmax epilogue', att('qk_softmax')),
+        ('attn dO V^T + softmax-bwd epilogue', att('dp_softmax_bwd')), ('attn PV', att('pv')), ('attn P^T dO', att('ptv')),
         ('decoder fwd 4096x30522x768', fwd(H, V)), ('decoder dX', dx(H, V)), ('decoder dW (acc)', dw(H, V)),
     ]
 

@@ -189,14 +189,21 @@ int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void*
  * C: with accumulate != 0 every group adds into it (dX = sum_g dY_g W_g). */
 int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const void* const* a, const void* const* b,
                     void* const* c, const void* const* bias, int accumulate);
-/* One plain (unbatched) product with an activation fused into its epilogue -- the two halves of
- * gelu(x W1^T + b1) in BertLayer (examples/bert.py:12,150-153 of the reference):
+/* A product with the operation that follows it fused into the GEMM epilogue.
+ * One plain (unbatched) product -- the two halves of gelu(x W1^T + b1) in BertLayer (examples/bert.py:12,150-153
+ * of the reference):
  *   LG_EPI_GELU_FWD: c = a b + bias (kept for backward) and aux = gelu(c), both written by the epilogue;
  *   LG_EPI_GELU_BWD: c = (a b) * gelu'(aux), aux = the pre-activation saved by the forward call.
+ * Batched, N <= 128, tensor-core mode only (check lg_gemm_tc_supported) -- attention of BertSelfAttention
+ * (examples/bert.py:78-88):
+ *   LG_EPI_SOFTMAX_FWD: c = softmax(alpha * (a b)) along each row            (scores -> probabilities);
+ *   LG_EPI_SOFTMAX_BWD: c = alpha * aux * (a b - sum_row(aux * (a b))), aux = the probabilities (c's layout).
  * aux has c's shape, row pitch aux_ld elements. */
-typedef enum { LG_EPI_NONE = 0, LG_EPI_GELU_FWD = 1, LG_EPI_GELU_BWD = 2 } LgGemmEpilogue;
+typedef enum {
+    LG_EPI_NONE = 0, LG_EPI_GELU_FWD = 1, LG_EPI_GELU_BWD = 2, LG_EPI_SOFTMAX_FWD = 3, LG_EPI_SOFTMAX_BWD = 4
+} LgGemmEpilogue;
 int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias,
-                     int epi_op, void* aux, int64_t aux_ld);
+                     int epi_op, void* aux, int64_t aux_ld, double alpha);
 /* Persistent tensor-core GEMM grids use at most n_sms SMs (0 = all).  The data-parallel wrapper lowers it while
  * gradient all-reduces overlap backward, so the collective's CTAs do not push a one-CTA-per-SM grid into a
  * second wave. */

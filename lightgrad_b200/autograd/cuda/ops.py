@@ -29,7 +29,7 @@ _matmul_mode = _MODES[os.environ.get('LG_MATMUL_MODE', 'fp32').lower()]
 
 Gradients.after_backward.append(rt.side_join)
 
-# A/B switch for measurements: LG_DISABLE=add_ln,mlp,attn,dx_acc turns the named fusions off
+# A/B switch for measurements: LG_DISABLE=add_ln,mlp,attn,attn_epi,dx_acc turns the named fusions off
 _DISABLED = set(filter(None, os.environ.get('LG_DISABLE', '').split(',')))
 
 
@@ -927,8 +927,28 @@ def _gemm_epilogue(a, b, out, bias, epi, aux):
     d = rt.GemmDesc(M, N, K, 1, 1, 0, 0, a._strides[0], a._strides[1], 0, 0, b._strides[0], b._strides[1],
                     0, 0, out._strides[0], 1)
     rt.api.gemm_epilogue(_matmul_mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr,
-                         bias.ptr if bias is not None else None, epi, aux.ptr, aux._strides[0])
+                         bias.ptr if bias is not None else None, epi, aux.ptr, aux._strides[0], 0.0)
     return out
+
+
+def _attention_gemm(a, b, out, epi, alpha, aux=None):
+    """Batched (batch, heads, M, K) @ (batch, heads, K, N) into the dense (batch, heads, M, N) ``out`` with a row
+    epilogue (lg_gemm_epilogue 3: softmax(alpha * product); 4: alpha * aux * (product - rowsum(aux * product))).
+    Returns False -- nothing launched -- when the tensor-core row epilogue cannot take the problem."""
+    if _matmul_mode == rt.GEMM_FP32_SIMT or 'attn_epi' in _DISABLED:
+        return False
+    B0, B1, M, K = a._shape
+    N = b._shape[-1]
+    if N > 128 or N % 4 or not out._contig or (aux is not None and not aux._contig) or a._code != rt.F32:
+        return False
+    d = rt.GemmDesc(M, N, K, B0, B1, a._strides[0], a._strides[1], a._strides[2], a._strides[3],
+                    b._strides[0], b._strides[1], b._strides[2], b._strides[3],
+                    out._strides[0], out._strides[1], out._strides[2], 1)
+    if not rt.api.gemm_tc_supported(_matmul_mode, a._code, C.byref(d)):
+        return False
+    rt.api.gemm_epilogue(_matmul_mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr, None, epi,
+                         aux.ptr if aux is not None else None, N, float(alpha))
+    return True
 
 
 @CudaTensor.register_op()
@@ -1026,10 +1046,11 @@ class self_attention(Function):
         hv = (b, heads, s, dh), (s * H, dh, H, 1)                      # per-head view of a (rows, H) matrix
         q, k, v = (qkv._view(hv[0], hv[1], g * rows * H) for g in range(3))
         scale = 1.0 / float(np.sqrt(dh))
-        scores = _gemm(q, _swap_last(k))
-        probs = CudaTensor._new(scores._shape, x._dtype)
-        rt.api.softmax_fwd(x._code, scores.ptr, probs.ptr, scores._numel // s, s, scale)
-        del scores
+        probs = CudaTensor._new((b, heads, s, s), x._dtype)
+        if not _attention_gemm(q, _swap_last(k), probs, 3, scale):      # softmax fused into the score GEMM's epilogue
+            scores = _gemm(q, _swap_last(k))
+            rt.api.softmax_fwd(x._code, scores.ptr, probs.ptr, scores._numel // s, s, scale)
+            del scores
         out = CudaTensor._new((b, s, H), x._dtype)
         _gemm(probs, v, out=out._view(hv[0], hv[1]))
         probs._temp = qkv._temp = False
@@ -1049,10 +1070,11 @@ class self_attention(Function):
         dqkv = CudaTensor._new((3, rows, H), x2._dtype)
         dq, dk, dv = (dqkv._view(hv[0], hv[1], i * rows * H) for i in range(3))
         _gemm(_swap_last(probs), go, out=dv)                            # dV = P^T dO
-        dp = _gemm(go, _swap_last(v))                                   # dP = dO V^T
         ds = CudaTensor._new(probs._shape, x2._dtype)
-        rt.api.softmax_bwd(x2._code, probs.ptr, dp.ptr, ds.ptr, probs._numel // s, s, scale)
-        del dp
+        if not _attention_gemm(go, _swap_last(v), ds, 4, scale, aux=probs):   # dS straight from the dP GEMM's epilogue
+            dp = _gemm(go, _swap_last(v))                               # dP = dO V^T
+            rt.api.softmax_bwd(x2._code, probs.ptr, dp.ptr, ds.ptr, probs._numel // s, s, scale)
+            del dp
         _gemm(ds, k, out=dq)                                            # dQ = dS K
         _gemm(_swap_last(ds), q, out=dk)                                # dK = dS^T Q
         parts = [dqkv._view((rows, H), (H, 1), i * rows * H) for i in range(3)]

@@ -80,7 +80,7 @@ _SIGNATURES = {
     'lg_gemm_tc_supported': [C.c_int, C.c_int, C.POINTER(GemmDesc)],
     'lg_gemm_grouped': [C.c_int, C.c_int, C.POINTER(GemmDesc), C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                         C.POINTER(_vp), C.c_int],
-    'lg_gemm_epilogue': [C.c_int, C.c_int, C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64],
+    'lg_gemm_epilogue': [C.c_int, C.c_int, C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double],
     'lg_gemm_sm_limit': [C.c_int],
     'lg_prof_gemm': [C.c_int],
     'lg_prof_gemm_read': [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)],

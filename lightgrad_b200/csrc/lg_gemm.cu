@@ -7,10 +7,10 @@ int gemm_simt(int dtype, const LgGemmDesc* d, const void* a, const void* b, void
 int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate);
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c);
 int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
-                    const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld);
+                    const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld, double alpha);
 int gemm_set_sm_limit(int n);
 int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
-                     int64_t aux_ld);
+                     int64_t aux_ld, double alpha);
 }  // namespace lg
 
 using namespace lg;
@@ -113,7 +113,7 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
     }
     int rc = 0;
     if (tc) {
-        rc = gemm_tc_grouped(d, groups, a, b, c, bias, accumulate, 0, nullptr, 0);
+        rc = gemm_tc_grouped(d, groups, a, b, c, bias, accumulate, 0, nullptr, 0, 0.0);
     } else {
         // exact path: one launch per group (a repeated C accumulates from the second group on)
         for (int g = 0; g < groups && !rc; ++g) {
@@ -130,28 +130,36 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
 }
 
 int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias,
-                     int epi_op, void* aux, int64_t aux_ld) {
+                     int epi_op, void* aux, int64_t aux_ld, double alpha) {
     LG_INIT();
-    LG_REQUIRE(epi_op == LG_EPI_GELU_FWD || epi_op == LG_EPI_GELU_BWD, "lg_gemm_epilogue: unknown epilogue %d", epi_op);
-    LG_REQUIRE(d->batch0 == 1 && d->batch1 == 1 && d->sc_n == 1, "lg_gemm_epilogue: one plain row-major result");
-    LG_REQUIRE(aux && aux_ld >= d->N, "lg_gemm_epilogue: aux operand missing");
+    LG_REQUIRE(epi_op >= LG_EPI_GELU_FWD && epi_op <= LG_EPI_SOFTMAX_BWD, "lg_gemm_epilogue: unknown epilogue %d", epi_op);
+    const bool rows = epi_op >= LG_EPI_SOFTMAX_FWD;
+    LG_REQUIRE(d->sc_n == 1, "lg_gemm_epilogue: row-major result");
+    LG_REQUIRE(rows || (d->batch0 == 1 && d->batch1 == 1), "lg_gemm_epilogue: the GELU epilogues take one plain product");
+    LG_REQUIRE(epi_op == LG_EPI_SOFTMAX_FWD || (aux && aux_ld >= d->N), "lg_gemm_epilogue: aux operand missing");
+    const double flops = 2.0 * (double)d->M * (double)d->N * (double)d->K * (double)(d->batch0 * d->batch1);
     if (g_skip) {
         g_skip_launches += 1;
-        g_skip_flops += 2.0 * (double)d->M * (double)d->N * (double)d->K;
+        g_skip_flops += flops;
         return 0;
     }
-    const bool tc = mode != LG_GEMM_FP32_SIMT && gemm_tc_supported(mode, dtype, d, a, b, c) &&
-                    (((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0 && d->N % 4 == 0;
+    bool tc = mode != LG_GEMM_FP32_SIMT && gemm_tc_supported(mode, dtype, d, a, b, c) && d->N % 4 == 0 &&
+              (!aux || ((((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0));
+    if (rows) {
+        // the row epilogues exist only on the tensor-core path (a row must fit one 128-column tile); callers
+        // check lg_gemm_tc_supported first and otherwise run the product and the softmax kernel separately
+        LG_REQUIRE(tc && d->N <= 128 && !bias, "lg_gemm_epilogue: row epilogue needs the tensor-core path, N <= 128, no bias");
+    }
     GemmProbe pr;
     if (g_prof_on) {
         LG_CUDA(cudaEventCreate(&pr.e0));
         LG_CUDA(cudaEventCreate(&pr.e1));
-        pr.flops = 2.0 * (double)d->M * (double)d->N * (double)d->K;
+        pr.flops = flops;
         LG_CUDA(cudaEventRecord(pr.e0, stream()));
     }
     int rc;
     if (tc) {
-        rc = gemm_tc_epilogue(d, a, b, c, bias, epi_op, aux, aux_ld);
+        rc = gemm_tc_epilogue(d, a, b, c, bias, epi_op, aux, aux_ld, alpha);
     } else {
         // exact path: the product, then the activation as a strided elementwise pass over the same buffers
         rc = gemm_simt(dtype, d, a, b, c, bias, 0);

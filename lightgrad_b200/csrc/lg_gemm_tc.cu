@@ -181,9 +181,12 @@ struct TcParams {
     int reduce_out;           // 1: C += tile (TMA reduce-add): split-K partials and/or accumulate mode
     int groups;               // problems of identical shape served by this launch (1-CTA kernel only)
     int a_chunked, b_chunked; // MN-major operand addressed through a rank-5 chunked map (one box per stage)
-    int epi_op;               // LgGemmEpilogue: 0 none, 1 aux = gelu(C) as a second result, 2 C = acc * gelu'(aux)
-    const float* aux;         // epi_op 2: pre-activation matrix (same shape as C), row pitch aux_ld elements
+    int epi_op;               // LgGemmEpilogue: 0 none, 1 aux = gelu(C) as a second result, 2 C = acc * gelu'(aux),
+                              // 3 C = softmax_row(alpha * acc), 4 C = alpha * aux * (acc - sum_row(aux * acc))
+    const float* aux;         // epi_op 2 / 4: saved matrix of C's shape, row pitch aux_ld elements
     long long aux_ld;
+    long long aux_sb0, aux_sb1;   // its batch strides (epi_op 4; same batch dims as C)
+    float epi_alpha;
     int kcat;                 // operand pairs concatenated along K into ONE result: C = sum_g A_g B_g (1-CTA kernel)
     const float* bias[LG_MAX_GROUPS];
 };
@@ -314,6 +317,125 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, ui
         bnext = (c + 2 < NC) ? bias_slice(t.bias, col0 + 64 + lane, t.N) : 0.f;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         epi_emit(t, v, bcur, col0, buf, lane);
+    }
+}
+
+// Row-wise epilogues of the batched attention GEMMs (one tile spans the whole row: N <= BN <= 128).  A row's
+// BN/32 chunks are split between the two warps of a TMEM lane quarter, which exchange their partial row
+// statistic through each other's staging buffer (named barrier 1 + q, 64 threads).
+//   op 3 (scores = Q K^T):  C = softmax(alpha * acc) along the row            (softmax_fwd fused away)
+//   op 4 (dP = dO V^T):     C = alpha * P * (acc - sum_row(P * acc)), P = aux  (softmax_bwd fused away)
+__device__ __forceinline__ void pair_bar(int q) {
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+}
+// this thread's slice of the saved matrix (op 4): issued BEFORE the wait for the accumulator, so the global-memory
+// latency hides behind the tile's main loop
+template <int BN>
+__device__ __forceinline__ void epilogue_rows_prefetch(const EpiTile& t, int half, float (&aux)[(BN / 32 + 1) / 2][32]) {
+    constexpr int NC = BN / 32;
+    constexpr int PER = (NC + 1) / 2;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = half + 2 * k;
+        const int col0 = t.n0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t.epi_op == 4 && t.aux != nullptr && c < NC && col0 + 4 * j + 3 < t.N)
+                h = __ldg(reinterpret_cast<const float4*>(t.aux + col0 + 4 * j));
+            aux[k][4 * j] = h.x; aux[k][4 * j + 1] = h.y; aux[k][4 * j + 2] = h.z; aux[k][4 * j + 3] = h.w;
+        }
+    }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_rows(const EpiTile& t, uint32_t taddr0, uint8_t* buf, uint8_t* partner_buf,
+                                                   int half, int q, int lane, float alpha,
+                                                   const float (&aux)[(BN / 32 + 1) / 2][32]) {
+    constexpr int NC = BN / 32;
+    constexpr int PER = (NC + 1) / 2;        // chunks per warp: half, half + 2, ...
+    float x[PER][32];
+    float* mine = reinterpret_cast<float*>(buf);
+    const float* other = reinterpret_cast<const float*>(partner_buf);
+    // previous tile's TMA stores must have drained before the staging buffers carry statistics
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = half + 2 * k;
+        const int col0 = t.n0 + c * 32;
+        const bool live = c < NC && col0 < t.N;
+        uint32_t raw[32];
+        if (c < NC) {
+            tmem_ld32(raw, taddr0 + (uint32_t)(c * 32));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const bool ok = live && col0 + i < t.N;
+            x[k][i] = ok ? __uint_as_float(raw[i]) : 0.f;
+        }
+    }
+    if (t.epi_op == 3) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int col0 = t.n0 + (half + 2 * k) * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                // scores in units of log2(e), so that exp() below is a bare ex2
+                x[k][i] = (half + 2 * k < NC && col0 + i < t.N) ? x[k][i] * (alpha * 1.4426950408889634f) : -INFINITY;
+                m = fmaxf(m, x[k][i]);
+            }
+        }
+        mine[lane] = m;
+        pair_bar(q);
+        m = fmaxf(m, other[lane]);
+        pair_bar(q);                      // both warps have read the maxima
+        float ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                // only 8 warps per SM do this: ex2.approx (2^-22 relative) instead of expf; 2^-inf = 0 masks columns
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x[k][i]) : "f"(x[k][i] - m));
+                ssum += x[k][i];
+            }
+        mine[lane] = ssum;
+        pair_bar(q);
+        ssum += other[lane];
+        pair_bar(q);                      // statistics consumed: the buffers may be used for staging again
+        const float inv = 1.0f / ssum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[k][i] *= inv;
+    } else {
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dot += aux[k][i] * x[k][i];
+        mine[lane] = dot;
+        pair_bar(q);
+        dot += other[lane];
+        pair_bar(q);
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[k][i] = aux[k][i] * (x[k][i] - dot) * alpha;
+    }
+    if (!t.rows_live) return;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = half + 2 * k;
+        const int col0 = t.n0 + c * 32;
+        if (c < NC && col0 < t.N) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(x[k][i]);
+            epi_store(t.map_c, v, buf, col0, t.row0, t.bc1, t.bc0, 0, lane);
+        }
     }
 }
 
@@ -539,7 +661,9 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             t.epi_op = p.epi_op;
             t.bias = split == 0 ? bias : nullptr;
             t.row0 = m0 + 32 * q;
-            t.aux = (p.epi_op == 2 && t.row0 + lane < p.M) ? p.aux + (long long)(t.row0 + lane) * p.aux_ld : nullptr;
+            t.aux = ((p.epi_op == 2 || p.epi_op == 4) && t.row0 + lane < p.M)
+                        ? p.aux + bc0 * p.aux_sb0 + bc1 * p.aux_sb1 + (long long)(t.row0 + lane) * p.aux_ld
+                        : nullptr;
             t.n0 = n0;
             t.N = p.N;
             t.bc1 = bc1;
@@ -547,9 +671,22 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             t.reduce_out = p.reduce_out;
             t.rows_live = t.row0 < p.M;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
+            float row_aux[BN <= 128 ? (BN / 32 + 1) / 2 : 1][32];
+            if constexpr (BN <= 128) {
+                if (p.epi_op == 4) epilogue_rows_prefetch<BN>(t, half, row_aux);
+            }
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, half, lane);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
+            if constexpr (BN <= 128) {
+                if (p.epi_op >= 3)
+                    epilogue_tile_rows<BN>(t, taddr0, buf0, epi_base + (ew ^ 4) * EPI_BUF_BYTES, half, q, lane,
+                                           p.epi_alpha, row_aux);
+                else
+                    epilogue_tile<BN>(t, bfirst, taddr0, buf0, half, lane);
+            } else {
+                epilogue_tile<BN>(t, bfirst, taddr0, buf0, half, lane);
+            }
             // this warp is done reading the accumulator stage
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&tempty[acc]);
@@ -1033,12 +1170,17 @@ int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, c
 // 3 x 128 tiles instead of three one-wave launches).  Several groups may name the same C: with
 // accumulate they all reduce-add into it (dX = sum_g dY_g W_g).
 int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
-                    const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld) {
+                    const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld, double alpha) {
     if (load_encode()) return 1;
-    if (epi_op) {
+    if (epi_op == 1 || epi_op == 2) {
         LG_REQUIRE(groups == 1 && d->batch0 * d->batch1 == 1 && !accumulate, "gemm_tc: epilogue ops need one plain GEMM");
         LG_REQUIRE(aux && (((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0 && aux_ld >= d->N && d->N % 4 == 0,
                    "gemm_tc: epilogue operand must be 16-byte aligned with a row pitch that is a multiple of 4");
+    }
+    if (epi_op >= 3) {
+        LG_REQUIRE(groups == 1 && !accumulate && !bias && d->N <= 128, "gemm_tc: row epilogues need N <= 128, no bias");
+        LG_REQUIRE(epi_op == 3 || (aux && (((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0 && d->N % 4 == 0),
+                   "gemm_tc: row epilogue operand must be 16-byte aligned with a row pitch that is a multiple of 4");
     }
     LG_REQUIRE(groups >= 1 && groups <= LG_MAX_GROUPS, "gemm_tc: 1..%d groups per launch", LG_MAX_GROUPS);
     const int64_t M = d->M, N = d->N, K = d->K;
@@ -1058,6 +1200,11 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     // split-K partials meet in C by reduce-add: C must be zeroed first (done below for one plain matrix) or
     // already hold the value being accumulated into
     Plan pl = choose_plan(M, N, K, batches * n_problems, !epi_op && (accumulate || batches * n_problems == 1));
+    if (epi_op >= 3) {
+        // the whole row must live in one tile
+        const int bn = N <= 64 ? 64 : 128;
+        pl = Plan{bn, 1, (int)((M + BM - 1) / BM), 1, pl.kblocks, pl.kblocks};
+    }
     int rc;
     const BatchDims ba{d->batch1, d->sa_b1, d->batch0, d->sa_b0}, bb{d->batch1, d->sb_b1, d->batch0, d->sb_b0},
         bc{d->batch1, d->sc_b1, d->batch0, d->sc_b0};
@@ -1066,7 +1213,8 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     //  independent CTAs on the one-wave BERT projections, which therefore keep cta_group::1)
     static const int force_pair = getenv("LG_GEMM_PAIR") ? atoi(getenv("LG_GEMM_PAIR")) : -1;
     const bool big = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits >= 2 * (int64_t)gemm_sms();
-    const bool pair_mma = groups == 1 && batches == 1 && pl.tiles_m >= 2 && (force_pair < 0 ? big : force_pair == 1);
+    const bool pair_mma = groups == 1 && batches == 1 && epi_op < 3 && pl.tiles_m >= 2 &&
+                          (force_pair < 0 ? big : force_pair == 1);
     const int cl = pair_mma ? 2 : 1;
     TcMaps maps;
     TcParams p;
@@ -1102,6 +1250,9 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     p.epi_op = epi_op;
     p.aux = (const float*)aux;
     p.aux_ld = aux_ld;
+    p.aux_sb0 = d->sc_b0;      // a saved matrix of a row epilogue has C's batch layout
+    p.aux_sb1 = d->sc_b1;
+    p.epi_alpha = (float)alpha;
     if (epi_op == 1) {
         // second result: same geometry as C, its own row pitch
         rc = make_map(&maps.aux, aux, N, M, aux_ld, BatchDims{1, 0, 1, 0}, 32, 32);
@@ -1146,16 +1297,16 @@ int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c
     const void* bv[1] = {b};
     void* cv[1] = {c};
     const void* biasv[1] = {bias};
-    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate, 0, nullptr, 0);
+    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate, 0, nullptr, 0, 0.0);
 }
 
 int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
-                     int64_t aux_ld) {
+                     int64_t aux_ld, double alpha) {
     const void* av[1] = {a};
     const void* bv[1] = {b};
     void* cv[1] = {c};
     const void* biasv[1] = {bias};
-    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, 0, epi_op, aux, aux_ld);
+    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, 0, epi_op, aux, aux_ld, alpha);
 }
 
 int gemm_set_sm_limit(int n) {

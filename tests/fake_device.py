@@ -217,12 +217,22 @@ class FakeDevice(object):
                       1 if (accumulate or again) else 0)
             seen.append(c[g])
 
-    def gemm_epilogue(self, mode, dt, dref, a, b, c, bias, epi, aux, aux_ld):
+    def gemm_epilogue(self, mode, dt, dref, a, b, c, bias, epi, aux, aux_ld, alpha):
         d = dref._obj
         self.gemm(mode, dt, dref, a, b, c, bias, 0)
+        f = NP[dt]
+        if epi >= 3:
+            Cm = _arr(c, dt, [d.batch0, d.batch1, d.M, d.N], [d.sc_b0, d.sc_b1, d.sc_m, 1])
+            if epi == 3:
+                X = Cm * f(alpha)
+                e = np.exp(X - X.max(axis=-1, keepdims=True))
+                Cm[...] = e / e.sum(axis=-1, keepdims=True)
+            else:
+                P = _arr(aux, dt, [d.batch0, d.batch1, d.M, d.N], [d.sc_b0, d.sc_b1, aux_ld, 1])
+                Cm[...] = P * (Cm - (P * Cm).sum(axis=-1, keepdims=True)) * f(alpha)
+            return
         Cm = _arr(c, dt, [d.M, d.N], [d.sc_m, 1])
         X = _arr(aux, dt, [d.M, d.N], [aux_ld, 1])
-        f = NP[dt]
         c1, c2 = f(0.7978845608), f(0.044715)
         if epi == 1:
             inner = (Cm * c1) * (f(1.0) + (c2 * Cm) * Cm)
