@@ -271,24 +271,29 @@ __device__ __forceinline__ void epi_store(const CUtensorMap* map, const uint32_t
 }
 
 // v: this thread's 32 accumulator values of the chunk (as raw bits), finished and stored in place
-__device__ __forceinline__ void epi_emit(const EpiTile& t, uint32_t (&v)[32], float bcur, int col0, uint8_t* buf,
-                                         int lane) {
+// this thread's 32 pre-activation values of a chunk (op 2): one 128-byte line; columns past N are never stored
+__device__ __forceinline__ void epi_load_h(const EpiTile& t, int col0, float4 (&h)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        h[j] = (t.epi_op == 2 && t.aux != nullptr && col0 + 4 * j + 3 < t.N)
+                   ? __ldg(reinterpret_cast<const float4*>(t.aux + col0 + 4 * j))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void epi_emit(const EpiTile& t, uint32_t (&v)[32], float bcur, const float4 (&h)[8], int col0,
+                                         uint8_t* buf, int lane) {
     if (t.bias != nullptr) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __shfl_sync(0xffffffffu, bcur, k));
     }
     if (!t.rows_live) return;
     if (t.epi_op == 2) {
-        // pre-activation values of this thread's row (one 128-byte line; columns past N are never stored)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 h = (t.aux != nullptr && col0 + 4 * j + 3 < t.N)
-                                 ? __ldg(reinterpret_cast<const float4*>(t.aux + col0 + 4 * j))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * j + 0] = __float_as_uint(epi_gelu_bwd(h.x, __uint_as_float(v[4 * j + 0])));
-            v[4 * j + 1] = __float_as_uint(epi_gelu_bwd(h.y, __uint_as_float(v[4 * j + 1])));
-            v[4 * j + 2] = __float_as_uint(epi_gelu_bwd(h.z, __uint_as_float(v[4 * j + 2])));
-            v[4 * j + 3] = __float_as_uint(epi_gelu_bwd(h.w, __uint_as_float(v[4 * j + 3])));
+            v[4 * j + 0] = __float_as_uint(epi_gelu_bwd(h[j].x, __uint_as_float(v[4 * j + 0])));
+            v[4 * j + 1] = __float_as_uint(epi_gelu_bwd(h[j].y, __uint_as_float(v[4 * j + 1])));
+            v[4 * j + 2] = __float_as_uint(epi_gelu_bwd(h[j].z, __uint_as_float(v[4 * j + 2])));
+            v[4 * j + 3] = __float_as_uint(epi_gelu_bwd(h[j].w, __uint_as_float(v[4 * j + 3])));
         }
     }
     epi_store(t.map_c, v, buf, col0, t.row0, t.bc1, t.bc0, t.reduce_out, lane);
@@ -301,12 +306,17 @@ __device__ __forceinline__ void epi_emit(const EpiTile& t, uint32_t (&v)[32], fl
 
 // This warp takes chunks half, half + 2, ... of the tile (its partner on the same TMEM lane quarter takes the
 // others; eight epilogue warps keep enough TMEM loads / stores in flight without software pipelining).
-// `bfirst` = bias_slice of its first chunk, loaded by the caller BEFORE it waited for the accumulator.
+// `bfirst` / `hfirst` = bias slice / saved pre-activations (op 2) of its first chunk, loaded by the caller BEFORE
+// it waited for the accumulator; inside the loop both are fetched one chunk ahead, so no global-memory latency
+// sits between the TMEM read and the store.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, uint32_t taddr0, uint8_t* buf, int half,
-                                              int lane) {
+__device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, const float (&hfirst)[32], uint32_t taddr0,
+                                              uint8_t* buf, int half, int lane) {
     constexpr int NC = BN / 32;
     float bnext = bfirst;
+    float4 hnext[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hnext[j] = make_float4(hfirst[4 * j], hfirst[4 * j + 1], hfirst[4 * j + 2], hfirst[4 * j + 3]);
 #pragma unroll 1
     for (int c = half; c < NC; c += 2) {
         const int col0 = t.n0 + c * 32;
@@ -314,9 +324,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, ui
         uint32_t v[32];
         tmem_ld32(v, taddr0 + (uint32_t)(c * 32));
         const float bcur = bnext;
-        bnext = (c + 2 < NC) ? bias_slice(t.bias, col0 + 64 + lane, t.N) : 0.f;
+        float4 hcur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hcur[j] = hnext[j];
+        if (c + 2 < NC) {
+            bnext = bias_slice(t.bias, col0 + 64 + lane, t.N);
+            if (t.epi_op == 2) epi_load_h(t, col0 + 64, hnext);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        epi_emit(t, v, bcur, col0, buf, lane);
+        epi_emit(t, v, bcur, hcur, col0, buf, lane);
     }
 }
 
@@ -671,9 +687,22 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             t.reduce_out = p.reduce_out;
             t.rows_live = t.row0 < p.M;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
+            // operands the epilogue reads from global memory, fetched before the wait for the accumulator:
+            // op 2: the first chunk's pre-activations (row_aux[0]); op 4: this thread's slice of the probabilities
             float row_aux[BN <= 128 ? (BN / 32 + 1) / 2 : 1][32];
+            bool rows_op = false;
+            if constexpr (BN <= 128) rows_op = p.epi_op == 4;
             if constexpr (BN <= 128) {
-                if (p.epi_op == 4) epilogue_rows_prefetch<BN>(t, half, row_aux);
+                if (rows_op) epilogue_rows_prefetch<BN>(t, half, row_aux);
+            }
+            if (!rows_op) {
+                float4 h4[8];
+                epi_load_h(t, n0 + half * 32, h4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    row_aux[0][4 * j] = h4[j].x; row_aux[0][4 * j + 1] = h4[j].y;
+                    row_aux[0][4 * j + 2] = h4[j].z; row_aux[0][4 * j + 3] = h4[j].w;
+                }
             }
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -683,9 +712,9 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
                     epilogue_tile_rows<BN>(t, taddr0, buf0, epi_base + (ew ^ 4) * EPI_BUF_BYTES, half, q, lane,
                                            p.epi_alpha, row_aux);
                 else
-                    epilogue_tile<BN>(t, bfirst, taddr0, buf0, half, lane);
+                    epilogue_tile<BN>(t, bfirst, row_aux[0], taddr0, buf0, half, lane);
             } else {
-                epilogue_tile<BN>(t, bfirst, taddr0, buf0, half, lane);
+                epilogue_tile<BN>(t, bfirst, row_aux[0], taddr0, buf0, half, lane);
             }
             // this warp is done reading the accumulator stage
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -907,9 +936,19 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
             t.reduce_out = p.reduce_out;
             t.rows_live = t.row0 < p.M;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
+            float hfirst[32];
+            {
+                float4 h4[8];
+                epi_load_h(t, n0 + half * 32, h4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    hfirst[4 * j] = h4[j].x; hfirst[4 * j + 1] = h4[j].y; hfirst[4 * j + 2] = h4[j].z; hfirst[4 * j + 3] = h4[j].w;
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile<BN>(t, bfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, half, lane);
+            epilogue_tile<BN>(t, bfirst, hfirst, tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN), buf0, half,
+                              lane);
             // one arrival per warp on the LEADER's barrier: the accumulator stage of this CTA is drained
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -1273,7 +1312,7 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int64_t items64 = (int64_t)p.tiles_m * pl.tiles_n * pl.splits * batches * n_problems;   // cluster work items
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
-    const int max_clusters = gemm_sms() / cl;
+    const int max_clusters = gemm_sms() / cl > 0 ? gemm_sms() / cl : 1;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
     if (pair_mma) {
         switch (pl.bn) {

@@ -238,3 +238,67 @@ def test_add_layernorm_matches_oracle(device, shape, preset_grads):
     np.testing.assert_allclose(got_out, want_out, rtol=3e-5, atol=3e-6)
     for n, g, wv in zip('abwB', got_g, want_g):
         np.testing.assert_allclose(g, wv, rtol=2e-4, atol=2e-5 * max(1.0, float(np.abs(wv).max())), err_msg=n)
+
+
+@pytest.mark.gpu
+def test_side_stream_results_visible_after_join(cuda):
+    # work issued between lg_side_begin / lg_side_end runs on the second stream; lg_side_join (and, implicitly,
+    # numpy()) orders the compute stream after it
+    prev = ops.set_matmul_mode('tf32')
+    try:
+        rs = np.random.RandomState(11)
+        a = rs.uniform(-1, 1, (512, 256)).astype(np.float32)
+        b = rs.uniform(-1, 1, (256, 384)).astype(np.float32)
+        A, B = CudaTensor.from_numpy(a), CudaTensor.from_numpy(b)
+        acc = CudaTensor.zeros((512, 384))
+        for _ in range(3):
+            with rt.side_stream(A, B, writes=(acc,)):
+                ops._gemm(A, B, out=acc, accumulate=True)
+            # an in-place update from the compute stream must first wait for the side stream's writes
+            acc += 1.0
+        rt.side_join()
+        want = 3 * (a.astype(np.float64) @ b.astype(np.float64)) + 3
+        assert rel(acc.numpy(), want) <= 5e-3
+    finally:
+        ops.set_matmul_mode(prev)
+
+
+@pytest.mark.gpu
+def test_gemm_sm_limit_keeps_results(cuda):
+    prev = ops.set_matmul_mode('tf32')
+    try:
+        rs = np.random.RandomState(12)
+        a = rs.uniform(-1, 1, (1024, 512)).astype(np.float32)
+        b = rs.uniform(-1, 1, (512, 768)).astype(np.float32)
+        A, B = CudaTensor.from_numpy(a), CudaTensor.from_numpy(b)
+        want = a.astype(np.float64) @ b.astype(np.float64)
+        for limit in (100, 37, 1, 0):
+            rt.api.gemm_sm_limit(limit)
+            assert rel((A @ B).numpy(), want) <= 5e-3, limit
+    finally:
+        rt.api.gemm_sm_limit(0)
+        ops.set_matmul_mode(prev)
+
+
+def test_mlp_gelu_unaligned_width_takes_the_exact_path(mode):
+    # intermediate width not a multiple of 4: no TMA-aligned pitch -> product and activation as separate kernels
+    rs = np.random.RandomState(13)
+    x = rs.uniform(-1, 1, (2, 8, 64)).astype(np.float32)
+    w1 = (rs.uniform(-1, 1, (130, 64)) / 8).astype(np.float32)
+    w2 = (rs.uniform(-1, 1, (64, 130)) / 11).astype(np.float32)
+    b1 = rs.uniform(-0.5, 0.5, (130,)).astype(np.float32)
+    b2 = rs.uniform(-0.5, 0.5, (64,)).astype(np.float32)
+
+    def run(T):
+        X = T.from_numpy(x)
+        P = [T.from_numpy(v) for v in (w1, b1, w2, b2)]
+        out = X.mlp_gelu(*P) if T is CudaTensor else _oracle_mlp(T, X, *P)
+        out.sum().backward()
+        return out.numpy(), [X.grad.numpy()] + [p.grad.numpy() for p in P]
+
+    want_out, want_g = run(CpuTensor)
+    got_out, got_g = run(CudaTensor)
+    tol = _tol(mode) * (10 if mode == 'fp32' else 1)
+    assert rel(got_out, want_out) <= tol
+    for g, w in zip(got_g, want_g):
+        assert rel(g, w) <= tol
