@@ -183,6 +183,21 @@ def cases():
                     3.0 * rows * cols * 4
             return make
 
+        def ce(bwd):
+            ld = (V + 31) // 32 * 32
+            def make(sets):
+                X = [rand(R, ld) for _ in range(sets)]
+                lab = CudaTensor.from_numpy(np.random.randint(0, V, size=(R,)).astype(np.int32), requires_grad=False)
+                loss_rows, lse, one = CudaTensor.empty((R,)), CudaTensor.empty((R,)), CudaTensor.ones((1,))
+                D = [CudaTensor.empty((R, ld)) for _ in range(sets)]
+                rt.api.cross_entropy_fwd(rt.F32, rt.I32, X[0].ptr, ld, lab.ptr, loss_rows.ptr, lse.ptr, R, V)
+                if not bwd:
+                    return (lambda i: rt.api.cross_entropy_fwd(rt.F32, rt.I32, X[i].ptr, ld, lab.ptr, loss_rows.ptr,
+                                                               lse.ptr, R, V)), 1.0 * R * V * 4
+                return (lambda i: rt.api.cross_entropy_bwd(rt.F32, rt.I32, X[i].ptr, ld, lab.ptr, lse.ptr, one.ptr,
+                                                           D[i].ptr, ld, R, V)), 2.0 * R * V * 4
+            return make
+
         def adam():
             def make(sets):
                 n = 110 * 1000 * 1000 // 64 * 64
@@ -198,6 +213,7 @@ def cases():
                 ('add 4096x768', ew('ADD', 2, H)), ('gelu 4096x3072', ew('GELU', 1, F)),
                 ('gelu_bwd 4096x3072', ew('GELU_BWD', 2, F)),
                 ('softmax fwd 49152x128', softmax(False)), ('softmax bwd 49152x128', softmax(True)),
+                ('cross entropy fwd 4096x30522', ce(False)), ('cross entropy bwd 4096x30522', ce(True)),
                 ('adam 110M', adam())]
 
     if os.environ.get('GEMM_GRAPH_SUITE') == 'layout':
@@ -234,7 +250,7 @@ def main():
     for name, make in cases():
         if a.only and a.only not in name:
             continue
-        sets = 2 if ('decoder' in name or '4096x4096' in name) else (12 if '768' in name and 'x3072' not in name and os.environ.get('GEMM_GRAPH_SUITE') == 'fused' else a.sets)
+        sets = 2 if ('decoder' in name or '4096x4096' in name or 'cross entropy' in name) else (12 if '768' in name and 'x3072' not in name and os.environ.get('GEMM_GRAPH_SUITE') == 'fused' else a.sets)
         go, flops = make(sets)
 
         def body():

@@ -856,6 +856,7 @@ class linear(Function):
         if xg is not None:
             # x already holds a gradient from another consumer (residual branch): dX is reduce-added into it by
             # the GEMM epilogue instead of being materialised and added by a separate pass
+            rt.side_join_if_written(xg)
             _gemm(g2, weight, out=_fold_rows(xg), accumulate=True)
             dx = Function.ACCUMULATED
         else:
@@ -990,6 +991,7 @@ class mlp_gelu(Function):
         _gemm_epilogue(g2, w2, dh, None, 2, h)                     # dh = (dY W2) * gelu'(h)
         xg = _direct_grad(xin, code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
         if xg is not None:
+            rt.side_join_if_written(xg)
             _gemm(dh, w1, out=_fold_rows(xg), accumulate=True)
             dx = Function.ACCUMULATED
         else:
@@ -1083,6 +1085,7 @@ class self_attention(Function):
         xg = _direct_grad(xin, x2._code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
         if xg is not None:
             # dX = sum_g dY_g W_g added into the gradient x already received through the residual branch
+            rt.side_join_if_written(xg)
             _gemm_grouped(parts, list(ws), [_fold_rows(xg)] * 3, accumulate=True)
             dx = Function.ACCUMULATED
         else:
@@ -1264,6 +1267,7 @@ class getitem(Function):
                 and a.grad._code == out_grad._code and a.grad._code in (rt.F32, rt.F64):
             # scatter-add straight into the existing gradient of the table (skips zero-filling and adding a
             # table-sized temporary: 94 MB for BERT's word embeddings)
+            rt.side_join_if_written(a.grad)     # e.g. a table tied to a Linear weight whose dW runs on the side stream
             src, plan = _index_plan(a.grad, idx)
             rows, row_stride, n_rows, n_idx, row_len, bshape, tail_shape, _keep = plan
             if src._data is a.grad._data:
@@ -1394,6 +1398,9 @@ def _ln_backward(x, w, mean, rstd, weight, bias, out_grad):
             and bg._contig and wg._code == bg._code == x._code and wg._shape == bg._shape == (cols,):
         # d(gamma), d(beta) are added straight into the existing gradients
         rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, wg.ptr, bg.ptr, rows, cols, 1)
+        # (the library sums the per-CTA partials into wg / bg on the side stream)
+        rt._side_dirty.add(wg.ptr)
+        rt._side_dirty.add(bg.ptr)
         return dx, Function.ACCUMULATED, Function.ACCUMULATED
     dw, db = CudaTensor._new((cols,), x._dtype), CudaTensor._new((cols,), x._dtype)
     rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols, 0)

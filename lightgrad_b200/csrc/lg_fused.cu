@@ -130,11 +130,27 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, in
         int64_t nv = 0;
         if (((uintptr_t)p & 15) == 0) {
             nv = cols / V;
-            for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
-                Vec<T, V> w = reinterpret_cast<const Vec<T, V>*>(p)[j];
+            // two vectors per iteration in flight; the running maximum is raised at most once per vector, so the
+            // common case costs one exp per element instead of a data-dependent branch around two
+            auto feed_vec = [&](const Vec<T, V>& w) {
+                T vm = w.v[0];
 #pragma unroll
-                for (int k = 0; k < V; ++k) feed(w.v[k]);
+                for (int k = 1; k < V; ++k) vm = vm > w.v[k] ? vm : w.v[k];
+                if (vm > m) {
+                    s = s * f_exp(m - vm);
+                    m = vm;
+                }
+#pragma unroll
+                for (int k = 0; k < V; ++k) s += f_exp(w.v[k] - m);
+            };
+            int64_t j = threadIdx.x;
+            for (; j + blockDim.x < nv; j += 2 * blockDim.x) {
+                Vec<T, V> w0 = reinterpret_cast<const Vec<T, V>*>(p)[j];
+                Vec<T, V> w1 = reinterpret_cast<const Vec<T, V>*>(p)[j + blockDim.x];
+                feed_vec(w0);
+                feed_vec(w1);
             }
+            for (; j < nv; j += blockDim.x) feed_vec(reinterpret_cast<const Vec<T, V>*>(p)[j]);
         }
         for (int64_t j = nv * V + threadIdx.x; j < cols; j += blockDim.x) feed(p[j]);
         T gm = block_max(m, sm);

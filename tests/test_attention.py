@@ -302,3 +302,29 @@ def test_mlp_gelu_unaligned_width_takes_the_exact_path(mode):
     assert rel(got_out, want_out) <= tol
     for g, w in zip(got_g, want_g):
         assert rel(g, w) <= tol
+
+
+@pytest.mark.parametrize("preset_grads", [False, True])
+def test_tied_embedding_and_projection_weight(mode, preset_grads):
+    # one table used as an embedding (gather / scatter-add backward, compute stream) AND as a Linear weight (dW on the
+    # side stream): both contributions must land in the same gradient
+    rs = np.random.RandomState(14)
+    V, H, n = 96, 64, 256
+    w = (rs.uniform(-1, 1, (V, H)) / 8).astype(np.float32)
+    ids = rs.randint(0, V, size=(n,)).astype(np.int32)
+    up = rs.uniform(-1, 1, (n, V)).astype(np.float32)
+
+    def run(T):
+        W = T.from_numpy(w)
+        if T is CudaTensor and preset_grads:
+            W.zero_grad()
+        x = W[ids]
+        y = x.linear(W) if T is CudaTensor else x @ W.transpose(1, 0)
+        (y * T.from_numpy(up, requires_grad=False)).sum().backward()
+        return y.numpy(), W.grad.numpy()
+
+    want_y, want_g = run(CpuTensor)
+    got_y, got_g = run(CudaTensor)
+    tol = _tol(mode) * (10 if mode == 'fp32' else 1)
+    assert rel(got_y, want_y) <= tol
+    assert rel(got_g, want_g) <= tol
