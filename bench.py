@@ -119,10 +119,12 @@ def make_step(model, opt, dp, light):
         loss = light.loss.cross_entropy(logits.reshape(-1, model.vocab_size), labels)
         opt.zero_grad()
         if dp is not None:
-            dp.backward(loss)          # backward with the bucketed gradient all-reduce overlapped
+            # backward with the bucketed gradient all-reduce overlapped (+ LG_DP_PIPELINED_STEP=1: the optimizer
+            # pipelined behind each bucket's exchange), then the optimizer step
+            dp.backward_and_step(loss)
         else:
             loss.backward()
-        opt.step()
+            opt.step()
         return loss
     return step
 

@@ -130,6 +130,11 @@ int lg_stream_delay_us(uint64_t us);
  * reference has a single in-order OpenCL queue, opencl/device.py:58-60).  lg_side_join makes the compute stream
  * wait for them; lg_sync, lg_memcpy_d2h, lg_graph_begin/end and lg_nccl_fork join / order implicitly.  The caller
  * keeps every buffer those launches touch alive until the join. */
+/* lg_comm_compute_begin .. end: launches in between go to the COLLECTIVE stream, i.e. right behind the all-reduce
+ * queued there (per-bucket optimizer updates that must not stall backward on the compute stream); lg_nccl_wait
+ * orders the compute stream after them. */
+int lg_comm_compute_begin(void);
+int lg_comm_compute_end(void);
 int lg_side_begin(void);
 int lg_side_end(void);
 int lg_side_join(void);
@@ -261,11 +266,15 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
 /* all tensors of one optimizer live in flat fp32 arenas; `seg_end_dev[i]` (device, int64) is the
  * exclusive end offset of tensor i.  Tensor i uses step count t = *t_dev + i + 1 in its bias
  * corrections 1 - beta^t (the reference advances t once per parameter, optim.py:36-37); the counter
- * lives on the device so that a captured step stays correct when replayed.                       */
+ * lives on the device so that a captured step stays correct when replayed.
+ * A call may cover a sub-range of the arena (per-bucket updates): the pointers address its first element,
+ * seg_base is that element's offset in the arena (seg_end_dev entries are arena offsets), its tensors are
+ * number seg_offset .. seg_offset + n_seg - 1, and the counter is advanced by t_advance (0 for all but one call
+ * of a step; the whole-arena call passes 0, 0, n_seg). */
 int lg_sgd_step(void* param, const void* grad, void* delta, int64_t n, double lr, double momentum);
 int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, int64_t n,
-                 int n_seg, const int64_t* seg_end_dev, int64_t* t_dev /* device counter, advanced by n_seg */,
-                 double lr, double beta1, double beta2, double eps);
+                 int n_seg, const int64_t* seg_end_dev, int64_t* t_dev, double lr, double beta1, double beta2,
+                 double eps, int64_t seg_base, int seg_offset, int t_advance);
 
 /* ---- collectives (new; NCCL over NVLink, one process per GPU) ------------------------------- */
 int lg_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId */

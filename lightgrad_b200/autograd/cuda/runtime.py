@@ -65,6 +65,8 @@ _SIGNATURES = {
     'lg_graph_begin': [C.POINTER(C.c_int)],
     'lg_graph_end': [C.POINTER(_vp), C.POINTER(C.c_uint64)],
     'lg_graph_abort': [],
+    'lg_comm_compute_begin': [],
+    'lg_comm_compute_end': [],
     'lg_side_begin': [],
     'lg_side_end': [],
     'lg_side_join': [],
@@ -97,7 +99,7 @@ _SIGNATURES = {
     'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
     'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp,
-                     C.c_double, C.c_double, C.c_double, C.c_double],
+                     C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int],
     'lg_nccl_unique_id': [_vp],
     'lg_nccl_init': [_vp, C.c_int, C.c_int],
     'lg_nccl_allreduce_f32': [_vp, C.c_int64, C.c_int, C.c_int],

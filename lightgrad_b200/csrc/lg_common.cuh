@@ -18,7 +18,9 @@ namespace lg {
 // ---- error plumbing ---------------------------------------------------------------------------
 int set_error(const char* fmt, ...);
 cudaStream_t stream();        // stream kernels launch on: the compute stream, or the side stream inside lg_side_begin/end
-bool on_side_stream();
+bool on_side_stream();      // launching on the side stream or (lg_comm_compute_begin) on the collective stream
+int alt_stream_index();     // 0 compute, 1 side, 2 collective stream
+void comm_release_deferred();
 int side_join();
 int side_order_before(cudaStream_t other);
 cudaStream_t comm_stream();   // collective stream

@@ -93,6 +93,7 @@ int lg_nccl_wait(void) {
     LG_REQUIRE(g_comm_nccl, "lg_nccl_wait: communicator not initialised");
     LG_CUDA(cudaEventRecord(g_ev_join, comm_stream()));
     LG_CUDA(cudaStreamWaitEvent(stream(), g_ev_join, 0));
+    comm_release_deferred();
     return 0;
 }
 

@@ -43,11 +43,11 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
 // per-tensor bias corrections 1 - beta^t with t = *t_dev + i + 1, evaluated in double like python does;
 // one CTA, so the counter can be advanced after every thread has read it
 __global__ void adam_prep_kernel(int n_seg, int64_t* __restrict__ t_dev, double b1, double b2,
-                                 float* __restrict__ c1, float* __restrict__ c2) {
+                                 float* __restrict__ c1, float* __restrict__ c2, int seg_offset, int t_advance) {
     LG_PDL_TRIGGER();
     const int64_t t0 = *t_dev;
     for (int i = threadIdx.x; i < n_seg; i += blockDim.x) {
-        const double t = (double)(t0 + i + 1);
+        const double t = (double)(t0 + seg_offset + i + 1);
         const float f1 = (float)(1.0 - pow(b1, t)), f2 = (float)(1.0 - pow(b2, t));
         c1[i] = f1;
         c2[i] = f2;
@@ -56,11 +56,12 @@ __global__ void adam_prep_kernel(int n_seg, int64_t* __restrict__ t_dev, double 
         c2[n_seg * 2 + i] = (float)(1.0 / (double)f2);
     }
     __syncthreads();
-    if (threadIdx.x == 0) *t_dev = t0 + n_seg;
+    if (threadIdx.x == 0) *t_dev = t0 + t_advance;
 }
 
 // arenas are padded so that every tensor starts on a 64-element boundary: a float4 never straddles tensors
 __device__ __forceinline__ int adam_segment(int seg, int64_t e, int n_seg, const int64_t* __restrict__ seg_end) {
+    // (e already carries the offset of this launch's range inside the arena: seg_end holds arena offsets)
     if (e < seg_end[seg] && (seg == 0 || e >= seg_end[seg - 1])) return seg;
     int lo = 0, hi = n_seg - 1;
     while (lo < hi) {
@@ -106,7 +107,8 @@ __device__ __forceinline__ void adam_update4(float4& pv, const float4& gv, float
 template <bool BELIEF, int U>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, int n_seg,
-                                                   const int64_t* __restrict__ seg_end, const float* __restrict__ c1,
+                                                   const int64_t* __restrict__ seg_end, int64_t seg_base,
+                                                   const float* __restrict__ c1,
                                                    const float* __restrict__ c2, float neg_lr, float b1, float b2,
                                                    float omb1, float omb2, float eps) {
     LG_PDL_TRIGGER();
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * 256;
             if (i < nv) {
-                seg = adam_segment(seg, i * 4, n_seg, seg_end);
+                seg = adam_segment(seg, i * 4 + seg_base, n_seg, seg_end);
                 adam_update4<BELIEF>(pv[u], gv[u], mv[u], vv[u], c1[seg], c2[seg], c1[2 * n_seg + seg], c2[2 * n_seg + seg],
                                      neg_lr, b1, b2, omb1, omb2, eps);
                 reinterpret_cast<float4*>(p)[i] = pv[u];
@@ -156,7 +158,8 @@ int lg_sgd_step(void* param, const void* grad, void* delta, int64_t n, double lr
 }
 
 int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, int64_t n, int n_seg,
-                 const int64_t* seg_end_dev, int64_t* t_dev, double lr, double beta1, double beta2, double eps) {
+                 const int64_t* seg_end_dev, int64_t* t_dev, double lr, double beta1, double beta2, double eps,
+                 int64_t seg_base, int seg_offset, int t_advance) {
     LG_INIT();
     if (n == 0) return 0;
     LG_REQUIRE(n_seg >= 1, "lg_adam_step: need at least one segment");
@@ -166,7 +169,7 @@ int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, in
     if (!corr) return 1;
     float* seg_c1_dev = corr;
     float* seg_c2_dev = corr + n_seg;
-    adam_prep_kernel<<<1, 256, 0, stream()>>>(n_seg, t_dev, beta1, beta2, seg_c1_dev, seg_c2_dev);
+    adam_prep_kernel<<<1, 256, 0, stream()>>>(n_seg, t_dev, beta1, beta2, seg_c1_dev, seg_c2_dev, seg_offset, t_advance);
     count_launch();
     static const int U = getenv("LG_ADAM_U") ? atoi(getenv("LG_ADAM_U")) : 1;
     static const int bps = getenv("LG_ADAM_BPS") ? atoi(getenv("LG_ADAM_BPS")) : 8;
@@ -176,7 +179,8 @@ int lg_adam_step(int belief, void* param, const void* grad, void* m, void* v, in
     float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
 #define LG_ADAM(B_, U_)                                                                                          \
     adam_kernel<B_, U_><<<grid, 256, 0, stream()>>>((float*)param, (const float*)grad, (float*)m, (float*)v, n, n_seg, \
-                                                    seg_end_dev, seg_c1_dev, seg_c2_dev, (float)(-lr), b1, b2, omb1,   \
+                                                    seg_end_dev, seg_base, seg_c1_dev, seg_c2_dev, (float)(-lr), b1, b2,  \
+                                                    omb1,                                                              \
                                                     omb2, (float)eps)
     if (belief) {
         if (U == 1) LG_ADAM(true, 1); else if (U == 2) LG_ADAM(true, 2); else LG_ADAM(true, 4);

@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(256) red_cols(const T* __restrict__ x, T* __re
 constexpr int64_t kTicketSlots = 16384;
 // (one set per stream: reductions on the side stream may run concurrently with reductions on the main one)
 unsigned int* ticket_buffer() {
-    static unsigned int* bufs[2] = {nullptr, nullptr};
-    unsigned int*& buf = bufs[on_side_stream() ? 1 : 0];
+    static unsigned int* bufs[3] = {nullptr, nullptr, nullptr};
+    unsigned int*& buf = bufs[alt_stream_index()];
     if (!buf) {
         if (cudaMalloc(&buf, kTicketSlots * sizeof(unsigned int)) != cudaSuccess) {
             cudaGetLastError();

@@ -23,6 +23,10 @@ static cudaStream_t g_side = nullptr, g_cur = nullptr;
 static cudaEvent_t g_ev_side_fork = nullptr, g_ev_side_join = nullptr;
 static bool g_side_mode = false, g_side_pending = false;
 static std::vector<void*> g_side_deferred;   // blocks freed in side mode: reusable only after the join
+// lg_comm_compute_begin / end: kernels issued in between go to the collective stream, right behind the
+// all-reduce they depend on (per-bucket optimizer updates of the data-parallel wrapper)
+static bool g_comm_mode = false;
+static std::vector<void*> g_comm_deferred;   // blocks freed in that mode: reusable after lg_nccl_wait
 static int g_sms = 148;
 static std::atomic<uint64_t> g_launches{0};
 
@@ -34,7 +38,8 @@ int set_error(const char* fmt, ...) {
     return 1;
 }
 cudaStream_t stream() { return g_cur; }
-bool on_side_stream() { return g_side_mode; }
+bool on_side_stream() { return g_side_mode || g_comm_mode; }
+int alt_stream_index() { return g_comm_mode ? 2 : (g_side_mode ? 1 : 0); }
 cudaStream_t comm_stream() { return g_comm; }
 int sm_count() { return g_sms; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
@@ -123,8 +128,15 @@ bool capturing() { return g_capturing; }
 void* tmp_alloc(size_t nbytes) { return g_cache->get(nbytes ? nbytes : 1); }
 void tmp_free(void* p) {
     if (!p) return;
-    if (g_side_mode) g_side_deferred.push_back(p);
+    if (g_comm_mode) g_comm_deferred.push_back(p);
+    else if (g_side_mode) g_side_deferred.push_back(p);
     else g_cache->put(p);
+}
+
+// called once the compute stream has been ordered after the collective stream (lg_nccl_wait)
+void comm_release_deferred() {
+    for (void* p : g_comm_deferred) g_cache->put(p);
+    g_comm_deferred.clear();
 }
 
 // main stream waits for everything issued on the side stream so far; deferred blocks become reusable
@@ -261,11 +273,29 @@ int lg_alloc(size_t nbytes, void** ptr) {
 
 int lg_free(void* ptr) {
     if (!ptr || !g_cache) return 0;
+    if (g_comm_mode) {
+        g_comm_deferred.push_back(ptr);
+        return 0;
+    }
     if (g_side_mode) {
         g_side_deferred.push_back(ptr);
         return 0;
     }
     return g_cache->put(ptr);
+}
+
+int lg_comm_compute_begin(void) {
+    LG_INIT();
+    LG_REQUIRE(!g_side_mode && !g_comm_mode, "lg_comm_compute_begin: already on another stream");
+    g_cur = g_comm;
+    g_comm_mode = true;
+    return 0;
+}
+
+int lg_comm_compute_end(void) {
+    g_cur = g_stream;
+    g_comm_mode = false;
+    return 0;
 }
 
 // ---- side stream ---------------------------------------------------------------------------------
@@ -276,7 +306,7 @@ int lg_side_begin(void) {
     LG_INIT();
     static const bool off = getenv("LG_NO_SIDE_STREAM") != nullptr;
     if (off) return 0;
-    LG_REQUIRE(!g_side_mode, "lg_side_begin: already on the side stream");
+    LG_REQUIRE(!g_side_mode && !g_comm_mode, "lg_side_begin: already on another stream");
     LG_CUDA(cudaEventRecord(g_ev_side_fork, g_stream));
     LG_CUDA(cudaStreamWaitEvent(g_side, g_ev_side_fork, 0));
     g_cur = g_side;
@@ -415,6 +445,7 @@ int lg_graph_end(void** graph_exec, uint64_t* n_nodes) {
     // a forked side stream must rejoin the capturing stream before the capture can end
     g_cur = g_stream;
     g_side_mode = false;
+    g_comm_mode = false;
     if (side_join()) return 1;
     g_capturing = false;
     {

@@ -172,6 +172,11 @@ class Adam(Optimizer):
         return grad
 
     def _fused_step(self, a):
+        self._fused_step_range(a, 0, len(self.parameters), last=True)
+
+    def _fused_step_range(self, a, i0, i1, last):
+        """Update parameters i0 .. i1-1 (a contiguous window of the arenas).  The calls of one step may come in any
+        order; the one with ``last=True`` (issued last) advances the step counter for the whole step."""
         P = len(self.parameters)
         if self._m is None:
             self._m, self._v = a.state(), a.state()
@@ -179,12 +184,15 @@ class Adam(Optimizer):
             # a CUDA graph keeps counting when it is replayed
             self._t_dev = a.T.from_numpy(np.array([self.t], dtype=np.int64), requires_grad=False)
         seg = a.segments(self.parameters)
+        lo = a.offsets[i0]
+        hi = a.offsets[i1] if i1 < P else a.total
         # parameter i uses t = t_dev + i + 1 (the reference bumps t once per parameter); the kernel
         # derives the two bias corrections from t itself, so nothing is uploaded per step
-        a.rt.api.adam_step(self._belief, a.param_buf.ptr, a.grad_buf.ptr, self._m.ptr, self._v.ptr, a.total,
-                           P, seg.ptr, self._t_dev.ptr, float(self.lr), float(self.b1), float(self.b2),
-                           float(self.eps))
-        self.t += P
+        a.rt.api.adam_step(self._belief, a.param_buf.ptr + lo * 4, a.grad_buf.ptr + lo * 4, self._m.ptr + lo * 4,
+                           self._v.ptr + lo * 4, hi - lo, i1 - i0, seg.ptr + i0 * 8, self._t_dev.ptr, float(self.lr),
+                           float(self.b1), float(self.b2), float(self.eps), lo, i0, P if last else 0)
+        if last:
+            self.t += P
 
 
 class AdaBelief(Adam):

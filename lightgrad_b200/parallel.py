@@ -129,7 +129,23 @@ class DataParallel(object):
             p.fill(0.0)
             p += p.__class__.from_numpy(new.copy(), requires_grad=False)
 
-    def backward(self, loss, bucket_bytes=None):
+    def backward_and_step(self, loss, bucket_bytes=None):
+        """``backward`` + ``optimizer.step()`` with the optimizer pipelined behind the exchange: the update of a
+        bucket's parameters is queued on the communication stream right after that bucket's all-reduce, so only the
+        last bucket's exchange and update remain after backward instead of the whole optimizer pass.  Safe because
+        a bucket is exchanged only after every consumer of its parameters has run its backward."""
+        # Measured (2 GPUs, local batch 128): 30.56 ms pipelined vs 30.44 ms plain -- whatever runs on the
+        # communication stream competes with the persistent one-CTA-per-SM GEMMs of backward for the same SMs, so
+        # moving the optimizer there buys nothing today.  Off unless LG_DP_PIPELINED_STEP=1.
+        fused = getattr(self.optimizer, '_fused_step_range', None)
+        if self.world == 1 or not self._nccl or fused is None or os.environ.get('LG_DP_NO_OVERLAP') \
+                or not os.environ.get('LG_DP_PIPELINED_STEP'):
+            self.backward(loss, bucket_bytes)
+            self.optimizer.step()
+            return
+        self.backward(loss, bucket_bytes, _step_buckets=True)
+
+    def backward(self, loss, bucket_bytes=None, _step_buckets=False):
         """``loss.backward()`` with the gradient exchange overlapped: the flat gradient arena is cut into
         ~``bucket_bytes`` buckets of consecutive parameters; as soon as the walk has delivered the last
         contribution to every parameter of a bucket, its all-reduce is queued on the communication
@@ -161,11 +177,27 @@ class DataParallel(object):
         launched = [False] * len(self._buckets)
         api = a.rt.api
 
+        n_buckets = len(self._buckets)
+        first_param = [0] * n_buckets                      # bucket -> index of its first parameter
+        for i, b in enumerate(self._bucket_of):
+            if i == 0 or self._bucket_of[i - 1] != b:
+                first_param[b] = i
+        n_launched = [0]
+
         def launch(b):
-            lo, hi, _ = self._buckets[b]
+            lo, hi, count = self._buckets[b]
             launched[b] = True
+            n_launched[0] += 1
             api.nccl_fork()                                   # comm stream waits for the gradients written so far
             api.nccl_allreduce_f32(a.grad_buf.ptr + lo * 4, hi - lo, 1, 1)
+            if _step_buckets:
+                # the optimizer update of this bucket, behind its all-reduce on the communication stream
+                api.comm_compute_begin()
+                try:
+                    self.optimizer._fused_step_range(a, first_param[b], first_param[b] + count,
+                                                     last=n_launched[0] == n_buckets)
+                finally:
+                    api.comm_compute_end()
 
         def leaf_done(t):
             i = self._index.get(id(t))

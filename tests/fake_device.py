@@ -245,6 +245,10 @@ class FakeDevice(object):
 
     def gemm_sm_limit(self, n): pass
 
+    def comm_compute_begin(self): pass
+
+    def comm_compute_end(self): pass
+
     def side_begin(self): pass
 
     def side_end(self): pass
@@ -358,15 +362,16 @@ class FakeDevice(object):
             D[...] = delta
         P[...] += delta
 
-    def adam_step(self, belief, p, g, m, v, n, n_seg, seg_end, t_dev, lr, b1, b2, eps):
+    def adam_step(self, belief, p, g, m, v, n, n_seg, seg_end, t_dev, lr, b1, b2, eps, seg_base, seg_offset,
+                  t_advance):
         self.launches += 1
         tcount = _arr(t_dev, rt.I64, [1])
         t0 = int(tcount[0])
-        tcount[0] = t0 + n_seg
+        tcount[0] = t0 + t_advance
         P, G, M, V = (_arr(q, rt.F32, [n]) for q in (p, g, m, v))
         ends = _arr(seg_end, rt.I64, [n_seg])
-        seg = np.searchsorted(ends, np.arange(n), side='right')
-        t = (t0 + seg + 1).astype(np.float64)
+        seg = np.searchsorted(ends, np.arange(n) + seg_base, side='right')
+        t = (t0 + seg_offset + seg + 1).astype(np.float64)
         d1 = (1.0 - np.power(b1, t)).astype(np.float32)
         d2 = (1.0 - np.power(b2, t)).astype(np.float32)
         M[...] = np.float32(b1) * M + np.float32(1.0 - b1) * G

@@ -78,3 +78,50 @@ def test_shard_rows():
     from lightgrad_b200.parallel import shard_rows
     assert [shard_rows(256, r, 8) for r in (0, 7)] == [(0, 32), (224, 256)]
     assert shard_rows(256, 1, 2) == (128, 256)
+
+
+def test_pipelined_bucket_step_equals_plain_step(fake_device, monkeypatch):
+    """DataParallel.backward_and_step (per-bucket all-reduce + Adam behind it) against loss.backward();
+    optimizer.step() on the numpy stand-in of the device (its all-reduce is the identity): same parameters,
+    Adam state and step counter after several steps, for bucket sizes from one parameter to everything."""
+    import lightgrad_b200 as light
+    import lightgrad_b200.nn as nn
+    from lightgrad_b200 import CudaTensor, parallel
+    from examples import bert
+
+    monkeypatch.setenv('LG_DP_PIPELINED_STEP', '1')
+    cfg = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, vocab_size=50,
+               max_position_embeddings=16, type_vocab_size=2)
+    ids, labels = bert.synthetic_batch(2, 8, cfg['vocab_size'])
+
+    def build():
+        with nn.use_tensor(CudaTensor):
+            np.random.seed(3)
+            model = bert.BertForMaskedLM(**cfg)
+        return model, light.optim.Adam(model.parameters(), lr=1e-2)
+
+    def run(bucket_bytes):
+        model, opt = build()
+        dp = None
+        if bucket_bytes is not None:
+            dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm())
+            dp.world, dp._nccl = 2, True             # take the multi-GPU code path; the fake all-reduce is the identity
+        x = CudaTensor.from_numpy(ids, requires_grad=False)
+        y = CudaTensor.from_numpy(labels, requires_grad=False)
+        for _ in range(3):
+            loss = light.loss.cross_entropy(model(x).reshape(-1, cfg['vocab_size']), y)
+            opt.zero_grad()
+            if dp is None:
+                loss.backward()
+                opt.step()
+            else:
+                dp.backward_and_step(loss, bucket_bytes=bucket_bytes)
+        return [p.numpy() for p in model.parameters()], opt.t, loss.item()
+
+    want, t_want, loss_want = run(None)
+    for bucket_bytes in (1, 4096, 1 << 30):
+        got, t_got, loss_got = run(bucket_bytes)
+        assert t_got == t_want
+        assert loss_got == loss_want
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
