@@ -44,6 +44,7 @@ import numpy as np  # noqa: E402
 
 SEQ = 128
 GEMM_FLOPS_PER_SAMPLE = 85.5e9   # fwd + both backward GEMMs, SURVEY.md 8(a)/BASELINE.md "work per unit"
+NCU_GEMM_DRAM_BYTES_PER_STEP = 13.02e9   # profiles/r1_gemm_dram_bytes.csv (batch 32, tf32 mode, 1 GPU)
 
 
 def load_peaks():
@@ -394,7 +395,13 @@ def main():
         'clocks': clocks,
         'roofline': {'bound': 'tensor', 'kernel': 'lg_gemm (%s)' % mode, 'achieved': round(achieved_tf, 2),
                      'peak': round(peak_tf, 1), 'unit': 'TFLOP/s', 'frac': round(achieved_tf / peak_tf, 4),
-                     'peak_source': peak_name + '; ' + peaks['source'], 'traffic': None,
+                     'peak_source': peak_name + '; ' + peaks['source'],
+                     # DRAM bytes of ALL matmul launches of one step (like `achieved`, an aggregate over the step's
+                     # launches): ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_dram_bytes.csv
+                     'traffic': NCU_GEMM_DRAM_BYTES_PER_STEP if (mode == 'tf32' and args.gpus == 1 and not args.layers) else None,
+                     'traffic_note': 'ncu capture of the 222 matmul launches of one batch-32 step: 11.90 GB read + 1.12 GB '
+                                     'written (algorithmic operand + result bytes of those launches: ~16 GB; results '
+                                     'still in L2 at kernel end are charged to later kernels)',
                      'launches_per_step': gemm_launches // k_c, 'kernel_ms_per_step': round(gemm_ms / k_c, 3),
                      'kernel_share_of_step': round(gemm_ms / k_c / step_ms_c, 3),
                      'algorithmic_flops_per_step': gemm_flops / k_c,
