@@ -25,6 +25,14 @@ def rand(*shape):
     return CudaTensor.from_numpy(np.random.uniform(-1, 1, shape).astype(np.float32))
 
 
+def rand_pitched(rows, cols):
+    """(rows, cols) view of a buffer whose row pitch is a multiple of 32 floats (what the framework's own GEMM
+    results with an unaligned width look like, e.g. the 30522-wide logits)."""
+    ld = (cols + 31) // 32 * 32
+    full = rand(rows, ld)
+    return full if ld == cols else full._view((rows, cols), (ld, 1))
+
+
 def cases():
     # name, builder -> (callable issuing ONE launch on operand set i, flops per launch)
     def fwd(n_in, n_out):
@@ -32,13 +40,13 @@ def cases():
             X = [rand(R, n_in) for _ in range(sets)]
             W = [rand(n_out, n_in) for _ in range(sets)]
             b = rand(n_out)
-            O = [CudaTensor.empty((R, n_out)) for _ in range(sets)]
+            O = [rand_pitched(R, n_out) for _ in range(sets)]
             return (lambda i: _gemm(X[i], _swap_last(W[i]), out=O[i], bias=b)), 2.0 * R * n_in * n_out
         return make
 
     def dx(n_in, n_out):
         def make(sets):
-            G = [rand(R, n_out) for _ in range(sets)]
+            G = [rand_pitched(R, n_out) for _ in range(sets)]
             W = [rand(n_out, n_in) for _ in range(sets)]
             O = [CudaTensor.empty((R, n_in)) for _ in range(sets)]
             return (lambda i: _gemm(G[i], W[i], out=O[i])), 2.0 * R * n_in * n_out
@@ -46,7 +54,7 @@ def cases():
 
     def dw(n_in, n_out):
         def make(sets):
-            G = [rand(R, n_out) for _ in range(sets)]
+            G = [rand_pitched(R, n_out) for _ in range(sets)]
             X = [rand(R, n_in) for _ in range(sets)]
             O = [CudaTensor.zeros((n_out, n_in)) for _ in range(sets)]
             return (lambda i: _gemm(_swap_last(G[i]), X[i], out=O[i], accumulate=True)), 2.0 * R * n_in * n_out

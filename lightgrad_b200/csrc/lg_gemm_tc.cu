@@ -1173,19 +1173,32 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_sp
             if (splits < 1) splits = 1;
         }
         if (force_splits && allow_split) splits = force_splits < kblocks ? force_splits : kblocks;
-        int kper = (kblocks + splits - 1) / splits;
-        splits = (kblocks + kper - 1) / kper;
-        const int items = tiles * splits;
-        const int waves = (items + sms - 1) / sms;
-        const double util = (double)items / ((double)waves * sms);
+        // very long K (the decoder's dX, K = vocabulary): the reduce-add of the partials is negligible next to
+        // the main loop, so also try the split counts that fill 2 and 3 whole waves (96 tiles x 3 = 288 items on
+        // 148 SMs instead of 128 one-wave tiles)
+        int cand_splits[3] = {splits, splits, splits};
+        if (tiles < sms && allow_split && !force_splits && kblocks >= 512) {
+            cand_splits[1] = (2 * sms) / tiles;
+            cand_splits[2] = (3 * sms) / tiles;
+        }
         const double useful = ((double)M * N) / ((double)tm * BM * tn * bn);   // padding waste
         const double shape = bn == 256 ? 1.0 : (bn == 192 ? 0.95 : (bn == 128 ? 0.85 : 0.6));
-        const double split_cost = splits > 1 ? 0.92 : 1.0;
-        const double score = util * useful * shape * split_cost;
-        if (score > best_score) {
-            best_score = score;
-            best = Plan{bn, splits, tm, tn, kblocks, kper};
-            (void)tiles;
+        for (int ci = 0; ci < 3; ++ci) {
+            int sp = cand_splits[ci];
+            if (sp < 1) sp = 1;
+            if (sp > 16) sp = 16;
+            if (ci > 0 && (sp == cand_splits[0] || kblocks / sp < 64)) continue;
+            int kper = (kblocks + sp - 1) / sp;
+            sp = (kblocks + kper - 1) / kper;
+            const int items = tiles * sp;
+            const int waves = (items + sms - 1) / sms;
+            const double util = (double)items / ((double)waves * sms);
+            const double split_cost = sp > 1 ? 0.92 : 1.0;
+            const double score = util * useful * shape * split_cost;
+            if (score > best_score) {
+                best_score = score;
+                best = Plan{bn, sp, tm, tn, kblocks, kper};
+            }
         }
     }
     return best;
