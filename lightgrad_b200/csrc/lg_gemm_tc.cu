@@ -187,9 +187,38 @@ struct TcParams {
     long long aux_ld;
     long long aux_sb0, aux_sb1;   // its batch strides (epi_op 4; same batch dims as C)
     float epi_alpha;
+    // tail-wave split (plain one-problem GEMMs, splits == 1): the last `tiles % clusters` tiles, which would run as
+    // a mostly empty extra wave, are each cut into tail_splits K-ranges whose partials meet by reduce-add
+    int items_per_batch;      // work items of one problem: tail_first whole tiles + (tiles - tail_first) * tail_splits
+    int tail_first, tail_splits, tail_kper;
     int kcat;                 // operand pairs concatenated along K into ONE result: C = sum_g A_g B_g (1-CTA kernel)
     const float* bias[LG_MAX_GROUPS];
 };
+
+// work item -> (tile, K-range); `wi` counts inside one problem of one batch
+struct TcItem {
+    int tile, split, kb0, kb1, partial;   // partial: the result is one of several K-range partials of its tile
+};
+__device__ __forceinline__ TcItem decode_item(const TcParams& p, int wi) {
+    TcItem it;
+    int kper;
+    if (wi >= p.tail_first && p.tail_splits > 1) {
+        const int r = wi - p.tail_first;
+        it.tile = p.tail_first + r / p.tail_splits;
+        it.split = r - (r / p.tail_splits) * p.tail_splits;
+        kper = p.tail_kper;
+        it.partial = 1;
+    } else {
+        it.tile = wi / p.splits;
+        it.split = wi - it.tile * p.splits;
+        kper = p.kblocks_per_split;
+        it.partial = p.splits > 1;
+    }
+    it.kb0 = it.split * kper;
+    it.kb1 = it.kb0 + kper;
+    if (it.kb1 > p.kblocks_total) it.kb1 = p.kblocks_total;
+    return it;
+}
 
 struct TcMaps {
     CUtensorMap a[LG_MAX_GROUPS], b[LG_MAX_GROUPS], c[LG_MAX_GROUPS];
@@ -482,7 +511,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // p.tiles_m counts groups of CL vertically adjacent tiles; work items are distributed over clusters
-    const int items_per_batch = p.tiles_m * p.tiles_n * p.splits;
+    const int items_per_batch = p.items_per_batch;
     // grouped launch: `groups` problems of identical shape (own operand / result maps), enumerated group-major
     const int items_per_group = items_per_batch * p.batches;
     const int work_items = items_per_group * p.groups;
@@ -528,11 +557,9 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
                 const int grp = w / items_per_group, wg = w - grp * items_per_group;
                 const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
                 const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
-                const int tile = wi / p.splits, split = wi - tile * p.splits;
+                const TcItem item = decode_item(p, wi);
+                const int tile = item.tile, kb0 = item.kb0, kb1 = item.kb1;
                 const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
-                const int kb0 = split * p.kblocks_per_split;
-                int kb1 = kb0 + p.kblocks_per_split;
-                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
                 const int kspan = kb1 - kb0;
                 for (int it = 0; it < kspan * p.kcat; ++it) {
                     // K-concatenated operands: chunk kc supplies k-blocks kb0..kb1 of its own (A, B) pair
@@ -596,10 +623,8 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int w = cluster_id; w < work_items; w += n_clusters) {
-                const int split = ((w % items_per_group) % items_per_batch) % p.splits;
-                const int kb0 = split * p.kblocks_per_split;
-                int kb1 = kb0 + p.kblocks_per_split;
-                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                const TcItem item = decode_item(p, (w % items_per_group) % items_per_batch);
+                const int kb0 = item.kb0, kb1 = item.kb1;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -669,7 +694,8 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             const float* bias = p.bias[grp];
             const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
-            const int tile = wi / p.splits, split = wi - tile * p.splits;
+            const TcItem item = decode_item(p, wi);
+            const int tile = item.tile, split = item.split;
             const int m0 = ((tile % p.tiles_m) * CL + crank) * BM, n0 = (tile / p.tiles_m) * BN;
             EpiTile t;
             t.map_c = map_c;
@@ -684,7 +710,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
             t.N = p.N;
             t.bc1 = bc1;
             t.bc0 = bc0;
-            t.reduce_out = p.reduce_out;
+            t.reduce_out = p.reduce_out | item.partial;
             t.rows_live = t.row0 < p.M;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
             // operands the epilogue reads from global memory, fetched before the wait for the accumulator:
@@ -770,7 +796,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items_per_batch = p.tiles_m * p.tiles_n * p.splits;   // p.tiles_m counts 256-row tile pairs
+    const int items_per_batch = p.items_per_batch;   // p.tiles_m counts 256-row tile pairs
     const int work_items = items_per_batch * p.batches;
     const int crank = (int)cluster_ctarank();
     const bool leader = crank == 0;
@@ -813,12 +839,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
             for (int w = cluster_id; w < work_items; w += n_clusters) {
                 const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
                 const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
-                const int tile = wi / p.splits, split = wi - tile * p.splits;
+                const TcItem item = decode_item(p, wi);
+                const int tile = item.tile;
                 const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM;
                 const int n0 = (tile / p.tiles_m) * BN + crank * HB;     // this CTA's half of the B tile
-                const int kb0 = split * p.kblocks_per_split;
-                int kb1 = kb0 + p.kblocks_per_split;
-                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                const int kb0 = item.kb0, kb1 = item.kb1;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * STAGE_BYTES;
@@ -860,10 +885,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int w = cluster_id; w < work_items; w += n_clusters) {
-                const int split = (w % items_per_batch) % p.splits;
-                const int kb0 = split * p.kblocks_per_split;
-                int kb1 = kb0 + p.kblocks_per_split;
-                if (kb1 > p.kblocks_total) kb1 = p.kblocks_total;
+                const TcItem item = decode_item(p, w % items_per_batch);
+                const int kb0 = item.kb0, kb1 = item.kb1;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -920,7 +943,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
         for (int w = cluster_id; w < work_items; w += n_clusters) {
             const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
-            const int tile = wi / p.splits, split = wi - tile * p.splits;
+            const TcItem item = decode_item(p, wi);
+            const int tile = item.tile, split = item.split;
             const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM, n0 = (tile / p.tiles_m) * BN;
             EpiTile t;
             t.map_c = &map_c;
@@ -933,7 +957,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
             t.N = p.N;
             t.bc1 = bc1;
             t.bc0 = bc0;
-            t.reduce_out = p.reduce_out;
+            t.reduce_out = p.reduce_out | item.partial;
             t.rows_live = t.row0 < p.M;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
             float hfirst[32];
@@ -1151,7 +1175,7 @@ struct Plan {
     int bn, splits, tiles_m, tiles_n, kblocks, kper;
 };
 
-Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split) {
+Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split, bool tail_ok = false) {
     const int sms = gemm_sms();
     const int kblocks = (int)((K + BK - 1) / BK);
     Plan best{};
@@ -1192,7 +1216,20 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_sp
             sp = (kblocks + kper - 1) / kper;
             const int items = tiles * sp;
             const int waves = (items + sms - 1) / sms;
-            const double util = (double)items / ((double)waves * sms);
+            double util = (double)items / ((double)waves * sms);
+            if (tail_ok && sp == 1 && tiles > sms) {
+                // the launch code cuts the tiles of a mostly idle last wave into K-ranges (tail-wave split):
+                // that wave then costs 1/ranges of a full one
+                const bool pair = tiles >= 2 * sms && tm >= 2;
+                const int clusters = pair ? sms / 2 : sms;
+                const int items_c = pair ? ((tm + 1) / 2) * tn : tiles;
+                const int tail = items_c % clusters;
+                int ts = tail > 0 ? clusters / tail : 1;
+                if (ts > 4) ts = 4;
+                while (ts > 1 && kblocks / ts < 16) --ts;
+                // (0.94: the cut tiles pay a zero-fill and reduce-add stores)
+                if (ts > 1) util = 0.94 * (double)items_c / (((double)(items_c / clusters) + 1.0 / ts) * clusters);
+            }
             const double split_cost = sp > 1 ? 0.92 : 1.0;
             const double score = util * useful * shape * split_cost;
             if (score > best_score) {
@@ -1263,7 +1300,8 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int n_problems = same_c ? 1 : groups;
     // split-K partials meet in C by reduce-add: C must be zeroed first (done below for one plain matrix) or
     // already hold the value being accumulated into
-    Plan pl = choose_plan(M, N, K, batches * n_problems, !epi_op && (accumulate || batches * n_problems == 1));
+    Plan pl = choose_plan(M, N, K, batches * n_problems, !epi_op && (accumulate || batches * n_problems == 1),
+                          !epi_op && n_problems == 1 && batches == 1 && !same_c);
     if (epi_op >= 3) {
         // the whole row must live in one tile
         const int bn = N <= 64 ? 64 : 128;
@@ -1334,10 +1372,37 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
             LG_CUDA(cudaMemset2DAsync(c[0], (size_t)d->sc_m * 4, 0, (size_t)N * 4, (size_t)M, stream()));
         }
     }
-    const int64_t items64 = (int64_t)p.tiles_m * pl.tiles_n * pl.splits * batches * n_problems;   // cluster work items
+    const int max_clusters = gemm_sms() / cl > 0 ? gemm_sms() / cl : 1;
+    // tail-wave split: tiles % clusters tiles would occupy a mostly idle extra wave; when at least two K-ranges
+    // of each fit into that wave, cut them up (partials meet by reduce-add in a zeroed / accumulating C)
+    int64_t per_batch = (int64_t)p.tiles_m * pl.tiles_n * pl.splits;
+    p.tail_first = (int)per_batch;
+    p.tail_splits = 1;
+    p.tail_kper = pl.kper;
+    static const bool tail_off = getenv("LG_GEMM_NO_TAIL_SPLIT") != nullptr;
+    if (!tail_off && pl.splits == 1 && n_problems == 1 && batches == 1 && !epi_op && p.kcat == 1 &&
+        per_batch > max_clusters) {
+        const int tail = (int)(per_batch % max_clusters);
+        int ts = tail > 0 ? max_clusters / tail : 1;
+        if (ts > 4) ts = 4;
+        while (ts > 1 && pl.kblocks / ts < 16) --ts;          // >= 16 k-blocks (512 of K) per range
+        if (ts > 1) {
+            p.tail_first = (int)per_batch - tail;
+            p.tail_kper = (pl.kblocks + ts - 1) / ts;
+            p.tail_splits = (pl.kblocks + p.tail_kper - 1) / p.tail_kper;
+            per_batch = p.tail_first + (int64_t)tail * p.tail_splits;
+            if (!accumulate) {
+                // zero the tile columns the cut tiles live in (whole tiles there overwrite the zeros)
+                const int64_t col0 = (int64_t)(p.tail_first / p.tiles_m) * pl.bn;
+                LG_CUDA(cudaMemset2DAsync((float*)c[0] + col0, (size_t)d->sc_m * 4, 0, (size_t)(N - col0) * 4, (size_t)M,
+                                          stream()));
+            }
+        }
+    }
+    p.items_per_batch = (int)per_batch;
+    const int64_t items64 = per_batch * batches * n_problems;   // cluster work items
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
-    const int max_clusters = gemm_sms() / cl > 0 ? gemm_sms() / cl : 1;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
     if (pair_mma) {
         switch (pl.bn) {
