@@ -1221,7 +1221,7 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_sp
                 // the launch code cuts the tiles of a mostly idle last wave into K-ranges (tail-wave split):
                 // that wave then costs 1/ranges of a full one
                 const bool pair = tiles >= 2 * sms && tm >= 2;
-                const int clusters = pair ? sms / 2 : sms;
+                const int clusters = pair ? (sms / 2 > 0 ? sms / 2 : 1) : sms;
                 const int items_c = pair ? ((tm + 1) / 2) * tn : tiles;
                 const int tail = items_c % clusters;
                 int ts = tail > 0 ? clusters / tail : 1;
