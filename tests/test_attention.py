@@ -4,7 +4,6 @@ The node replaces BertSelfAttention.forward of the reference (examples/bert.py:6
 below spells that forward with the reference's own operators on the CPU tensor, so output and every
 gradient are compared op-for-op.  Exact mode: <= 1e-5 (fp32 matmul bound); tf32 mode: <= 5e-3.
 """
-import ctypes as C
 import math
 import numpy as np
 import pytest
