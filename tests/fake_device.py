@@ -95,6 +95,9 @@ class FakeDevice(object):
 
     # ---- runtime
     def init(self, device): pass
+    def device_count(self, ref): ref._obj.value = 1
+    def device(self, ref): ref._obj.value = 0
+    def host_free(self, p): pass
     def sync(self): pass
     def empty_cache(self): pass
     def profiler_range(self, start): pass
@@ -135,6 +138,7 @@ class FakeDevice(object):
         C.memset(int(dst), int(byte), int(n))
 
     def event_create(self, ref): ref._obj.value = 1
+    def event_destroy(self, h): pass
     def event_record(self, h): pass
     def event_sync(self, h): pass
     def event_elapsed_ms(self, a, b, ref): ref._obj.value = 0.0
