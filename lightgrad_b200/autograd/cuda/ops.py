@@ -877,6 +877,7 @@ class linear(Function):
                                           g2._strides[0], 1.0, 1)
             return (dx, Function.ACCUMULATED, Function.ACCUMULATED) if has_bias else (dx, Function.ACCUMULATED)
         if wg is not None:
+            rt.side_join_if_written(wg)       # a weight shared with another layer may have side-stream writes pending
             _gemm(_swap_last(g2), x2, out=wg, accumulate=True)
             dw = Function.ACCUMULATED
         else:

@@ -121,7 +121,11 @@ class _Checked(object):
 
     def __call__(self, *args):
         if self.fn(*args):
-            raise RuntimeError("%s: %s" % (self.name, _lib.lg_last_error().decode()))
+            msg = _lib.lg_last_error().decode()
+            if msg.startswith('IndexError:'):
+                # an out-of-range index / label met by a kernel, reported by the synchronisation that followed it
+                raise IndexError(msg[len('IndexError:'):].strip())
+            raise RuntimeError("%s: %s" % (self.name, msg))
 
 
 class _Api(object):

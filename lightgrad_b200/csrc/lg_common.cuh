@@ -28,6 +28,10 @@ int sm_count();
 void count_launch(int n = 1);
 int ensure_init();
 bool capturing();     // a whole-step CUDA graph capture is in progress on the compute stream
+// Device-side error word (host-mapped, so stable under graph replay): kernels that meet an out-of-range index or
+// label store a code there instead of reading out of bounds; the next lg_sync / lg_memcpy_d2h reports it once.
+enum { LG_DEVERR_INDEX = 1, LG_DEVERR_LABEL = 2 };
+unsigned int* error_flag();
 
 #define LG_CUDA(expr)                                                                         \
     do {                                                                                      \

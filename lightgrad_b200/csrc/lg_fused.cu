@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 template <typename T, typename L>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, int64_t ld,
                                                      const L* __restrict__ labels, T* __restrict__ loss_rows,
-                                                     T* __restrict__ lse, int64_t rows, int64_t cols) {
+                                                     T* __restrict__ lse, int64_t rows, int64_t cols,
+                                                     unsigned int* __restrict__ errflag) {
     LG_PDL_TRIGGER();
     __shared__ T sm[8];
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -161,7 +162,14 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, in
             int64_t lab = (int64_t)labels[row];
             if (lab < 0) lab += cols;
             lse[row] = l;
-            loss_rows[row] = l - p[lab];
+            if (lab >= 0 && lab < cols) {
+                loss_rows[row] = l - p[lab];
+            } else {
+                // numpy raises IndexError (loss.py:16 indexes with the labels): no out-of-bounds read here; the
+                // row's loss is NaN and the error is reported by the next synchronisation
+                loss_rows[row] = T(NAN);
+                *errflag = LG_DEVERR_LABEL;
+            }
         }
     }
 }
@@ -180,6 +188,11 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, in
         const T l = lse[row];
         int64_t lab = (int64_t)labels[row];
         if (lab < 0) lab += cols;
+        if (lab < 0 || lab >= cols) {
+            // label out of range (flagged by the forward kernel): this row contributes no gradient
+            for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) q[j] = T(0);
+            continue;
+        }
         constexpr int V = 16 / sizeof(T);
         int64_t nv = 0;
         if ((((uintptr_t)p | (uintptr_t)q) & 15) == 0) {
@@ -618,7 +631,8 @@ template <typename T, typename L>
 int ce_fwd(const void* x, int64_t ld, const void* labels, void* loss_rows, void* lse, int64_t rows, int64_t cols) {
     int64_t cap = (int64_t)sm_count() * 8;
     ce_fwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>((const T*)x, ld, (const L*)labels,
-                                                                              (T*)loss_rows, (T*)lse, rows, cols);
+                                                                              (T*)loss_rows, (T*)lse, rows, cols,
+                                                                              error_flag());
     LG_CHECK_LAUNCH();
     return 0;
 }

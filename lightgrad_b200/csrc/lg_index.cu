@@ -29,7 +29,7 @@ template <typename W>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const W* __restrict__ src, int64_t n_src_rows,
                                                           int64_t row_stride_w, const void* __restrict__ idx,
                                                           int idx_dt, int64_t n_idx, int64_t row_words,
-                                                          W* __restrict__ out) {
+                                                          W* __restrict__ out, unsigned int* __restrict__ errflag) {
     LG_PDL_TRIGGER();
     const int64_t total = n_idx * row_words;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
@@ -39,7 +39,11 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const W* __restrict__ 
         if (r < 0) r += n_src_rows;
         W v;
         if (r >= 0 && r < n_src_rows) v = src[r * row_stride_w + j];
-        else memset(&v, 0, sizeof(W));
+        else {
+            // numpy raises IndexError here; the row is zero-filled and the error surfaces at the next sync
+            memset(&v, 0, sizeof(W));
+            if (j == 0) *errflag = LG_DEVERR_INDEX;
+        }
         out[w] = v;
     }
 }
@@ -48,7 +52,8 @@ template <typename W>
 __global__ void __launch_bounds__(256) scatter_set_rows_kernel(W* __restrict__ dst, int64_t n_dst_rows,
                                                                int64_t row_stride_w, const void* __restrict__ idx,
                                                                int idx_dt, int64_t n_idx, int64_t row_words,
-                                                               const W* __restrict__ src, W value) {
+                                                               const W* __restrict__ src, W value,
+                                                               unsigned int* __restrict__ errflag) {
     LG_PDL_TRIGGER();
     const int64_t total = n_idx * row_words;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
@@ -57,6 +62,7 @@ __global__ void __launch_bounds__(256) scatter_set_rows_kernel(W* __restrict__ d
         int64_t r = fetch_index(idx, idx_dt, i);
         if (r < 0) r += n_dst_rows;
         if (r >= 0 && r < n_dst_rows) dst[r * row_stride_w + j] = src ? src[w] : value;
+        else if (j == 0) *errflag = LG_DEVERR_INDEX;
     }
 }
 
@@ -64,7 +70,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(T* __restrict__ dst, int64_t n_dst_rows,
                                                                int64_t row_stride, const void* __restrict__ idx,
                                                                int idx_dt, int64_t n_idx, int64_t row_len,
-                                                               const T* __restrict__ src) {
+                                                               const T* __restrict__ src,
+                                                               unsigned int* __restrict__ errflag) {
     LG_PDL_TRIGGER();
     const int64_t total = n_idx * row_len;
     for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total;
@@ -73,6 +80,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(T* __restrict__ d
         int64_t r = fetch_index(idx, idx_dt, i);
         if (r < 0) r += n_dst_rows;
         if (r >= 0 && r < n_dst_rows) atomicAdd(dst + r * row_stride + j, src[w]);
+        else if (j == 0) *errflag = LG_DEVERR_INDEX;
     }
 }
 
@@ -83,17 +91,22 @@ struct LinArgs {
     int64_t size[4], stride[4];
 };
 
-__global__ void __launch_bounds__(256) linearize_kernel(LinArgs a, int64_t n, int64_t* __restrict__ lin) {
+__global__ void __launch_bounds__(256) linearize_kernel(LinArgs a, int64_t n, int64_t* __restrict__ lin,
+                                                        unsigned int* __restrict__ errflag) {
     LG_PDL_TRIGGER();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t off = 0;
+        bool bad = false;
         for (int k = 0; k < a.n_arrays; ++k) {
             int64_t r = fetch_index(a.idx[k], a.dt[k], i);
             if (r < 0) r += a.size[k];
-            if (r < 0 || r >= a.size[k]) { off = INT64_MIN / 2; }
+            if (r < 0 || r >= a.size[k]) bad = true;
             off += r * a.stride[k];
         }
-        lin[i] = off;  // hugely negative when any index was out of range -> consumers skip the row
+        // an out-of-range entry raises IndexError at the next sync; INT64_MIN makes the consumers skip that row
+        // (they are handed element offsets with a row count of 2^62, so it stays negative after their wrap test)
+        if (bad) *errflag = LG_DEVERR_INDEX;
+        lin[i] = bad ? INT64_MIN : off;
     }
 }
 
@@ -116,7 +129,7 @@ int lg_gather_rows(int dtype, int idx_dtype, const void* src, int64_t n_src_rows
     grid = grid_for(n_idx * (row_bytes / (int64_t)sizeof(W)), 256, 8);                                     \
     gather_rows_kernel<W><<<grid, 256, 0, stream()>>>((const W*)src, n_src_rows,                           \
                                                       stride_bytes / (int64_t)sizeof(W), idx, idx_dtype,  \
-                                                      n_idx, row_bytes / (int64_t)sizeof(W), (W*)out)
+                                                      n_idx, row_bytes / (int64_t)sizeof(W), (W*)out, error_flag())
     if (row_bytes % 16 == 0 && stride_bytes % 16 == 0 && aligned16(src) && aligned16(out)) { GO(uint4); }
     else if (es == 8) { GO(uint64_t); }
     else if (es == 4) { GO(uint32_t); }
@@ -135,7 +148,7 @@ int lg_scatter_set_rows(int dtype, int idx_dtype, void* dst, int64_t n_dst_rows,
     int grid = grid_for(n_idx * row_len, 256, 8);
 #define GO(W, VAL)                                                                                         \
     scatter_set_rows_kernel<W><<<grid, 256, 0, stream()>>>((W*)dst, n_dst_rows, row_stride, idx, idx_dtype, \
-                                                           n_idx, row_len, (const W*)src, VAL)
+                                                           n_idx, row_len, (const W*)src, VAL, error_flag())
     switch (dtype) {
         case LG_F32: GO(float, (float)value); break;
         case LG_F64: GO(double, value); break;
@@ -159,10 +172,10 @@ int lg_scatter_add_rows(int dtype, int idx_dtype, void* dst, int64_t n_dst_rows,
     int grid = grid_for(n_idx * row_len, 256, 8);
     if (dtype == LG_F32)
         scatter_add_rows_kernel<float><<<grid, 256, 0, stream()>>>((float*)dst, n_dst_rows, row_stride, idx,
-                                                                   idx_dtype, n_idx, row_len, (const float*)src);
+                                                                   idx_dtype, n_idx, row_len, (const float*)src, error_flag());
     else if (dtype == LG_F64)
         scatter_add_rows_kernel<double><<<grid, 256, 0, stream()>>>((double*)dst, n_dst_rows, row_stride, idx,
-                                                                    idx_dtype, n_idx, row_len, (const double*)src);
+                                                                    idx_dtype, n_idx, row_len, (const double*)src, error_flag());
     else
         return set_error("lg_scatter_add_rows: unsupported dtype %d", dtype);
     LG_CHECK_LAUNCH();
@@ -184,7 +197,7 @@ int lg_index_linearize(int n_arrays, const void* const* idx, const int* idx_dtyp
         a.stride[k] = dim_strides[k];
     }
     if (n == 0) return 0;
-    linearize_kernel<<<grid_for(n, 256, 8), 256, 0, stream()>>>(a, n, lin);
+    linearize_kernel<<<grid_for(n, 256, 8), 256, 0, stream()>>>(a, n, lin, error_flag());
     LG_CHECK_LAUNCH();
     return 0;
 }

@@ -28,6 +28,8 @@ static std::vector<void*> g_side_deferred;   // blocks freed in side mode: reusa
 static bool g_comm_mode = false;
 static std::vector<void*> g_comm_deferred;   // blocks freed in that mode: reusable after lg_nccl_wait
 static int g_sms = 148;
+static unsigned int* g_errflag_host = nullptr;   // pinned + mapped: kernels store LG_DEVERR_* codes here
+static unsigned int* g_errflag_dev = nullptr;
 static std::atomic<uint64_t> g_launches{0};
 
 int set_error(const char* fmt, ...) {
@@ -38,6 +40,19 @@ int set_error(const char* fmt, ...) {
     return 1;
 }
 cudaStream_t stream() { return g_cur; }
+unsigned int* error_flag() { return g_errflag_dev; }
+// after a synchronisation: report (once) what a kernel flagged since the last check
+static int check_device_error() {
+    if (!g_errflag_host) return 0;
+    const unsigned int code = *(volatile unsigned int*)g_errflag_host;
+    if (!code) return 0;
+    *(volatile unsigned int*)g_errflag_host = 0;
+    if (code == LG_DEVERR_LABEL)
+        return set_error("IndexError: a cross-entropy label is out of range for the number of classes "
+                         "(that row's loss is NaN and its gradient zero)");
+    return set_error("IndexError: an index array holds an entry that is out of bounds for the indexed axis "
+                     "(gathered rows were zero-filled, scattered rows skipped)");
+}
 bool on_side_stream() { return g_side_mode || g_comm_mode; }
 int alt_stream_index() { return g_comm_mode ? 2 : (g_side_mode ? 1 : 0); }
 cudaStream_t comm_stream() { return g_comm; }
@@ -188,6 +203,9 @@ static int do_init(int device) {
     LG_CUDA(cudaEventCreateWithFlags(&g_ev_side_fork, cudaEventDisableTiming));
     LG_CUDA(cudaEventCreateWithFlags(&g_ev_side_join, cudaEventDisableTiming));
     g_cur = g_stream;
+    LG_CUDA(cudaHostAlloc((void**)&g_errflag_host, sizeof(unsigned int), cudaHostAllocMapped));
+    *g_errflag_host = 0;
+    LG_CUDA(cudaHostGetDevicePointer((void**)&g_errflag_dev, g_errflag_host, 0));
     g_cache = new Cache();
     g_device = device;
     return 0;
@@ -260,7 +278,7 @@ int lg_sync(void) {
     if (side_join()) return 1;
     LG_CUDA(cudaStreamSynchronize(g_stream));
     LG_CUDA(cudaStreamSynchronize(g_comm));
-    return 0;
+    return check_device_error();
 }
 
 int lg_alloc(size_t nbytes, void** ptr) {
@@ -361,20 +379,20 @@ int lg_memcpy_d2h(void* dst, const void* src, size_t nbytes) {
     if (side_join()) return 1;
     if (nbytes) LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
     LG_CUDA(cudaStreamSynchronize(g_stream));
-    return 0;
+    return check_device_error();
 }
 
 int lg_memcpy_d2d(void* dst, const void* src, size_t nbytes) {
     LG_INIT();
     if (nbytes == 0) return 0;
-    LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, g_stream));
+    LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, g_cur));
     return 0;
 }
 
 int lg_memset(void* dst, int byte, size_t nbytes) {
     LG_INIT();
     if (nbytes == 0) return 0;
-    LG_CUDA(cudaMemsetAsync(dst, byte, nbytes, g_stream));
+    LG_CUDA(cudaMemsetAsync(dst, byte, nbytes, g_cur));
     return 0;
 }
 
@@ -473,6 +491,7 @@ int lg_graph_abort(void) {
     if (!g_capturing) return 0;
     g_cur = g_stream;
     g_side_mode = false;
+    g_comm_mode = false;
     side_join();
     g_capturing = false;
     g_cache->cur_pool = 0;

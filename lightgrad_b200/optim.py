@@ -99,6 +99,13 @@ class Optimizer(object):
         self.parameters = tuple(parameters)
         assert all(isinstance(p, AbstractTensor) for p in self.parameters)
         want = _can_fuse(self.parameters) if fused is None else fused
+        if want and len(set(id(p) for p in self.parameters)) != len(self.parameters):
+            # a tensor listed twice (tied weights) would get two arena slots, one of them orphaned.  The
+            # reference's loop updates such a tensor twice per step, each time with its own m / v / t
+            # (optim.py:10-13); only the generic per-parameter path reproduces that, so it is used here.
+            if fused:
+                raise ValueError("fused optimizer: every parameter must be listed once (tied weights: use fused=False)")
+            want = False
         self.arena = _Arena(self.parameters) if want else None
 
     def zero_grad(self):
@@ -160,6 +167,23 @@ class Adam(Optimizer):
         self.m = [0] * len(self.parameters)
         self.v = [0] * len(self.parameters)
         self._m = self._v = None
+        if self.arena is not None:
+            self._init_state(self.arena)
+
+    def _init_state(self, a):
+        # allocated and zeroed up front, on the compute stream: a per-bucket update issued on the collective stream
+        # (DataParallel.backward_and_step) must never be the one that creates -- and memsets -- this state
+        self._m, self._v = a.state(), a.state()
+        # the step counter lives on the device (and is advanced there) so that a step captured into
+        # a CUDA graph keeps counting when it is replayed
+        self._t_dev = a.T.from_numpy(np.array([self.t], dtype=np.int64), requires_grad=False)
+
+    def steps_taken(self):
+        """Parameter updates performed so far (``t`` of the reference), read from the device counter when the
+        fused path keeps it there -- the host-side ``self.t`` does not advance while a captured step is replayed."""
+        if self._m is not None:
+            return int(self._t_dev.numpy()[0])
+        return self.t
 
     def compute_delta(self, grad, i):
         self.t += 1
@@ -179,10 +203,7 @@ class Adam(Optimizer):
         order; the one with ``last=True`` (issued last) advances the step counter for the whole step."""
         P = len(self.parameters)
         if self._m is None:
-            self._m, self._v = a.state(), a.state()
-            # the step counter lives on the device (and is advanced there) so that a step captured into
-            # a CUDA graph keeps counting when it is replayed
-            self._t_dev = a.T.from_numpy(np.array([self.t], dtype=np.int64), requires_grad=False)
+            self._init_state(a)
         seg = a.segments(self.parameters)
         lo = a.offsets[i0]
         hi = a.offsets[i1] if i1 < P else a.total
