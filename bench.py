@@ -5,16 +5,22 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU tensor path (oracle port)
 
 A "step" is one pass of the hot path over one batch of synthetic tokens: forward, fused cross
-entropy, backward (topological walk), [N>1: one NCCL averaging all-reduce of the flat gradient
-arena], Adam update.  Workloads (BASELINE.json configs[3] / configs[4]):
+entropy, backward (topological walk), [N>1: gradient exchange over NVLink], Adam update.
+Workloads (BASELINE.json configs[3] / configs[4]):
     N = 1   BERT-base (12L, d=768, seq 128), batch 32, random-init weights, synthetic tokens
-    N > 1   same model, global batch 256 sharded by rows over the N ranks
+    N > 1   same model, 32 samples PER GPU (global batch 32 N, rows sharded over the ranks): weak scaling
+            against the N = 1 line at every N; at N = 8 this is exactly configs[4] (global batch 256).
+            --global-batch 256 runs configs[4] at N = 2 / 4 as written; the default N = 2 / 4 lines
+            carry that measurement too, in `config5_global_batch_256`.
 One JSON line is printed by rank 0:
     value      samples/s, whole job, inputs resident in HBM before the timed region (CUDA events)
     e2e        the same step driven through the public API with the step's token ids / labels copied
                from pinned host memory and the loss read back to the host EVERY step
     roofline   the dominant kernel (matmul): algorithmic flops / summed CUDA-event kernel time
     cpu_baseline  the oracle port of the reference CPU tensor on this box's host cores (bounded sample)
+    ops        N = 1 only: BASELINE.json configs 1-3 (MNIST MLP steps/s, elementwise / reduction GB/s, matmul
+               TFLOP/s per mode) measured after the timed region, each next to the CPU tensor's arithmetic
+    modes      N = 1 only: the same BERT step in the other matmul modes (exact fp32, tf32, bf16)
 """
 import argparse
 import json
@@ -26,6 +32,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the CPU arm uses every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
+    # OpenBLAS single-threaded; this has to happen before numpy is imported
+    for _k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_k] = str(os.cpu_count() or 1)
 # stdout carries exactly one JSON line.  Libraries write there behind python's back (NCCL prints its version
 # banner to fd 1 whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and the JSON
 # line goes to a private duplicate of the original stdout.
@@ -44,7 +55,12 @@ import numpy as np  # noqa: E402
 
 SEQ = 128
 GEMM_FLOPS_PER_SAMPLE = 85.5e9   # fwd + both backward GEMMs, SURVEY.md 8(a)/BASELINE.md "work per unit"
-NCU_GEMM_DRAM_BYTES_PER_STEP = 13.02e9   # profiles/r1_gemm_dram_bytes.csv (batch 32, tf32 mode, 1 GPU)
+# ncu dram__bytes_read.sum + dram__bytes_write.sum over the matmul launches of one batch-32 step on 1 GPU, per mode
+NCU_GEMM_DRAM_BYTES_PER_STEP = {
+    'tf32': (13.02e9, 'profiles/r1_gemm_dram_bytes.csv: 222 matmul launches of one batch-32 step, 11.90 GB read + '
+                      '1.12 GB written (algorithmic operand + result bytes of those launches: ~16 GB; results still '
+                      'in L2 at kernel end are charged to later kernels)'),
+}
 
 
 def load_peaks():
@@ -163,54 +179,94 @@ def cpu_reference_leg(steps, warmup, sample_batch, budget_s=150.0):
             'ms_per_step': per * 1e3, 'steps_timed': len(times), 'loss': float(loss.item())}
 
 
-def main():
+# matmul mode of the headline line when --mode auto: the fastest tensor-core mode whose end-to-end gradients are
+# held to the north star's 5e-3 by the -m gpu parity tests (tests/test_full_size.py)
+DEFAULT_TC_MODE = os.environ.get('LG_BENCH_MODE', 'tf32')
+PER_GPU_BATCH = 32
+
+
+def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default=os.environ.get('LG_BENCH_MODE', 'auto'), help='fp32 | tf32 | bf16 | auto')
-    ap.add_argument('--batch', type=int, default=0, help='override the global batch')
+    ap.add_argument('--mode', default='auto', help='fp32 | tf32 | bf16 | auto')
+    ap.add_argument('--per-gpu-batch', type=int, default=0, help='samples per GPU (default 32): weak scaling')
+    ap.add_argument('--global-batch', '--batch', dest='global_batch', type=int, default=0,
+                    help='fix the GLOBAL batch instead (e.g. 256 = BASELINE configs[4] at any N): strong scaling')
     ap.add_argument('--layers', type=int, default=0, help='debug only: fewer layers (marks the line invalid)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-ops', action='store_true', help='skip the configs 1-3 suite and the other-mode lines')
     ap.add_argument('--eager', action='store_true', help='dispatch every op from python every step (no CUDA graph replay)')
-    ap.add_argument('--cpu-sample-batch', type=int, default=0, help='oracle sample batch (default 8 for --impl reference, 4 for the cpu_baseline leg)')
-    args = ap.parse_args()
+    ap.add_argument('--cpu-sample-batch', type=int, default=0,
+                    help='oracle sample batch (default 8 for --impl reference, 4 for the cpu_baseline leg)')
+    return ap.parse_args()
+
+
+def workload_config(args):
+    per_gpu = args.per_gpu_batch or PER_GPU_BATCH
+    global_batch = args.global_batch or per_gpu * args.gpus
+    assert global_batch % args.gpus == 0, "global batch %d does not divide over %d GPUs" % (global_batch, args.gpus)
+    weak = not args.global_batch
+    config = {'workload': 'examples/bert.py BERT-base (12L, d=768, heads 12, vocab 30522) masked-LM training step, '
+                          'seq %d, global batch %d (%d per GPU), Adam(lr=1e-4), random-init weights, synthetic tokens'
+                          % (SEQ, global_batch, global_batch // args.gpus),
+              'global_batch': global_batch, 'per_gpu_batch': global_batch // args.gpus, 'seq_len': SEQ,
+              'parallelism': 'dp%d' % args.gpus,
+              'baseline_config': ('configs[3] (1 GPU, batch 32)' if args.gpus == 1 and global_batch == 32 else
+                                  'configs[4] (global batch 256)' if global_batch == 256 else
+                                  'configs[3] per-GPU workload replicated over %d GPUs' % args.gpus),
+              'l2_policy': 'per-step working set (531.8 MB parameters + activations) exceeds the 126 MB L2'}
+    return config, global_batch, ('weak' if weak else 'strong')
+
+
+def reference_arm(args, config, scaling):
+    """The reference's CPU implementation of the path (oracle port: numpy + OpenBLAS on every host core) on this
+    arm's workload; each step is a bounded sample of it (the full model and optimizer, a smaller batch)."""
+    sample = args.cpu_sample_batch or 8
+    res = cpu_reference_leg(args.steps, args.warmup, sample, budget_s=170.0)
+    config = dict(config)
+    config['reference_sample'] = ('each timed step runs batch %d of the workload above (full model, seq %d, Adam); '
+                                  'samples/s = %d / step time' % (sample, SEQ, sample))
+    config['sample_batch_per_step'] = sample
+    config['same_config'] = False
+    config['blas_threads'] = os.environ.get('OMP_NUM_THREADS')
+    emit({'impl': 'reference', 'metric': 'bert_train_samples_per_s', 'value': res['value'], 'unit': 'samples/s',
+          'n_gpus': args.gpus, 'steps': res['steps_timed'], 'warmup': args.warmup,
+          'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
+          'dtype': 'f32', 'data': 'synthetic', 'config': config,
+          'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+          'e2e': {'value': res['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+          'gpu_launches': 0})
+
+
+def main():
+    args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     W = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
-    global_batch = args.batch or (32 if args.gpus == 1 else 256)
-    config = {'workload': 'examples/bert.py BERT-base (12L, d=768, heads 12, vocab 30522) masked-LM training step, '
-                          'seq %d, global batch %d, Adam(lr=1e-4), random-init weights, synthetic tokens' % (SEQ, global_batch),
-              'global_batch': global_batch, 'seq_len': SEQ, 'parallelism': 'dp%d' % args.gpus,
-              'l2_policy': 'per-step working set (531.8 MB parameters + activations) exceeds the 126 MB L2'}
+    config, global_batch, scaling = workload_config(args)
 
     if args.impl == 'reference':
-        if rank != 0:
-            return
-        res = cpu_reference_leg(args.steps, args.warmup, args.cpu_sample_batch or 8, budget_s=170.0)
-        line = {'impl': 'reference', 'metric': 'bert_train_samples_per_s', 'value': res['value'], 'unit': 'samples/s',
-                'n_gpus': args.gpus, 'steps': res['steps_timed'], 'warmup': args.warmup,
-                'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-                'e2e': {'value': res['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-                'gpu_launches': 0}
-        emit(line)
+        if rank == 0:
+            reference_arm(args, config, scaling)
         return
 
     # ------------------------------------------------------------------------------------ our arm
     import lightgrad_b200 as light
     from lightgrad_b200 import CudaTensor, parallel
     from lightgrad_b200.autograd.cuda import runtime as rt, ops
+    from lightgrad_b200.autograd.cuda.graph import StepGraph
     from examples import bert
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     rt.ensure_device(int(os.environ.get('LOCAL_RANK', '0')))
+    import ctypes
+    probe = rt.GemmDesc(4096, 768, 768, 1, 1, 0, 0, 768, 1, 0, 0, 1, 768, 0, 0, 768, 1)
     mode = args.mode
     if mode == 'auto':
-        probe = rt.GemmDesc(4096, 768, 768, 1, 1, 0, 0, 768, 1, 0, 0, 1, 768, 0, 0, 768, 1)
-        import ctypes
-        mode = 'tf32' if rt.api.gemm_tc_supported(rt.GEMM_TF32_TC, rt.F32, ctypes.byref(probe)) else 'fp32'
+        tc_code = {'tf32': rt.GEMM_TF32_TC, 'bf16': rt.GEMM_BF16_TC}.get(DEFAULT_TC_MODE, rt.GEMM_TF32_TC)
+        mode = DEFAULT_TC_MODE if rt.api.gemm_tc_supported(tc_code, rt.F32, ctypes.byref(probe)) else 'fp32'
     ops.set_matmul_mode(mode)
     cfg = dict(bert.BERT_BASE)
     if args.layers:
@@ -222,27 +278,47 @@ def main():
     dp = parallel.DataParallel(model, opt, comm=comm) if world > 1 else None
     step = make_step(model, opt, dp, light)
     light.Gradients.retain_intermediate = False
-    ids_g, labels_g = bert.synthetic_batch(global_batch, SEQ, cfg['vocab_size'])
-    lo, hi = parallel.shard_rows(global_batch, rank, world)
-    local = hi - lo
-    ids_np, labels_np = ids_g[lo:hi], labels_g[lo * SEQ:hi * SEQ]
-    ids_d = CudaTensor.from_numpy(ids_np, requires_grad=False)
-    lab_d = CudaTensor.from_numpy(labels_np, requires_grad=False)
+    graphs = []                                  # every captured step, destroyed in order at teardown
 
     def barrier():
         rt.synchronize()
         comm.barrier()
 
+    def shard_inputs(batch):
+        ids_g, labels_g = bert.synthetic_batch(batch, SEQ, cfg['vocab_size'])
+        lo, hi = parallel.shard_rows(batch, rank, world)
+        ids_np, labels_np = ids_g[lo:hi], labels_g[lo * SEQ:hi * SEQ]
+        return (ids_np, labels_np, CudaTensor.from_numpy(ids_np, requires_grad=False),
+                CudaTensor.from_numpy(labels_np, requires_grad=False))
+
+    def timed(run, k):
+        """ms per call of run(): k calls between two CUDA events on the compute stream, ranks released together,
+        max over ranks."""
+        run()
+        barrier()
+        t0 = rt.Event().record()
+        out = None
+        for _ in range(k):
+            out = run()
+        t1 = rt.Event().record()
+        t1.synchronize()
+        barrier()
+        return comm.max_float(t0.elapsed_ms(t1)) / k, out
+
+    def captured(step_fn, ids, labels, warm):
+        sg = StepGraph(lambda: step_fn(ids, labels), warmup=0)
+        graphs.append(sg)
+        for _ in range(warm):
+            sg.replay()
+        return sg
+
+    ids_np, labels_np, ids_d, lab_d = shard_inputs(global_batch)
+    local = ids_np.shape[0]
+
     # ---- eager reference point: python dispatch of every op, every step
     for _ in range(2):
         loss = step(ids_d, lab_d)
-    barrier()
-    ee0 = rt.Event().record()
-    for _ in range(3):
-        step(ids_d, lab_d)
-    ee1 = rt.Event().record()
-    ee1.synchronize()
-    eager_ms = ee0.elapsed_ms(ee1) / 3
+    eager_ms, _ = timed(lambda: step(ids_d, lab_d), 3)
 
     # ---- the step is static-shape: record it once into a CUDA graph, replay it without python dispatch
     if args.eager:
@@ -250,11 +326,8 @@ def main():
         for _ in range(W):
             run_step()
     else:
-        from lightgrad_b200.autograd.cuda.graph import StepGraph
-        sg = StepGraph(lambda: step(ids_d, lab_d), warmup=0)
+        sg = captured(step, ids_d, lab_d, W)
         run_step = sg.replay
-        for _ in range(W):
-            run_step()
 
     # ---- phase A: inputs resident in HBM
     barrier()
@@ -311,123 +384,139 @@ def main():
         roof_how = ('CUDA events on the compute stream around every lg_gemm launch of one extra step queued behind '
                     'a stream delay (no host dispatch latency inside the events)')
     else:
-        def timed(replay):
-            replay()
-            barrier()                       # ranks enter the timed replays together
-            t0 = rt.Event().record()
-            for _ in range(k_c):
-                replay()
-            t1 = rt.Event().record()
-            t1.synchronize()
-            return comm.max_float(t0.elapsed_ms(t1)) / k_c
-        step_ms_c = timed(sg.replay)
+        step_ms_c, _ = timed(sg.replay, k_c)
         rt.gemm_profile(2)
-        sg_nogemm = StepGraph(lambda: step(ids_d, lab_d), warmup=0)
+        sg_nogemm = captured(step, ids_d, lab_d, 0)
         _, gemm_launches, gemm_flops = rt.gemm_profile_read()
         rt.gemm_profile(0)
-        nogemm_ms = timed(sg_nogemm.replay)
+        nogemm_ms, _ = timed(sg_nogemm.replay, k_c)
         gemm_ms = max(step_ms_c - nogemm_ms, 1e-6)
         roof_how = ('ablation inside the replayed CUDA graph: %d replays of the step (%.3f ms) minus %d replays of the '
-                    'same captured step with the lg_gemm launches removed (%.3f ms), both timed with CUDA events on '
+                    'same captured step with the matmul launches removed (%.3f ms), both timed with CUDA events on '
                     'the compute stream right after the timed region' % (k_c, step_ms_c, k_c, nogemm_ms))
+        sg.replay()                                # leave real values behind the garbage-valued ablation replays
     rt.gemm_profile(False)
 
     # ---- multi-GPU only: the gradient exchange on its own and what of it stays exposed
-    comm_info = None
-    if world > 1 and dp is not None and getattr(dp, '_nccl', False):
-        a = dp.arena
-        nbytes = a.total * 4
-        for _ in range(2):
-            rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
-        barrier()
-        c0 = rt.Event().record()
-        for _ in range(5):
-            rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
-        c1 = rt.Event().record()
-        c1.synchronize()
-        ar_ms = comm.max_float(c0.elapsed_ms(c1)) / 5
+    comm_info, config5 = None, None
+    if world > 1 and dp is not None:
+        comm_info = dp.exchange_report(rt, comm, barrier) if hasattr(dp, 'exchange_report') else {}
         # the same local step without any exchange (captured separately): step time minus this = exposed communication
         local_step = make_step(model, opt, None, light)
         if args.eager:
-            run_local = lambda: local_step(ids_d, lab_d)  # noqa: E731
+            local_ms, _ = timed(lambda: local_step(ids_d, lab_d), 3)
         else:
-            sg_local = StepGraph(lambda: local_step(ids_d, lab_d), warmup=0)
-            run_local = sg_local.replay
-        run_local()
-        barrier()
-        l0 = rt.Event().record()
-        for _ in range(k_c if not args.eager else 3):
-            run_local()
-        l1 = rt.Event().record()
-        l1.synchronize()
-        local_ms = comm.max_float(l0.elapsed_ms(l1)) / (k_c if not args.eager else 3)
-        comm_info = {'allreduce_bytes': int(nbytes), 'allreduce_ms_alone': round(ar_ms, 3),
-                     'allreduce_busbw_gbps': round(2.0 * (world - 1) / world * nbytes / (ar_ms / 1e3) / 1e9, 1),
-                     'step_ms_without_exchange': round(local_ms, 3),
-                     'exposed_comm_ms': round(max(ms_a - local_ms, 0.0), 3),
-                     'note': 'bucketed all-reduce (64 MB buckets) overlapped with backward on the communication stream'}
-    if rank != 0:
-        finish(comm)
+            local_ms, _ = timed(captured(local_step, ids_d, lab_d, 1).replay, k_c)
+        comm_info.update({'step_ms_without_exchange': round(local_ms, 3),
+                          'exposed_comm_ms': round(max(ms_a - local_ms, 0.0), 3),
+                          'like_for_like_efficiency': round(local_ms / ms_a, 4),
+                          'like_for_like_note': 'this rank count\'s step time without any exchange (same local batch, '
+                                                'same binary, same box) divided by the step time with it'})
+        if not args.global_batch and global_batch != 256 and not args.eager and 256 % world == 0:
+            # BASELINE configs[4] exactly as written, at this N: global batch 256
+            _i5, _l5, ids5, lab5 = shard_inputs(256)
+            ms5, _ = timed(captured(step, ids5, lab5, 3).replay, 10)
+            config5 = {'global_batch': 256, 'per_gpu_batch': 256 // world, 'ms_per_step': round(ms5, 3),
+                       'value': round(256 / (ms5 / 1e3), 2), 'unit': 'samples/s', 'scaling': 'strong', 'steps': 10}
+            del ids5, lab5
 
-    peaks = load_peaks()
-    value = global_batch / (ms_a / 1e3)
-    e2e = global_batch / (ms_b / 1e3)
-    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    k_c = 1   # gemm_ms / gemm_launches / gemm_flops are per step from here on
-    if mode == 'bf16':
-        peak_tf, peak_name = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']), 'measured cuBLAS bf16 (sustained)'
-    elif mode == 'tf32':
-        peak_tf = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']) / 2.0
-        peak_name = 'half of measured cuBLAS bf16 sustained (tf32 runs at half the bf16 rate; no tf32 figure in MEASURED_PEAKS.json)'
-    else:
-        peak_tf, peak_name = 148 * 128 * 2 * 1.965e9 / 1e12, 'nominal FP32 FMA pipe (148 SM x 128 lanes x 2 x 1.965 GHz): exact-fp32 SIMT mode'
-    line = {
-        'metric': 'bert_train_samples_per_s', 'value': round(value, 2), 'unit': 'samples/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': W, 'ms_per_step': round(ms_a, 3), 'higher_is_better': True,
-        'scaling': 'weak' if args.gpus == 1 else 'strong', 'vs_baseline': None,
-        'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'bf16': 'bf16'}[mode], 'data': 'synthetic', 'config': config,
-        'loss': round(final_loss, 5),
-        'execution': 'eager python dispatch' if args.eager else 'whole step captured once into a CUDA graph, replayed per step',
-        'eager_ms_per_step': round(eager_ms, 3),
-        'e2e': {'value': round(e2e, 2), 'unit': 'samples/s', 'h2d_bytes_per_step': int(ids_np.nbytes + labels_np.nbytes),
-                'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_b, 3), 'steps': k_b, 'last_loss': round(float(loss_host), 5)},
-        'gpu_launches': int(n1 - n0), 'gpu_launches_per_step': round((n1 - n0) / args.steps, 1),
-        'clocks': clocks,
-        'roofline': {'bound': 'tensor', 'kernel': 'lg_gemm (%s)' % mode, 'achieved': round(achieved_tf, 2),
-                     'peak': round(peak_tf, 1), 'unit': 'TFLOP/s', 'frac': round(achieved_tf / peak_tf, 4),
-                     'peak_source': peak_name + '; ' + peaks['source'],
-                     # DRAM bytes of ALL matmul launches of one step (like `achieved`, an aggregate over the step's
-                     # launches): ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_gemm_dram_bytes.csv
-                     'traffic': NCU_GEMM_DRAM_BYTES_PER_STEP if (mode == 'tf32' and args.gpus == 1 and not args.layers) else None,
-                     'traffic_note': 'ncu capture of the 222 matmul launches of one batch-32 step: 11.90 GB read + 1.12 GB '
-                                     'written (algorithmic operand + result bytes of those launches: ~16 GB; results '
-                                     'still in L2 at kernel end are charged to later kernels)',
-                     'launches_per_step': gemm_launches // k_c, 'kernel_ms_per_step': round(gemm_ms / k_c, 3),
-                     'kernel_share_of_step': round(gemm_ms / k_c / step_ms_c, 3),
-                     'algorithmic_flops_per_step': gemm_flops / k_c,
-                     'how': roof_how},
-        'mfu_vs_measured_bf16': round(GEMM_FLOPS_PER_SAMPLE * value / 1e12 / peaks['bf16_tflops'], 4),
-    }
-    if comm_info is not None:
-        line['comm'] = comm_info
-    line['config']['per_gpu_batch'] = int(local)
-    if args.gpus == 1 and not args.no_cpu_baseline:
-        res = cpu_reference_leg(2, 1, args.cpu_sample_batch or 4, budget_s=90.0)
-        line['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
-    emit(line)
-    finish(comm)
+    # ---- N = 1: the same step in the other matmul modes, and BASELINE configs 1-3
+    modes_info, ops_info = None, None
+    if args.gpus == 1 and not args.no_ops and not args.eager and not args.layers:
+        modes_info = {}
+        for other in ('fp32', 'tf32', 'bf16'):
+            if other == mode:
+                continue
+            code = {'tf32': rt.GEMM_TF32_TC, 'bf16': rt.GEMM_BF16_TC}.get(other)
+            if code is not None and not rt.api.gemm_tc_supported(code, rt.F32, ctypes.byref(probe)):
+                modes_info[other] = {'unavailable': 'lg_gemm_tc_supported says no for this mode'}
+                continue
+            try:
+                ops.set_matmul_mode(other)
+                sgo = captured(step, ids_d, lab_d, 3)
+                ms_o, loss_o = timed(sgo.replay, 5 if other != 'fp32' else 3)
+                modes_info[other] = {'ms_per_step': round(ms_o, 3), 'value': round(global_batch / (ms_o / 1e3), 2),
+                                     'unit': 'samples/s', 'loss': round(float(loss_o.item()), 5)}
+            except Exception as exc:                       # a mode that is not built must not take the line down
+                modes_info[other] = {'unavailable': '%s: %s' % (type(exc).__name__, str(exc)[:200])}
+            finally:
+                ops.set_matmul_mode(mode)
+        # release the step graphs' private pools before the 2^28-element sweeps
+        for g in graphs:
+            g.destroy()
+        del graphs[:]
+        sys.path.insert(0, os.path.join(ROOT, 'benchmarks'))
+        import ops_suite
+        peaks_ = load_peaks()
+        tc_modes = ['fp32', 'tf32'] + (['bf16'] if 'unavailable' not in (modes_info.get('bf16') or {}) or mode == 'bf16' else [])
+        ops_info = ops_suite.run(rt, light, CudaTensor, ops, peaks_, cpu=not args.no_cpu_baseline, modes=tc_modes)
 
+    if rank == 0:
+        peaks = load_peaks()
+        value = global_batch / (ms_a / 1e3)
+        e2e = global_batch / (ms_b / 1e3)
+        achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        # a sub-second timed region at full clocks: the burst figures are the honest denominators
+        burst, sustained = peaks['bf16_tflops'], peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+        if mode == 'bf16':
+            peak_tf, peak_name, nominal = burst, 'measured cuBLAS bf16 burst', 2250.0
+            alt = {'frac_of_sustained_bf16': round(achieved_tf / sustained, 4)}
+        elif mode == 'tf32':
+            peak_tf, nominal = burst / 2.0, 1125.0
+            peak_name = 'half of the measured cuBLAS bf16 burst (tf32 runs at half the bf16 rate; no tf32 figure in MEASURED_PEAKS.json)'
+            alt = {'frac_of_half_sustained_bf16': round(achieved_tf / (sustained / 2.0), 4)}
+        else:
+            peak_tf = nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+            peak_name, alt = 'nominal FP32 FMA pipe (148 SM x 128 lanes x 2 x 1.965 GHz): exact-fp32 SIMT mode', {}
+        traffic = NCU_GEMM_DRAM_BYTES_PER_STEP.get(mode) if (args.gpus == 1 and local == 32 and not args.layers) else None
+        roofline = {'bound': 'tensor', 'kernel': 'lg_gemm (%s)' % mode, 'achieved': round(achieved_tf, 2),
+                    'peak': round(peak_tf, 1), 'unit': 'TFLOP/s', 'frac': round(achieved_tf / peak_tf, 4),
+                    'frac_nominal': round(achieved_tf / nominal, 4), 'nominal_peak': nominal,
+                    'peak_source': peak_name + '; ' + peaks['source'],
+                    # DRAM bytes of ALL matmul launches of one step (like `achieved`, an aggregate over the step's
+                    # launches): ncu dram__bytes_read.sum + dram__bytes_write.sum over those launches
+                    'traffic': traffic[0] if traffic else None,
+                    'traffic_note': traffic[1] if traffic else 'no ncu capture for this mode / batch',
+                    'launches_per_step': int(gemm_launches), 'kernel_ms_per_step': round(gemm_ms, 3),
+                    'kernel_share_of_step': round(gemm_ms / step_ms_c, 3),
+                    'algorithmic_flops_per_step': gemm_flops, 'how': roof_how}
+        roofline.update(alt)
+        line = {
+            'metric': 'bert_train_samples_per_s', 'value': round(value, 2), 'unit': 'samples/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': W, 'ms_per_step': round(ms_a, 3), 'higher_is_better': True,
+            'scaling': scaling, 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'bf16': 'bf16'}[mode], 'data': 'synthetic', 'config': config,
+            'loss': round(final_loss, 5),
+            'execution': 'eager python dispatch' if args.eager else 'whole step captured once into a CUDA graph, replayed per step',
+            'eager_ms_per_step': round(eager_ms, 3),
+            'e2e': {'value': round(e2e, 2), 'unit': 'samples/s', 'h2d_bytes_per_step': int(ids_np.nbytes + labels_np.nbytes),
+                    'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_b, 3), 'steps': k_b, 'last_loss': round(float(loss_host), 5)},
+            'gpu_launches': int(n1 - n0), 'gpu_launches_per_step': round((n1 - n0) / args.steps, 1),
+            'clocks': clocks, 'roofline': roofline,
+            # whole-step model flops utilisation PER GPU (the aggregate divided by the GPUs that produced it)
+            'mfu_vs_measured_bf16': round(GEMM_FLOPS_PER_SAMPLE * value / args.gpus / 1e12 / peaks['bf16_tflops'], 4),
+        }
+        if comm_info is not None:
+            line['comm'] = comm_info
+        if config5 is not None:
+            line['config5_global_batch_256'] = config5
+        if modes_info is not None:
+            line['modes'] = modes_info
+        if ops_info is not None:
+            line['ops'] = ops_info
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            res = cpu_reference_leg(2, 1, args.cpu_sample_batch or 4, budget_s=90.0)
+            line['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        emit(line)
 
-def finish(comm):
-    """Leave without running destructors: a NCCL communicator that was captured into a CUDA graph must not
-    be torn down rank by rank (ncclCommDestroy can wait for peers that have already gone)."""
-    sys.stdout.flush()
-    sys.stderr.flush()
-    try:
-        comm.barrier()
-    except Exception:
-        pass
-    os._exit(0)
+    # ---- orderly teardown (normal interpreter exit afterwards): captured steps first, then the communicator
+    barrier()
+    for g in graphs:
+        g.destroy()
+    del graphs[:]
+    if dp is not None:
+        dp.close()
+    comm.close()
 
 
 if __name__ == '__main__':

@@ -62,6 +62,13 @@ class StepGraph(object):
         rt.api.graph_launch(self._exec, self.n_kernels)
         return self.outputs
 
+    def destroy(self):
+        """Release the instantiated graph now (teardown order matters when it holds NCCL nodes: graphs first,
+        then the communicator).  The outputs keep their last values; ``replay`` is no longer possible."""
+        if self._exec is not None and rt.api is not None:
+            h, self._exec = self._exec, None
+            rt.api.graph_destroy(h)
+
     def __del__(self):
         try:
             if self._exec is not None and rt.api is not None:

@@ -45,6 +45,16 @@ def get_matmul_mode():
     return [k for k, v in _MODES.items() if v == _matmul_mode][0]
 
 
+def matmul_mode_available(name):
+    """True when the library can run a BERT-sized projection (4096 x 768 x 768, x @ W^T) in that mode on the
+    tensor cores (always True for the exact 'fp32' mode)."""
+    code = _MODES[name.lower()]
+    if code == rt.GEMM_FP32_SIMT:
+        return True
+    d = rt.GemmDesc(4096, 768, 768, 1, 1, 0, 0, 768, 1, 0, 0, 1, 768, 0, 0, 768, 1)
+    return bool(rt.ensure_device().gemm_tc_supported(code, rt.F32, C.byref(d)))
+
+
 # ---------------------------------------------------------------------------------------------------
 # helpers
 def _is_scalar(v):

@@ -34,6 +34,9 @@ class LocalComm(object):
     def broadcast_bytes(self, b, root=0):
         return b
 
+    def close(self):
+        pass
+
 
 class GlooComm(object):
     """Control-plane communicator over torch.distributed (gloo).  Host memory only."""
@@ -69,6 +72,14 @@ class GlooComm(object):
         obj = [b if self.rank == root else None]
         self.dist.broadcast_object_list(obj, src=root)
         return obj[0]
+
+    def close(self):
+        """Leave the process group together (the last collective of the job)."""
+        if self.dist.is_initialized():
+            try:
+                self.dist.barrier()
+            finally:
+                self.dist.destroy_process_group()
 
 
 def default_comm():
@@ -241,7 +252,49 @@ class DataParallel(object):
             g.fill(0.0)
             g += g.__class__.from_numpy(avg, requires_grad=False)
 
-    def close(self):
-        if self._nccl:
-            self.arena.rt.api.nccl_destroy()
-            self._nccl = False
+    def exchange_report(self, rt, comm, barrier, reps=5):
+        """The gradient exchange on its own (timed with CUDA events, max over ranks), for bench.py's `comm` object."""
+        if not self._nccl:
+            return {}
+        a = self.arena
+        nbytes = a.total * 4
+        for _ in range(2):
+            rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
+        barrier()
+        c0 = rt.Event().record()
+        for _ in range(reps):
+            rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
+        c1 = rt.Event().record()
+        c1.synchronize()
+        ms = comm.max_float(c0.elapsed_ms(c1)) / reps
+        return {'allreduce_bytes': int(nbytes), 'allreduce_ms_alone': round(ms, 3),
+                'allreduce_busbw_gbps': round(2.0 * (self.world - 1) / self.world * nbytes / (ms / 1e3) / 1e9, 1),
+                'note': 'ncclAllReduce of the whole gradient arena, alone on the GPU'}
+
+    def close(self, timeout_s=20.0):
+        """Tear the communicator down in order: every rank drains its streams, all ranks meet, then
+        ncclCommDestroy.  Captured steps that hold NCCL nodes must have been destroyed before (StepGraph.destroy).
+        ncclCommDestroy is called from a helper thread with a deadline: if a peer has already gone it can wait
+        forever, and a clean interpreter exit matters more than returning NCCL's resources to a dying process."""
+        if not self._nccl:
+            return
+        import threading
+        self._nccl = False
+        rt = self.arena.rt
+        rt.synchronize()
+        self.comm.barrier()
+        done = []
+
+        def destroy():
+            try:
+                rt.api.nccl_destroy()
+                done.append(True)
+            except Exception as exc:          # reported, not raised: the job's work is over
+                done.append(exc)
+        th = threading.Thread(target=destroy, daemon=True)
+        th.start()
+        th.join(timeout_s)
+        if not done:
+            import sys
+            sys.stderr.write("lightgrad_b200: ncclCommDestroy did not return within %.0f s on rank %d; "
+                             "leaving it to process exit\n" % (timeout_s, self.rank))

@@ -133,3 +133,81 @@ def test_bert_base_full_size_step_is_sane_and_batch_splits_average():
         assert np.isfinite(g_all[n]).all(), n
         err = np.abs(g_all[n] - 0.5 * (g_a[n] + g_b[n])).max()
         assert err <= 5e-3 * max(np.abs(g_all[n]).max(), 1e-3 * gmax), n
+
+
+# ---- full-size parity against the oracle ("one full-size CPU step") -----------------
+_ORACLE_MEMO = {}
+
+
+def _step_grads(T, cfg, batch, seq, seed=0):
+    import lightgrad_b200.nn as nn
+    from examples import bert
+    ids, labels = bert.synthetic_batch(batch, seq, cfg['vocab_size'])
+    with nn.use_tensor(T):
+        np.random.seed(seed)
+        model = bert.BertForMaskedLM(**cfg)
+    for p in model.parameters():
+        p.zero_grad()
+    logits = model(T.from_numpy(ids, requires_grad=False))
+    loss = light.loss.cross_entropy(logits.reshape(-1, cfg['vocab_size']), T.from_numpy(labels, requires_grad=False))
+    loss.backward()
+    return loss.item(), {n: p.grad.numpy().astype(np.float64) for n, p in model.named_parameters()}
+
+
+def _oracle_and_device_grads(cfg, batch, seq, mode, seed=0):
+    """Loss and every parameter gradient of one masked-LM step, on the CPU oracle (computed once per
+    configuration) and on the CUDA tensor, from the same initial parameters and tokens."""
+    from oracle import CpuTensor
+    key = (tuple(sorted(cfg.items())), batch, seq, seed)
+    if key not in _ORACLE_MEMO:
+        _ORACLE_MEMO.clear()                       # one full-size gradient set (0.5 GB as float64) at a time
+        _ORACLE_MEMO[key] = _step_grads(CpuTensor, cfg, batch, seq, seed)
+    prev = ops.set_matmul_mode(mode)
+    try:
+        got = _step_grads(CudaTensor, cfg, batch, seq, seed)
+    finally:
+        ops.set_matmul_mode(prev)
+    return _ORACLE_MEMO[key], got
+
+
+def _worst_rel_err(g_ref, g_got):
+    """Per-tensor max |error| relative to that tensor's largest reference gradient; tensors whose true gradient
+    is zero (key biases: softmax is shift invariant) are held to 1e-6 of the largest gradient of the model."""
+    gmax = max(float(np.abs(g).max()) for g in g_ref.values())
+    worst, where = 0.0, None
+    for n in g_ref:
+        assert g_got[n].shape == g_ref[n].shape, n
+        assert np.isfinite(g_got[n]).all(), n
+        denom = max(float(np.abs(g_ref[n]).max()), 1e-6 * gmax)
+        e = float(np.abs(g_ref[n] - g_got[n]).max() / denom)
+        if e > worst:
+            worst, where = e, n
+    return worst, where
+
+
+@pytest.mark.parametrize('mode', ['tf32', 'bf16'])
+def test_bert_base_full_size_step_against_the_oracle_tensor_core(mode):
+    # BERT-base exactly as benchmarked (12 layers, d = 768, 12 heads x 64, vocabulary 30522, seq 128), batch 2:
+    # this is where the 2-CTA GEMM, the tail-wave split, 768-wide LayerNorm rows, cross entropy by pitch over the
+    # 30522 (-> 30528) columns and the fused attention run at their production shapes.  North-star bound for
+    # tensor-core modes: loss and every parameter gradient within 5e-3.
+    from examples import bert
+    if mode == 'bf16' and not ops.matmul_mode_available('bf16'):
+        pytest.skip("bf16 tensor-core mode is not built")
+    (l_ref, g_ref), (l_got, g_got) = _oracle_and_device_grads(dict(bert.BERT_BASE), 2, 128, mode)
+    assert abs(l_ref - l_got) <= 5e-3 * abs(l_ref), (l_ref, l_got)
+    worst, where = _worst_rel_err(g_ref, g_got)
+    assert len(g_ref) == 203
+    assert worst <= 5e-3, (mode, worst, where)
+
+
+def test_full_width_two_layer_step_against_the_oracle_exact_fp32():
+    # full width (d = 768, FFN 3072, 12 heads, vocabulary 30522, seq 128), 2 layers, exact-fp32 SIMT matmul:
+    # end-to-end gradients agree with the numpy oracle to summation-order noise (OpenBLAS vs the kernel's
+    # k-order: ~1e-6 per matmul, a few of them deep)
+    from examples import bert
+    cfg = dict(bert.BERT_BASE, num_hidden_layers=2)
+    (l_ref, g_ref), (l_got, g_got) = _oracle_and_device_grads(cfg, 2, 128, 'fp32')
+    assert abs(l_ref - l_got) <= 1e-5 * abs(l_ref), (l_ref, l_got)
+    worst, where = _worst_rel_err(g_ref, g_got)
+    assert worst <= 2e-5, (worst, where)
