@@ -281,9 +281,42 @@ int lg_nccl_unique_id(void* id128);                       /* 128-byte ncclUnique
 int lg_nccl_init(const void* id128, int world, int rank);
 int lg_nccl_allreduce_f32(void* buf, int64_t n, int op /* 0 sum, 1 avg, 2 max */, int on_comm_stream);
 int lg_nccl_broadcast(void* buf, int64_t nbytes, int root);
+/* stream ordering of the collective stream (usable without a communicator: the multicast exchange needs it too) */
 int lg_nccl_wait(void);                                   /* compute stream waits for comm stream */
 int lg_nccl_fork(void);                                   /* comm stream waits for compute stream */
 int lg_nccl_destroy(void);
+
+/* ---- gradient exchange fused with the optimizer over NVLink multicast (new; NVSwitch in-fabric reduction) --------
+ * Replaces "lg_nccl_allreduce_f32 over the gradient arena + lg_adam_step over all parameters" of the data-parallel
+ * step (the optimizer arithmetic is lightgrad/optim.py:27-52 of the reference, as in lg_adam_step / lg_sgd_step).
+ * Both arenas live in one region per GPU that is bound to a multicast object shared by all ranks:
+ *   lg_mc_supported      *yes = 1 when the device and driver offer multicast objects
+ *   lg_mc_region_bytes   region size and the byte offsets of the gradient arena, the parameter arena and the flag
+ *                        page inside it, for arenas of `arena_bytes` each
+ *   lg_mc_create         rank 0: create the object; *fd is a POSIX descriptor to pass to the other ranks (SCM_RIGHTS)
+ *   lg_mc_import         other ranks: open the object from the received descriptor
+ *   lg_mc_add_device     every rank; ALL ranks must have returned (host barrier) before the first lg_mc_bind
+ *   lg_mc_bind           every rank: allocate, map and bind this GPU's memory; *local_ptr / *mc_ptr are the plain and
+ *                        the multicast mapping of the same region (zero-filled); host barrier before first use
+ *   lg_mc_exchange_step  one bucket [lo, hi) (elements, multiples of 4) on the collective stream, ordered by
+ *                        lg_nccl_fork / lg_nccl_wait like an all-reduce: reduce-scatter of the gradients through the
+ *                        switch (multimem.ld_reduce), optimizer update of this rank's 1/world share (kind 0 Adam,
+ *                        1 AdaBelief -- arguments as lg_adam_step, m / v full-size arrays of which only the owned
+ *                        ranges are used; 2 SGD with m = previous deltas when momentum != 0; 3 no update), all-gather
+ *                        of the new parameters (multimem.st) -- one kernel whose CTAs fit next to a GEMM CTA
+ *   lg_mc_release        unmap / unbind / free (after a host barrier) */
+int lg_mc_supported(int* yes);
+int lg_mc_region_bytes(size_t arena_bytes, int world, size_t* region_bytes, size_t* grad_offset, size_t* param_offset,
+                       size_t* flag_offset);
+int lg_mc_create(size_t region_bytes, int world, int* fd);
+int lg_mc_import(int fd, size_t region_bytes, int world);
+int lg_mc_add_device(void);
+int lg_mc_bind(void** local_ptr, void** mc_ptr);
+int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_t flag_offset, int64_t lo, int64_t hi,
+                        int rank, int world, void* m, void* v, int n_seg, const int64_t* seg_end_dev, int64_t* t_dev,
+                        double lr, double beta1, double beta2, double eps, double momentum, int seg_offset,
+                        int t_advance);
+int lg_mc_release(void);
 
 #ifdef __cplusplus
 }

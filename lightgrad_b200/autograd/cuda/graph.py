@@ -37,12 +37,16 @@ class StepGraph(object):
             api.graph_destroy(self._exec)
             self._exec = None
         n0 = rt.launch_count()
+        from . import ops
+        ops.drop_staging_copies()        # copies made before the capture would never be refreshed by replays
         api.graph_begin(C.byref(self._pool))
         try:
             self.outputs = self.fn()
         except BaseException:
             api.graph_abort()
+            ops.drop_staging_copies()
             raise
+        ops.drop_staging_copies()        # ... and copies made inside it live in the graph's private pool
         # drop the autograd history of the outputs: the activations it references go back to the graph's
         # private pool (their addresses stay reserved for replays) instead of staying allocated
         outs = self.outputs if isinstance(self.outputs, (tuple, list)) else (self.outputs,)

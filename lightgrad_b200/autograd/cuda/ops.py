@@ -45,6 +45,75 @@ def get_matmul_mode():
     return [k for k, v in _MODES.items() if v == _matmul_mode][0]
 
 
+# ---------------------------------------------------------------------------------------------------
+# bf16 tensor-core mode: operands are bf16 STAGING COPIES of the fp32 tensors (the tensors themselves, the
+# accumulation and every result stay fp32).  A copy covers a whole device block (the tensor's buffer, or the
+# optimizer arena a parameter lives in) and is shared by every view of it -- x, x^T, per-head slices, W and W^T
+# all address the same copy with the same element strides -- so each block is converted once per step however many
+# GEMMs read it (x: forward and dW; dY: dX and dW; W: forward and dX).  The copy is dropped whenever the block is
+# written through this module (in-place operators, ``out=`` results, optimizer updates).
+import weakref  # noqa: E402
+_staged = weakref.WeakSet()
+
+
+def _root(t):
+    d = t._data
+    return d.parent if isinstance(d, rt.ArenaSlice) else d
+
+
+def _bf16_ptr(t):
+    """Device address of view ``t`` inside the bf16 staging copy of its block (made on first use)."""
+    root = _root(t)
+    sh = root._bf16
+    if sh is None:
+        n = root.nbytes // 4
+        sh = rt.Buffer(max(n, 8) * 2)
+        rt.api.cast(rt.F32, rt.BF16, 1, i64arr((n,)), root.ptr, None, sh.ptr, None)
+        root._bf16 = sh
+        _staged.add(root)
+    return sh.ptr + (t.ptr - root.ptr) // 2
+
+
+def _written(t):
+    """``t``'s block is about to be modified in place: its staging copy (if any) is stale."""
+    root = _root(t)
+    if root._bf16 is not None:
+        root._bf16 = None
+
+
+def drop_staging_copies():
+    """Forget every bf16 staging copy (before / after a CUDA-graph capture: a copy made outside the capture would
+    not be refreshed by replays, one made inside it lives in the graph's private pool)."""
+    for root in list(_staged):
+        root._bf16 = None
+    _staged.clear()
+
+
+def _stage_for_side_stream(tensors):
+    if _matmul_mode == rt.GEMM_BF16_TC:
+        for t in tensors:
+            if isinstance(t, CudaTensor) and t._code == rt.F32 and t._numel:
+                _bf16_ptr(t)
+
+
+rt.side_prepare = _stage_for_side_stream
+
+
+def _launch_gemm(mode, code, d, a, b, out, bias, accumulate):
+    """lg_gemm in the selected mode; in bf16 mode through the staging copies, or -- when the tensor-core kernel
+    cannot take the problem (tiny, or strides that are not 16-byte multiples of bf16) -- exactly, on the fp32 data."""
+    bias_ptr = bias.ptr if bias is not None else None
+    if mode == rt.GEMM_BF16_TC:
+        if code == rt.F32 and not (accumulate and bias is not None) and \
+                rt.api.gemm_tc_supported(mode, rt.BF16, C.byref(d)):
+            pa, pb = _bf16_ptr(a), _bf16_ptr(b)
+            if not ((pa | pb | out.ptr) & 15):
+                rt.api.gemm(mode, rt.BF16, C.byref(d), pa, pb, out.ptr, bias_ptr, 1 if accumulate else 0)
+                return
+        mode = rt.GEMM_FP32_SIMT
+    rt.api.gemm(mode, code, C.byref(d), a.ptr, b.ptr, out.ptr, bias_ptr, 1 if accumulate else 0)
+
+
 def matmul_mode_available(name):
     """True when the library can run a BERT-sized projection (4096 x 768 x 768, x @ W^T) in that mode on the
     tensor cores (always True for the exact 'fp32' mode)."""
@@ -52,7 +121,7 @@ def matmul_mode_available(name):
     if code == rt.GEMM_FP32_SIMT:
         return True
     d = rt.GemmDesc(4096, 768, 768, 1, 1, 0, 0, 768, 1, 0, 0, 1, 768, 0, 0, 768, 1)
-    return bool(rt.ensure_device().gemm_tc_supported(code, rt.F32, C.byref(d)))
+    return bool(rt.ensure_device().gemm_tc_supported(code, rt.BF16 if code == rt.GEMM_BF16_TC else rt.F32, C.byref(d)))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -156,6 +225,7 @@ def _assign(dst, val):
     """dst[...] = val with numpy broadcasting of ``val``; ``dst`` may be any strided view."""
     if val._code != dst._code:
         val = val.astype(dst._dtype)
+    _written(dst)
     shp = dst._shape
     if _bshape(shp, val._shape) != shp:
         raise ValueError("could not broadcast input from shape %s into shape %s" % (val._shape, shp))
@@ -473,6 +543,7 @@ def _inplace(op, s_op, negate=False):
     class _Op(Function):
         def forward(ctx, t, other):
             rt.side_join_if_written(t)
+            _written(t)
             if _is_scalar(other):
                 v = -float(other) if negate else float(other)
                 if t._code not in (rt.F32, rt.F64):
@@ -499,6 +570,7 @@ for _name, _op, _sop, _neg in (('__iadd__', EW['ADD'], EW['ADD_S'], False),
 @CudaTensor.register_op()
 class fill(Function):
     def forward(ctx, t, val):
+        _written(t)
         t._fill_value(val)
         return t._view(t._shape, t._strides)
 
@@ -714,11 +786,11 @@ def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
                     csb[0], csb[1], b._strides[-2], b._strides[-1],
                     csc[0], csc[1], out._strides[-2], out._strides[-1])
     if out._numel:
+        _written(out)
         if K == 0:
             out._fill_value(0)
         else:
-            rt.api.gemm(_matmul_mode if mode is None else mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr,
-                        bias.ptr if bias is not None else None, 1 if accumulate else 0)
+            _launch_gemm(_matmul_mode if mode is None else mode, a._code, d, a, b, out, bias, accumulate)
     return out
 
 
@@ -924,8 +996,21 @@ def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False):
                     csc[0], csc[1], out._strides[-2], out._strides[-1])
     n = len(As)
     arr = C.c_void_p * n
-    rt.api.gemm_grouped(_matmul_mode, a._code, C.byref(d), n, arr(*[t.ptr for t in As]), arr(*[t.ptr for t in Bs]),
-                        arr(*[t.ptr for t in outs]),
+    for o in outs:
+        _written(o)
+    mode, code = _matmul_mode, a._code
+    pa, pb = [t.ptr for t in As], [t.ptr for t in Bs]
+    if mode == rt.GEMM_BF16_TC:
+        ok = code == rt.F32 and not (accumulate and biases is not None) and \
+            rt.api.gemm_tc_supported(mode, rt.BF16, C.byref(d))
+        if ok:
+            qa, qb = [_bf16_ptr(t) for t in As], [_bf16_ptr(t) for t in Bs]
+            ok = not any((x | y | o.ptr) & 15 for x, y, o in zip(qa, qb, outs))
+        if ok:
+            pa, pb, code = qa, qb, rt.BF16
+        else:
+            mode = rt.GEMM_FP32_SIMT
+    rt.api.gemm_grouped(mode, code, C.byref(d), n, arr(*pa), arr(*pb), arr(*[t.ptr for t in outs]),
                         arr(*[t.ptr for t in biases]) if biases is not None else None, 1 if accumulate else 0)
     return outs
 
@@ -938,7 +1023,20 @@ def _gemm_epilogue(a, b, out, bias, epi, aux):
     assert b._shape[0] == K and out._shape == (M, N) == aux._shape and out._strides[1] == 1 == aux._strides[1]
     d = rt.GemmDesc(M, N, K, 1, 1, 0, 0, a._strides[0], a._strides[1], 0, 0, b._strides[0], b._strides[1],
                     0, 0, out._strides[0], 1)
-    rt.api.gemm_epilogue(_matmul_mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr,
+    _written(out)
+    if epi == 1:
+        _written(aux)
+    mode, code, pa, pb = _matmul_mode, a._code, a.ptr, b.ptr
+    if mode == rt.GEMM_BF16_TC:
+        ok = code == rt.F32 and rt.api.gemm_tc_supported(mode, rt.BF16, C.byref(d))
+        if ok:
+            qa, qb = _bf16_ptr(a), _bf16_ptr(b)
+            ok = not ((qa | qb | out.ptr) & 15)
+        if ok:
+            pa, pb, code = qa, qb, rt.BF16
+        else:
+            mode = rt.GEMM_FP32_SIMT
+    rt.api.gemm_epilogue(mode, code, C.byref(d), pa, pb, out.ptr,
                          bias.ptr if bias is not None else None, epi, aux.ptr, aux._strides[0], 0.0)
     return out
 
@@ -956,9 +1054,17 @@ def _attention_gemm(a, b, out, epi, alpha, aux=None):
     d = rt.GemmDesc(M, N, K, B0, B1, a._strides[0], a._strides[1], a._strides[2], a._strides[3],
                     b._strides[0], b._strides[1], b._strides[2], b._strides[3],
                     out._strides[0], out._strides[1], out._strides[2], 1)
-    if not rt.api.gemm_tc_supported(_matmul_mode, a._code, C.byref(d)):
+    code, pa, pb = a._code, a.ptr, b.ptr
+    if _matmul_mode == rt.GEMM_BF16_TC:
+        code = rt.BF16
+    if not rt.api.gemm_tc_supported(_matmul_mode, code, C.byref(d)):
         return False
-    rt.api.gemm_epilogue(_matmul_mode, a._code, C.byref(d), a.ptr, b.ptr, out.ptr, None, epi,
+    if code == rt.BF16:
+        pa, pb = _bf16_ptr(a), _bf16_ptr(b)
+        if (pa | pb) & 15:
+            return False
+    _written(out)
+    rt.api.gemm_epilogue(_matmul_mode, code, C.byref(d), pa, pb, out.ptr, None, epi,
                          aux.ptr if aux is not None else None, N, float(alpha))
     return True
 
@@ -1305,6 +1411,7 @@ class getitem(Function):
 @CudaTensor.register_op("__setitem__")
 class setitem(Function):
     def forward(ctx, a, idx, val):
+        _written(a)
         src, plan = _index_plan(a, idx)
         if plan is None:
             if _is_scalar(val):

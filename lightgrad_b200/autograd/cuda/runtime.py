@@ -107,6 +107,16 @@ _SIGNATURES = {
     'lg_nccl_wait': [],
     'lg_nccl_fork': [],
     'lg_nccl_destroy': [],
+    'lg_mc_supported': [C.POINTER(C.c_int)],
+    'lg_mc_region_bytes': [C.c_size_t, C.c_int] + [C.POINTER(C.c_size_t)] * 4,
+    'lg_mc_create': [C.c_size_t, C.c_int, C.POINTER(C.c_int)],
+    'lg_mc_import': [C.c_int, C.c_size_t, C.c_int],
+    'lg_mc_add_device': [],
+    'lg_mc_bind': [C.POINTER(_vp), C.POINTER(_vp)],
+    'lg_mc_exchange_step': [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int64, C.c_int64, C.c_int, C.c_int, _vp, _vp,
+                            C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                            C.c_int],
+    'lg_mc_release': [],
 }
 
 _lib = None
@@ -197,6 +207,8 @@ class side_stream(object):
         self.hold, self.writes = hold, writes
 
     def __enter__(self):
+        if side_prepare is not None:
+            side_prepare(self.hold)      # anything the operands need staged happens on the compute stream first
         api.side_begin()
         _side_held.extend(self.hold)
         _side_held.extend(self.writes)
@@ -205,6 +217,9 @@ class side_stream(object):
 
     def __exit__(self, *exc):
         api.side_end()
+
+
+side_prepare = None      # hook of the operator layer: called with the tensors a side-stream block will read
 
 
 def side_join():
@@ -253,10 +268,11 @@ def device_props():
 
 class Buffer(object):
     """Ref-counted device block from the library's caching allocator (analogue of PooledBuffer)."""
-    __slots__ = ('ptr', 'nbytes', '_free', '__weakref__')
+    __slots__ = ('ptr', 'nbytes', '_free', '_bf16', '__weakref__')
 
     def __init__(self, nbytes):
         self.ptr = 0
+        self._bf16 = None          # bf16 staging copy of the whole block (bf16 tensor-core matmul mode), or None
         a = ensure_device()
         p = _vp()
         a.alloc(int(nbytes), C.byref(p))
@@ -272,6 +288,15 @@ class Buffer(object):
                 self._free(p)
             except Exception:
                 pass
+
+
+class ExternalBuffer(object):
+    """Device memory this module does not own (a window of the NVLink multicast region): same face as Buffer, never
+    freed here; ``keep`` holds whatever must outlive it."""
+    __slots__ = ('ptr', 'nbytes', 'keep', '_bf16', '__weakref__')
+
+    def __init__(self, ptr, nbytes, keep=None):
+        self.ptr, self.nbytes, self.keep, self._bf16 = int(ptr), int(nbytes), keep, None
 
 
 class ArenaSlice(object):

@@ -21,6 +21,7 @@ cudaStream_t stream();        // stream kernels launch on: the compute stream, o
 bool on_side_stream();      // launching on the side stream or (lg_comm_compute_begin) on the collective stream
 int alt_stream_index();     // 0 compute, 1 side, 2 collective stream
 void comm_release_deferred();
+void comm_defer_free(void* p);   // block from tmp_alloc that the collective stream still uses: freed by comm_release_deferred
 int side_join();
 int side_order_before(cudaStream_t other);
 cudaStream_t comm_stream();   // collective stream

@@ -6,10 +6,10 @@ int gemm_simt(int dtype, const LgGemmDesc* d, const void* a, const void* b, void
               int accumulate);
 int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate);
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c);
-int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
+int gemm_tc_grouped(int mode, const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
                     const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld, double alpha);
 int gemm_set_sm_limit(int n);
-int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
+int gemm_tc_epilogue(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
                      int64_t aux_ld, double alpha);
 }  // namespace lg
 
@@ -28,6 +28,16 @@ std::vector<GemmProbe> g_probes;
 bool g_skip = false;
 uint64_t g_skip_launches = 0;
 double g_skip_flops = 0.0;
+
+// LG_GEMM_BF16_TC multiplies bf16 operands (dtype LG_BF16: staging copies made with lg_cast or written by a producer
+// kernel) into an fp32 result; fp32 operands in that mode are an error, never a silent change of arithmetic
+int bf16_contract(int mode, int dtype, const char* who) {
+    if (mode == LG_GEMM_BF16_TC && dtype != LG_BF16)
+        return set_error("%s: LG_GEMM_BF16_TC takes bf16 operands (dtype LG_BF16); stage fp32 operands with lg_cast first", who);
+    if (dtype == LG_BF16 && mode != LG_GEMM_BF16_TC)
+        return set_error("%s: bf16 operands need mode LG_GEMM_BF16_TC", who);
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -82,8 +92,12 @@ int lg_gemm(int mode, int dtype, const LgGemmDesc* d, const void* a, const void*
         LG_CUDA(cudaEventRecord(pr.e0, stream()));
     }
     int rc;
+    if (bf16_contract(mode, dtype, "lg_gemm")) return 1;
     if (mode != LG_GEMM_FP32_SIMT && !(accumulate && bias) && gemm_tc_supported(mode, dtype, d, a, b, c))
         rc = gemm_tc(mode, d, a, b, c, bias, accumulate);
+    else if (dtype == LG_BF16)
+        rc = set_error("lg_gemm: this problem cannot run on the bf16 tensor-core path (check lg_gemm_tc_supported "
+                       "first and use the exact mode on the fp32 operands instead)");
     else
         rc = gemm_simt(dtype, d, a, b, c, bias, accumulate);
     if (g_prof_on) {
@@ -102,8 +116,10 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
         g_skip_flops += 2.0 * (double)d->M * (double)d->N * (double)d->K * (double)(d->batch0 * d->batch1) * groups;
         return 0;
     }
+    if (bf16_contract(mode, dtype, "lg_gemm_grouped")) return 1;
     bool tc = mode != LG_GEMM_FP32_SIMT && !(accumulate && bias);
     for (int g = 0; g < groups && tc; ++g) tc = gemm_tc_supported(mode, dtype, d, a[g], b[g], c[g]) != 0;
+    LG_REQUIRE(tc || dtype != LG_BF16, "lg_gemm_grouped: this problem cannot run on the bf16 tensor-core path");
     GemmProbe pr;
     if (g_prof_on) {
         LG_CUDA(cudaEventCreate(&pr.e0));
@@ -113,7 +129,7 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
     }
     int rc = 0;
     if (tc) {
-        rc = gemm_tc_grouped(d, groups, a, b, c, bias, accumulate, 0, nullptr, 0, 0.0);
+        rc = gemm_tc_grouped(mode, d, groups, a, b, c, bias, accumulate, 0, nullptr, 0, 0.0);
     } else {
         // exact path: one launch per group (a repeated C accumulates from the second group on)
         for (int g = 0; g < groups && !rc; ++g) {
@@ -143,8 +159,10 @@ int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, co
         g_skip_flops += flops;
         return 0;
     }
+    if (bf16_contract(mode, dtype, "lg_gemm_epilogue")) return 1;
     bool tc = mode != LG_GEMM_FP32_SIMT && gemm_tc_supported(mode, dtype, d, a, b, c) && d->N % 4 == 0 &&
               (!aux || ((((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0));
+    LG_REQUIRE(tc || dtype != LG_BF16, "lg_gemm_epilogue: this problem cannot run on the bf16 tensor-core path");
     if (rows) {
         // the row epilogues exist only on the tensor-core path (a row must fit one 128-column tile); callers
         // check lg_gemm_tc_supported first and otherwise run the product and the softmax kernel separately
@@ -159,7 +177,7 @@ int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, co
     }
     int rc;
     if (tc) {
-        rc = gemm_tc_epilogue(d, a, b, c, bias, epi_op, aux, aux_ld, alpha);
+        rc = gemm_tc_epilogue(mode, d, a, b, c, bias, epi_op, aux, aux_ld, alpha);
     } else {
         // exact path: the product, then the activation as a strided elementwise pass over the same buffers
         rc = gemm_simt(dtype, d, a, b, c, bias, 0);

@@ -1,5 +1,5 @@
-// Tensor-core matmul for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators, operands staged
-// by TMA, persistent warp-specialised CTAs.
+// Tensor-core matmul for sm_100a: tcgen05.mma (kind::tf32 on fp32 operands, kind::f16 on bf16 operands) with
+// TMEM accumulators, operands staged by TMA, persistent warp-specialised CTAs.
 //
 // Replaces the reference's OpenCL SGEMM (opencl/kernels.py:201-337) for the "TF32 tensor-core mode".
 // fp32 operands are read straight from HBM by TMA (128-byte swizzled boxes) and consumed by
@@ -15,6 +15,11 @@
 //   warps 2..9    epilogue (two per TMEM lane quarter, alternate 32-column chunks): tcgen05.ld 32x32b.x32 -> (+bias) -> swizzled smem -> TMA store
 //                 (cp.reduce.async.bulk.tensor .add when the K range is split across CTAs)
 //   two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// BF16 mode (LG_GEMM_BF16_TC): the same kernels instantiated with 2-byte operands (ES = 2).  The byte geometry
+// of a stage is identical -- a k-block is still one 128-byte swizzle row (64 bf16 instead of 32 fp32), a UMMA
+// k-step still 32 bytes -- only the MN-major layout differs: 16-bit operands use the plain SWIZZLE_128B atoms
+// (64-element chunks, 8-row groups) where tf32 needs the 32-byte-base variant.  Operands are bf16 copies staged
+// by the host layer (lg_cast / fused producer epilogues); accumulation and the result stay fp32.
 // Roofline: tensor pipe (TF32 dense = half the bf16 rate).  Algorithmic flops 2*M*N*K.
 #include "lg_common.cuh"
 #include <cuda.h>
@@ -26,7 +31,17 @@ namespace {
 
 constexpr int LG_MAX_GROUPS = 4;
 constexpr int BM = 128;
-constexpr int BK = 32;               // fp32 elements per K step = 128 bytes
+// ES = operand element size in bytes (4: fp32 read as tf32, 2: bf16).  Per-ES geometry of one k-block:
+template <int ES> struct Geo {
+    static constexpr int BKE = 128 / ES;            // elements per k-block = one 128-byte swizzle row
+    static constexpr int CH = 128 / ES;             // MN-major: elements per contiguous chunk (one 128-byte row)
+    static constexpr int CH_SHIFT = ES == 4 ? 5 : 6;
+    static constexpr int CHUNK_BYTES = BKE * 128;   // MN-major: a chunk is BKE k-rows of 128 bytes
+    static constexpr int KSTEP_MN_BYTES = (32 / ES) * 128;   // MN-major: k-rows of one UMMA k-step (8 / 16) x 128 B
+    static constexpr int MN_SBO = ES == 4 ? 512 : 1024;      // 4-row (base32b) / 8-row groups
+    static constexpr int MN_LAYOUT = ES == 4 ? 1 : 2;        // SWIZZLE_128B_BASE32B / SWIZZLE_128B
+};
+constexpr int KSTEPS = 4;             // UMMA k-steps (32 bytes of K each) per k-block
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, taking alternate 32-column chunks
 constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
@@ -160,10 +175,31 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     return d;
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, bool a_mn, bool b_mn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate; operand format 2 = tf32, 1 = bf16
+template <int ES>
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, bool a_mn, bool b_mn) {
+    constexpr uint32_t fmt = ES == 4 ? 2u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <int ES, int CG>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    if constexpr (ES == 4 && CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accum) : "memory");
+    else if constexpr (ES == 4 && CG == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accum) : "memory");
+    else if constexpr (ES == 2 && CG == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accum) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
+                     "r"(idesc), "r"(accum) : "memory");
 }
 
 // SMs the persistent GEMM grids may occupy (lg_gemm_sm_limit): a data-parallel step leaves a few SMs to the
@@ -490,10 +526,11 @@ __device__ __forceinline__ void epilogue_tile_rows(const EpiTile& t, uint32_t ta
 // both CTAs.  Measured on B200: no faster than CL = 1 (a 2-CTA multicast does not reduce L2 traffic, and
 // every CTA still stages the whole B tile), so only CL = 1 is instantiated; CTA pairs use the
 // cta_group::2 kernel below, which really halves the B bytes per SM.
-template <int BN, bool A_MN, bool B_MN, int STAGES, int CL>
+template <int ES, int BN, bool A_MN, bool B_MN, int STAGES, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     LG_PDL_TRIGGER();
+    using G = Geo<ES>;
     constexpr int B_STAGE_BYTES = BN * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -570,25 +607,25 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
                     uint8_t* sa = stage_base + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    const int k0 = kb * BK;
+                    const int k0 = kb * G::BKE;
                     if (!A_MN) {
                         tma_load_4d(map_a, &full[stage], sa, k0, m0, bc1, bc0);
                     } else if (p.a_chunked) {
-                        tma_load_5d(map_a, &full[stage], sa, 0, k0, m0 >> 5, bc1, bc0);
+                        tma_load_5d(map_a, &full[stage], sa, 0, k0, m0 >> G::CH_SHIFT, bc1, bc0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 32; ++j)
-                            tma_load_4d(map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
+                        for (int j = 0; j < BM / G::CH; ++j)
+                            tma_load_4d(map_a, &full[stage], sa + j * G::CHUNK_BYTES, m0 + G::CH * j, k0, bc1, bc0);
                     }
                     if (CL == 1) {
                         if (!B_MN) {
                             tma_load_4d(map_b, &full[stage], sb, k0, n0, bc1, bc0);
                         } else if (p.b_chunked) {
-                            tma_load_5d(map_b, &full[stage], sb, 0, k0, n0 >> 5, bc1, bc0);
+                            tma_load_5d(map_b, &full[stage], sb, 0, k0, n0 >> G::CH_SHIFT, bc1, bc0);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 32; ++j)
-                                tma_load_4d(map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
+                            for (int j = 0; j < BN / G::CH; ++j)
+                                tma_load_4d(map_b, &full[stage], sb + j * G::CHUNK_BYTES, n0 + G::CH * j, k0, bc1, bc0);
                         }
                     } else {
                         // this CTA fetches its half of the B tile for the whole cluster
@@ -598,11 +635,11 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
                             tma_load_4d_mc(map_b, &full[stage], sb + crank * HALF * 128, k0, n0 + crank * HALF, bc1,
                                            bc0, kAll);
                         } else {
-                            constexpr int PER = (BN / 32) / CL;
+                            constexpr int PER = (BN / G::CH) / CL;
 #pragma unroll
                             for (int jj = 0; jj < PER; ++jj) {
                                 const int j = crank * PER + jj;
-                                tma_load_4d_mc(map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0,
+                                tma_load_4d_mc(map_b, &full[stage], sb + j * G::CHUNK_BYTES, n0 + G::CH * j, k0, bc1, bc0,
                                                kAll);
                             }
                         }
@@ -617,7 +654,7 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
     } else if (warp == 1) {
         // ===================================== MMA issuer ========================================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = umma_idesc<ES>(BM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -635,23 +672,16 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
                     const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
                         // K-major : SWIZZLE_128B; 32 bytes along the swizzled row per k-step, 8-row groups 1024 B apart
                         // MN-major: SWIZZLE_128B_BASE32B; 8 k-rows (1024 B) per k-step, 4-row groups 512 B apart,
                         //           32-element MN chunks BK*128 B apart
-                        const uint64_t da = A_MN ? umma_desc(sa + ks * 1024, BK * 128, 512, 1)
+                        const uint64_t da = A_MN ? umma_desc(sa + ks * G::KSTEP_MN_BYTES, G::CHUNK_BYTES, G::MN_SBO, G::MN_LAYOUT)
                                                  : umma_desc(sa + ks * 32, 16, 1024, 2);
-                        const uint64_t db = B_MN ? umma_desc(sb + ks * 1024, BK * 128, 512, 1)
+                        const uint64_t db = B_MN ? umma_desc(sb + ks * G::KSTEP_MN_BYTES, G::CHUNK_BYTES, G::MN_SBO, G::MN_LAYOUT)
                                                  : umma_desc(sb + ks * 32, 16, 1024, 2);
                         const uint32_t accum = (it > 0 || ks > 0) ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t"
-                            ".reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-                            "}" ::"r"(d_tmem),
-                            "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                            : "memory");
+                        umma_issue<ES, 1>(d_tmem, da, db, idesc, accum);
                     }
                     // frees the smem stage once the MMAs above have consumed it (in every CTA that fills it)
                     if (CL == 1) {
@@ -773,10 +803,11 @@ gemm_tf32_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Tc
 //   leader    : waits `full`, issues m256 nBN k8 MMAs, tcgen05.commit(multicast) -> `empty` of both CTAs,
 //               and `tfull` of both CTAs when a tile is complete; waits `tempty` (16 warp arrivals: 8 local,
 //               4 remote) before overwriting an accumulator stage.
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int ES, int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     LG_PDL_TRIGGER();
+    using G = Geo<ES>;
     const CUtensorMap& map_a = maps.a[0];
     const CUtensorMap& map_b = maps.b[0];
     const CUtensorMap& map_c = maps.c[0];
@@ -850,24 +881,24 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     // the leader's barrier collects the bytes of both CTAs
                     if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
-                    const int k0 = kb * BK;
+                    const int k0 = kb * G::BKE;
                     if (!A_MN) {
                         tma_load_4d_2sm(&map_a, &full[stage], sa, k0, m0, bc1, bc0);
                     } else if (p.a_chunked) {
-                        tma_load_5d_2sm(&map_a, &full[stage], sa, 0, k0, m0 >> 5, bc1, bc0);
+                        tma_load_5d_2sm(&map_a, &full[stage], sa, 0, k0, m0 >> G::CH_SHIFT, bc1, bc0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 32; ++j)
-                            tma_load_4d_2sm(&map_a, &full[stage], sa + j * (BK * 128), m0 + 32 * j, k0, bc1, bc0);
+                        for (int j = 0; j < BM / G::CH; ++j)
+                            tma_load_4d_2sm(&map_a, &full[stage], sa + j * G::CHUNK_BYTES, m0 + G::CH * j, k0, bc1, bc0);
                     }
                     if (!B_MN) {
                         tma_load_4d_2sm(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
                     } else if (p.b_chunked) {
-                        tma_load_5d_2sm(&map_b, &full[stage], sb, 0, k0, n0 >> 5, bc1, bc0);
+                        tma_load_5d_2sm(&map_b, &full[stage], sb, 0, k0, n0 >> G::CH_SHIFT, bc1, bc0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < HB / 32; ++j)
-                            tma_load_4d_2sm(&map_b, &full[stage], sb + j * (BK * 128), n0 + 32 * j, k0, bc1, bc0);
+                        for (int j = 0; j < HB / G::CH; ++j)
+                            tma_load_4d_2sm(&map_b, &full[stage], sb + j * G::CHUNK_BYTES, n0 + G::CH * j, k0, bc1, bc0);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -879,7 +910,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =======================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(2 * BM, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = umma_idesc<ES>(2 * BM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -896,20 +927,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant
                     const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t da = A_MN ? umma_desc(sa + ks * 1024, BK * 128, 512, 1)
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        const uint64_t da = A_MN ? umma_desc(sa + ks * G::KSTEP_MN_BYTES, G::CHUNK_BYTES, G::MN_SBO, G::MN_LAYOUT)
                                                  : umma_desc(sa + ks * 32, 16, 1024, 2);
-                        const uint64_t db = B_MN ? umma_desc(sb + ks * 1024, BK * 128, 512, 1)
+                        const uint64_t db = B_MN ? umma_desc(sb + ks * G::KSTEP_MN_BYTES, G::CHUNK_BYTES, G::MN_SBO, G::MN_LAYOUT)
                                                  : umma_desc(sb + ks * 32, 16, 1024, 2);
                         const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t"
-                            ".reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-                            "}" ::"r"(d_tmem),
-                            "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                            : "memory");
+                        umma_issue<ES, 2>(d_tmem, da, db, idesc, accum);
                     }
                     asm volatile(
                         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], "
@@ -1010,50 +1034,57 @@ int load_encode() {
     return 0;
 }
 
-// rank-4 fp32 tensor map: dim0 = contiguous extent, dim1 = strided extent, dim2 = batch1, dim3 = batch0
+// rank-4 tensor map (es = element size: 4 fp32, 2 bf16): dim0 = contiguous extent, dim1 = strided extent,
+// dim2 = batch1, dim3 = batch0
 struct BatchDims {
     int64_t n1, s1, n0, s0;   // extents and element strides of batch1 (inner) and batch0 (outer)
 };
 int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t outer_stride_elems,
-             const BatchDims& bd, int box_inner, int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+             const BatchDims& bd, int box_inner, int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+             int es = 4) {
     cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)bd.n1, (cuuint64_t)bd.n0};
     // a size-1 dim never advances: give it any legal (16-byte multiple, non-zero) stride
-    const int64_t s_outer = outer > 1 ? outer_stride_elems : ((inner + 3) / 4 * 4);
+    const int64_t q = 16 / es;
+    const int64_t s_outer = outer > 1 ? outer_stride_elems : ((inner + q - 1) / q * q);
     const int64_t dflt = s_outer * (outer > 0 ? outer : 1);
-    cuuint64_t strides[3] = {(cuuint64_t)s_outer * 4, (cuuint64_t)(bd.n1 > 1 ? bd.s1 : dflt) * 4,
-                             (cuuint64_t)(bd.n0 > 1 ? bd.s0 : dflt * (bd.n1 > 0 ? bd.n1 : 1)) * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)s_outer * es, (cuuint64_t)(bd.n1 > 1 ? bd.s1 : dflt) * es,
+                             (cuuint64_t)(bd.n0 > 1 ? bd.s0 : dflt * (bd.n1 > 0 ? bd.n1 : 1)) * es};
     cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = g_encode(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                          const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
 }
 
-// rank-5 map of an MN-major operand (k rows of `mn` contiguous elements, row pitch `ld`):
-// (32, k, ceil(mn/32), batch1, batch0) with element strides (1, ld, 32, s1, s0); box = (32, BK, chunks, 1, 1)
+// rank-5 map of an MN-major operand (k rows of `mn` contiguous elements, row pitch `ld`), CH = 128 / es elements
+// per chunk: (CH, k, ceil(mn/CH), batch1, batch0) with element strides (1, ld, CH, s1, s0);
+// box = (CH, k-block, chunks, 1, 1)
 int make_map_chunked(CUtensorMap* map, const void* base, int64_t mn, int64_t k, int64_t ld, const BatchDims& bd,
-                     int box_chunks) {
-    const int64_t chunks = (mn + 31) / 32;
-    cuuint64_t dims[5] = {32, (cuuint64_t)k, (cuuint64_t)chunks, (cuuint64_t)bd.n1, (cuuint64_t)bd.n0};
-    const int64_t s_k = k > 1 ? ld : chunks * 32;
+                     int box_chunks, int es = 4) {
+    const int64_t ch = 128 / es;
+    const int64_t chunks = (mn + ch - 1) / ch;
+    cuuint64_t dims[5] = {(cuuint64_t)ch, (cuuint64_t)k, (cuuint64_t)chunks, (cuuint64_t)bd.n1, (cuuint64_t)bd.n0};
+    const int64_t s_k = k > 1 ? ld : chunks * ch;
     const int64_t dflt = s_k * (k > 0 ? k : 1);
-    cuuint64_t strides[4] = {(cuuint64_t)s_k * 4, 128, (cuuint64_t)(bd.n1 > 1 ? bd.s1 : dflt) * 4,
-                             (cuuint64_t)(bd.n0 > 1 ? bd.s0 : dflt * (bd.n1 > 0 ? bd.n1 : 1)) * 4};
-    cuuint32_t box[5] = {32, (cuuint32_t)BK, (cuuint32_t)box_chunks, 1, 1};
+    cuuint64_t strides[4] = {(cuuint64_t)s_k * es, 128, (cuuint64_t)(bd.n1 > 1 ? bd.s1 : dflt) * es,
+                             (cuuint64_t)(bd.n0 > 1 ? bd.s0 : dflt * (bd.n1 > 0 ? bd.n1 : 1)) * es};
+    cuuint32_t box[5] = {(cuuint32_t)ch, (cuuint32_t)(128 / es), (cuuint32_t)box_chunks, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+    CUresult r = g_encode(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          es == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (chunked) failed with CUresult %d", (int)r);
     return 0;
 }
 // chunks must tile a row exactly: a partial last chunk would read past the end of the row (and, for the last
 // row of a view, possibly past the end of the allocation), which the tensor map cannot clip
-inline bool chunkable(int64_t mn) {
+inline bool chunkable(int64_t mn, int es) {
     static const bool off = getenv("LG_GEMM_NO_CHUNKED") != nullptr;
-    return !off && mn % 32 == 0;
+    return !off && mn % (128 / es) == 0;
 }
 
 // LG_GEMM_SMEM_CUT_KB (compile-time experiment knob): shrink the operand ring by that many KB so that another
@@ -1093,11 +1124,11 @@ constexpr size_t smem2_for() {
            (2 * stages2_for<BN>() + 4) * 8 + 16 + 1024;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int ES, int BN, bool A_MN, bool B_MN>
 int launch_2cta(const TcMaps& maps, const TcParams& p, int grid) {
     constexpr int ST = stages2_for<BN>();
     constexpr size_t smem = smem2_for<BN>();
-    auto kern = gemm_tf32_2cta_kernel<BN, A_MN, B_MN, ST>;
+    auto kern = gemm_tc_2cta_kernel<ES, BN, A_MN, B_MN, ST>;
     static bool attr_done = false;
     if (!attr_done) {
         LG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1122,20 +1153,20 @@ int launch_2cta(const TcMaps& maps, const TcParams& p, int grid) {
     return 0;
 }
 
-template <int BN>
+template <int ES, int BN>
 int launch_2cta_bn(bool a_mn, bool b_mn, const TcMaps& maps,
                    const TcParams& p, int grid) {
-    if (!a_mn && !b_mn) return launch_2cta<BN, false, false>(maps, p, grid);
-    if (!a_mn && b_mn) return launch_2cta<BN, false, true>(maps, p, grid);
-    if (a_mn && !b_mn) return launch_2cta<BN, true, false>(maps, p, grid);
-    return launch_2cta<BN, true, true>(maps, p, grid);
+    if (!a_mn && !b_mn) return launch_2cta<ES, BN, false, false>(maps, p, grid);
+    if (!a_mn && b_mn) return launch_2cta<ES, BN, false, true>(maps, p, grid);
+    if (a_mn && !b_mn) return launch_2cta<ES, BN, true, false>(maps, p, grid);
+    return launch_2cta<ES, BN, true, true>(maps, p, grid);
 }
 
-template <int BN, bool A_MN, bool B_MN, int CL>
+template <int ES, int BN, bool A_MN, bool B_MN, int CL>
 int launch_cfg(const TcMaps& maps, const TcParams& p, int grid) {
     constexpr int ST = stages_for<BN>();
     constexpr size_t smem = smem_for<BN>();
-    auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, ST, CL>;
+    auto kern = gemm_tc_kernel<ES, BN, A_MN, B_MN, ST, CL>;
     static bool attr_done = false;
     if (!attr_done) {
         LG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1160,24 +1191,43 @@ int launch_cfg(const TcMaps& maps, const TcParams& p, int grid) {
     return 0;
 }
 
-template <int BN, int CL>
+template <int ES, int BN, int CL>
 int launch_bn(bool a_mn, bool b_mn, const TcMaps& maps, const TcParams& p, int grid) {
-    if (!a_mn && !b_mn) return launch_cfg<BN, false, false, CL>(maps, p, grid);
-    if (!a_mn && b_mn) return launch_cfg<BN, false, true, CL>(maps, p, grid);
-    if (a_mn && !b_mn) return launch_cfg<BN, true, false, CL>(maps, p, grid);
-    return launch_cfg<BN, true, true, CL>(maps, p, grid);
+    if (!a_mn && !b_mn) return launch_cfg<ES, BN, false, false, CL>(maps, p, grid);
+    if (!a_mn && b_mn) return launch_cfg<ES, BN, false, true, CL>(maps, p, grid);
+    if (a_mn && !b_mn) return launch_cfg<ES, BN, true, false, CL>(maps, p, grid);
+    return launch_cfg<ES, BN, true, true, CL>(maps, p, grid);
+}
+template <int ES>
+int launch_any(bool pair_mma, int bn, bool a_mn, bool b_mn, const TcMaps& maps, const TcParams& p, int grid) {
+    if (pair_mma) {
+        switch (bn) {
+            case 256: return launch_2cta_bn<ES, 256>(a_mn, b_mn, maps, p, grid);
+            case 192: return launch_2cta_bn<ES, 192>(a_mn, b_mn, maps, p, grid);
+            case 128: return launch_2cta_bn<ES, 128>(a_mn, b_mn, maps, p, grid);
+            default: return launch_2cta_bn<ES, 64>(a_mn, b_mn, maps, p, grid);
+        }
+    }
+    switch (bn) {
+        case 256: return launch_bn<ES, 256, 1>(a_mn, b_mn, maps, p, grid);
+        case 192: return launch_bn<ES, 192, 1>(a_mn, b_mn, maps, p, grid);
+        case 128: return launch_bn<ES, 128, 1>(a_mn, b_mn, maps, p, grid);
+        default: return launch_bn<ES, 64, 1>(a_mn, b_mn, maps, p, grid);
+    }
 }
 
-bool k_major(int64_t s_mn, int64_t s_k, int64_t extent_mn) { return s_k == 1 && (s_mn % 4 == 0 || extent_mn == 1); }
-bool mn_major(int64_t s_mn, int64_t s_k, int64_t extent_k) { return s_mn == 1 && (s_k % 4 == 0 || extent_k == 1); }
+// strides must be 16-byte multiples for TMA: q = 16 / element size elements
+bool k_major(int64_t s_mn, int64_t s_k, int64_t extent_mn, int q) { return s_k == 1 && (s_mn % q == 0 || extent_mn == 1); }
+bool mn_major(int64_t s_mn, int64_t s_k, int64_t extent_k, int q) { return s_mn == 1 && (s_k % q == 0 || extent_k == 1); }
 
 struct Plan {
     int bn, splits, tiles_m, tiles_n, kblocks, kper;
 };
 
-Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split, bool tail_ok = false) {
+Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split, bool tail_ok, int es) {
     const int sms = gemm_sms();
-    const int kblocks = (int)((K + BK - 1) / BK);
+    const int bke = 128 / es;            // elements per k-block
+    const int kblocks = (int)((K + bke - 1) / bke);
     Plan best{};
     double best_score = -1.0;
     const int cands[4] = {256, 192, 128, 64};
@@ -1245,21 +1295,26 @@ Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_sp
 
 namespace lg {
 
+// tf32 mode: fp32 operands.  bf16 mode: bf16 operands (dtype LG_BF16; strides in bf16 elements) -- asked with
+// dtype LG_F32 it answers for the bf16 staging copy of an fp32 operand with the same element strides (pass no
+// pointers then).  The result is fp32 in both modes.
 int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, const void* b, const void* c) {
-    if (mode != LG_GEMM_TF32_TC || dtype != LG_F32) return 0;
+    if (!((mode == LG_GEMM_TF32_TC && dtype == LG_F32) || (mode == LG_GEMM_BF16_TC && (dtype == LG_BF16 || dtype == LG_F32))))
+        return 0;
+    const int q = mode == LG_GEMM_BF16_TC ? 8 : 4;     // operand elements per 16 bytes
     const int64_t batches = d->batch0 * d->batch1;
     if (batches < 1 || batches > 65535) return 0;
     if (d->M < 1 || d->N < 1 || d->K < 1) return 0;
     // batch strides go into the TMA descriptor: 16-byte multiples, no broadcast (stride 0) over a real batch dim
     const int64_t bs[6][2] = {{d->batch1, d->sa_b1}, {d->batch0, d->sa_b0}, {d->batch1, d->sb_b1},
                               {d->batch0, d->sb_b0}, {d->batch1, d->sc_b1}, {d->batch0, d->sc_b0}};
-    for (auto& e : bs)
-        if (e[0] > 1 && (e[1] <= 0 || e[1] % 4 != 0)) return 0;
+    for (int i = 0; i < 6; ++i)
+        if (bs[i][0] > 1 && (bs[i][1] <= 0 || bs[i][1] % (i < 4 ? q : 4) != 0)) return 0;
     if (d->M > 0x7fffffff || d->N > 0x7fffffff || d->K > 0x7fffffff) return 0;
     // tiny problems are launch bound either way; keep them on the exact path
     if ((double)d->M * d->N * d->K * (double)batches < 64.0 * 64.0 * 64.0 * 8) return 0;
-    const bool a_ok = k_major(d->sa_m, d->sa_k, d->M) || mn_major(d->sa_m, d->sa_k, d->K);
-    const bool b_ok = k_major(d->sb_n, d->sb_k, d->N) || mn_major(d->sb_n, d->sb_k, d->K);
+    const bool a_ok = k_major(d->sa_m, d->sa_k, d->M, q) || mn_major(d->sa_m, d->sa_k, d->K, q);
+    const bool b_ok = k_major(d->sb_n, d->sb_k, d->N, q) || mn_major(d->sb_n, d->sb_k, d->K, q);
     const bool c_ok = d->sc_n == 1 && (d->sc_m % 4 == 0 || d->M == 1);
     if (!a_ok || !b_ok || !c_ok) return 0;
     if (a && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15)) return 0;
@@ -1270,9 +1325,12 @@ int gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d, const void* a, c
 // pointers run as ONE launch of the 1-CTA kernel (e.g. the Q, K and V projections of an attention block:
 // 3 x 128 tiles instead of three one-wave launches).  Several groups may name the same C: with
 // accumulate they all reduce-add into it (dX = sum_g dY_g W_g).
-int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
+int gemm_tc_grouped(int mode, const LgGemmDesc* d, int groups, const void* const* a, const void* const* b, void* const* c,
                     const void* const* bias, int accumulate, int epi_op, void* aux, int64_t aux_ld, double alpha) {
     if (load_encode()) return 1;
+    const int es = mode == LG_GEMM_BF16_TC ? 2 : 4;    // operand element size
+    const int q = 16 / es, bke = 128 / es, ch = 128 / es;
+    const CUtensorMapSwizzle mn_swz = es == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     if (epi_op == 1 || epi_op == 2) {
         LG_REQUIRE(groups == 1 && d->batch0 * d->batch1 == 1 && !accumulate, "gemm_tc: epilogue ops need one plain GEMM");
         LG_REQUIRE(aux && (((uintptr_t)aux) & 15) == 0 && aux_ld % 4 == 0 && aux_ld >= d->N && d->N % 4 == 0,
@@ -1285,8 +1343,8 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     }
     LG_REQUIRE(groups >= 1 && groups <= LG_MAX_GROUPS, "gemm_tc: 1..%d groups per launch", LG_MAX_GROUPS);
     const int64_t M = d->M, N = d->N, K = d->K;
-    const bool a_mn = !k_major(d->sa_m, d->sa_k, M);
-    const bool b_mn = !k_major(d->sb_n, d->sb_k, N);
+    const bool a_mn = !k_major(d->sa_m, d->sa_k, M, q);
+    const bool b_mn = !k_major(d->sb_n, d->sb_k, N, q);
     const int64_t batches = d->batch0 * d->batch1;
     // every group naming the same C: one K-concatenated product C (+)= sum_g A_g B_g, accumulated in TMEM
     bool same_c = groups > 1;
@@ -1301,7 +1359,7 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     // split-K partials meet in C by reduce-add: C must be zeroed first (done below for one plain matrix) or
     // already hold the value being accumulated into
     Plan pl = choose_plan(M, N, K, batches * n_problems, !epi_op && (accumulate || batches * n_problems == 1),
-                          !epi_op && n_problems == 1 && batches == 1 && !same_c);
+                          !epi_op && n_problems == 1 && batches == 1 && !same_c, es);
     if (epi_op >= 3) {
         // the whole row must live in one tile
         const int bn = N <= 64 ? 64 : 128;
@@ -1320,18 +1378,18 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     const int cl = pair_mma ? 2 : 1;
     TcMaps maps;
     TcParams p;
-    const bool a_ch = a_mn && chunkable(M), b_ch = b_mn && chunkable(N);
+    const bool a_ch = a_mn && chunkable(M, es), b_ch = b_mn && chunkable(N, es);
     p.a_chunked = a_ch ? 1 : 0;
     p.b_chunked = b_ch ? 1 : 0;
     for (int g = 0; g < groups; ++g) {
         // operand maps: K-major -> (inner = K, outer = rows); MN-major -> (inner = rows, outer = K)
-        if (!a_mn) rc = make_map(&maps.a[g], a[g], K, M, d->sa_m, ba, BK, BM);
-        else if (a_ch) rc = make_map_chunked(&maps.a[g], a[g], M, K, d->sa_k, ba, BM / 32);
-        else rc = make_map(&maps.a[g], a[g], M, K, d->sa_k, ba, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!a_mn) rc = make_map(&maps.a[g], a[g], K, M, d->sa_m, ba, bke, BM, CU_TENSOR_MAP_SWIZZLE_128B, es);
+        else if (a_ch) rc = make_map_chunked(&maps.a[g], a[g], M, K, d->sa_k, ba, BM / ch, es);
+        else rc = make_map(&maps.a[g], a[g], M, K, d->sa_k, ba, ch, bke, mn_swz, es);
         if (rc) return rc;
-        if (!b_mn) rc = make_map(&maps.b[g], b[g], K, N, d->sb_n, bb, BK, pl.bn / cl);
-        else if (b_ch) rc = make_map_chunked(&maps.b[g], b[g], N, K, d->sb_k, bb, pl.bn / cl / 32);
-        else rc = make_map(&maps.b[g], b[g], N, K, d->sb_k, bb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (!b_mn) rc = make_map(&maps.b[g], b[g], K, N, d->sb_n, bb, bke, pl.bn / cl, CU_TENSOR_MAP_SWIZZLE_128B, es);
+        else if (b_ch) rc = make_map_chunked(&maps.b[g], b[g], N, K, d->sb_k, bb, pl.bn / cl / ch, es);
+        else rc = make_map(&maps.b[g], b[g], N, K, d->sb_k, bb, ch, bke, mn_swz, es);
         if (rc) return rc;
         rc = make_map(&maps.c[g], c[g], N, M, d->sc_m, bc, 32, 32);
         if (rc) return rc;
@@ -1404,38 +1462,25 @@ int gemm_tc_grouped(const LgGemmDesc* d, int groups, const void* const* a, const
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
-    if (pair_mma) {
-        switch (pl.bn) {
-            case 256: return launch_2cta_bn<256>(a_mn, b_mn, maps, p, grid);
-            case 192: return launch_2cta_bn<192>(a_mn, b_mn, maps, p, grid);
-            case 128: return launch_2cta_bn<128>(a_mn, b_mn, maps, p, grid);
-            default: return launch_2cta_bn<64>(a_mn, b_mn, maps, p, grid);
-        }
-    }
-    switch (pl.bn) {
-        case 256: return launch_bn<256, 1>(a_mn, b_mn, maps, p, grid);
-        case 192: return launch_bn<192, 1>(a_mn, b_mn, maps, p, grid);
-        case 128: return launch_bn<128, 1>(a_mn, b_mn, maps, p, grid);
-        default: return launch_bn<64, 1>(a_mn, b_mn, maps, p, grid);
-    }
+    return es == 4 ? launch_any<4>(pair_mma, pl.bn, a_mn, b_mn, maps, p, grid)
+                   : launch_any<2>(pair_mma, pl.bn, a_mn, b_mn, maps, p, grid);
 }
 
 int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate) {
-    (void)mode;
     const void* av[1] = {a};
     const void* bv[1] = {b};
     void* cv[1] = {c};
     const void* biasv[1] = {bias};
-    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate, 0, nullptr, 0, 0.0);
+    return gemm_tc_grouped(mode, d, 1, av, bv, cv, bias ? biasv : nullptr, accumulate, 0, nullptr, 0, 0.0);
 }
 
-int gemm_tc_epilogue(const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op, void* aux,
-                     int64_t aux_ld, double alpha) {
+int gemm_tc_epilogue(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int epi_op,
+                     void* aux, int64_t aux_ld, double alpha) {
     const void* av[1] = {a};
     const void* bv[1] = {b};
     void* cv[1] = {c};
     const void* biasv[1] = {bias};
-    return gemm_tc_grouped(d, 1, av, bv, cv, bias ? biasv : nullptr, 0, epi_op, aux, aux_ld, alpha);
+    return gemm_tc_grouped(mode, d, 1, av, bv, cv, bias ? biasv : nullptr, 0, epi_op, aux, aux_ld, alpha);
 }
 
 int gemm_set_sm_limit(int n) {

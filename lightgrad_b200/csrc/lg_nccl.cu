@@ -55,6 +55,12 @@ int load_api() {
 
 }  // namespace
 
+static int ensure_events() {
+    if (!g_ev_fork) LG_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+    if (!g_ev_join) LG_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    return 0;
+}
+
 extern "C" {
 
 int lg_nccl_unique_id(void* id128) {
@@ -75,13 +81,12 @@ int lg_nccl_init(const void* id128, int world, int rank) {
     LG_NCCL(api.CommInitRank(&g_comm_nccl, world, id, rank));
     g_world = world;
     g_rank = rank;
-    LG_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-    LG_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
-    return 0;
+    return ensure_events();
 }
 
 int lg_nccl_fork(void) {
-    LG_REQUIRE(g_comm_nccl, "lg_nccl_fork: communicator not initialised");
+    LG_INIT();
+    if (ensure_events()) return 1;
     LG_CUDA(cudaEventRecord(g_ev_fork, stream()));
     LG_CUDA(cudaStreamWaitEvent(comm_stream(), g_ev_fork, 0));
     // weight gradients are accumulated on the side stream: the collective must see those writes too
@@ -90,7 +95,8 @@ int lg_nccl_fork(void) {
 }
 
 int lg_nccl_wait(void) {
-    LG_REQUIRE(g_comm_nccl, "lg_nccl_wait: communicator not initialised");
+    LG_INIT();
+    if (ensure_events()) return 1;
     LG_CUDA(cudaEventRecord(g_ev_join, comm_stream()));
     LG_CUDA(cudaStreamWaitEvent(stream(), g_ev_join, 0));
     comm_release_deferred();

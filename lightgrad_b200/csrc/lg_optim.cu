@@ -10,8 +10,10 @@
 // bias corrections differ per tensor: they arrive as per-segment scalars.
 // Algorithmic bytes per parameter: SGD 12 (+8 with momentum), Adam 28.
 #include "lg_ew.cuh"
+#include "lg_adam.cuh"
 
 using namespace lg;
+using namespace lg::adam;
 
 namespace {
 
@@ -37,69 +39,6 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
         float d = neg_lr * g[j] + (delta ? mom * delta[j] : 0.0f);
         if (delta) delta[j] = d;
         p[j] += d;
-    }
-}
-
-// per-tensor bias corrections 1 - beta^t with t = *t_dev + i + 1, evaluated in double like python does;
-// one CTA, so the counter can be advanced after every thread has read it
-__global__ void adam_prep_kernel(int n_seg, int64_t* __restrict__ t_dev, double b1, double b2,
-                                 float* __restrict__ c1, float* __restrict__ c2, int seg_offset, int t_advance) {
-    LG_PDL_TRIGGER();
-    const int64_t t0 = *t_dev;
-    for (int i = threadIdx.x; i < n_seg; i += blockDim.x) {
-        const double t = (double)(t0 + seg_offset + i + 1);
-        const float f1 = (float)(1.0 - pow(b1, t)), f2 = (float)(1.0 - pow(b2, t));
-        c1[i] = f1;
-        c2[i] = f2;
-        // correctly rounded reciprocals of the fp32 corrections (for the exact-quotient sequence below)
-        c1[n_seg * 2 + i] = (float)(1.0 / (double)f1);
-        c2[n_seg * 2 + i] = (float)(1.0 / (double)f2);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *t_dev = t0 + t_advance;
-}
-
-// arenas are padded so that every tensor starts on a 64-element boundary: a float4 never straddles tensors
-__device__ __forceinline__ int adam_segment(int seg, int64_t e, int n_seg, const int64_t* __restrict__ seg_end) {
-    // (e already carries the offset of this launch's range inside the arena: seg_end holds arena offsets)
-    if (e < seg_end[seg] && (seg == 0 || e >= seg_end[seg - 1])) return seg;
-    int lo = 0, hi = n_seg - 1;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (seg_end[mid] > e) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-// a / d as fma(fma(-q0, d, a), r, q0) with q0 = a * r and r the correctly rounded reciprocal of d: the
-// correctly rounded quotient (Markstein) for normal-range operands -- what div.rn's fast path computes, minus
-// its range check and the slow path.  The three IEEE divisions per element made this kernel issue-bound
-// (683 us for 110 M parameters against a 500 us memory floor); with this sequence it streams at the floor.
-__device__ __forceinline__ float quot(float a, float d, float r) {
-    const float q0 = a * r;
-    return fmaf(fmaf(-q0, d, a), r, q0);
-}
-__device__ __forceinline__ float rcp_approx(float d) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-    return r;
-}
-
-template <bool BELIEF>
-__device__ __forceinline__ void adam_update4(float4& pv, const float4& gv, float4& mv, float4& vv, float d1, float d2,
-                                             float r1, float r2, float neg_lr, float b1, float b2, float omb1,
-                                             float omb2, float eps) {
-    float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float gi = gp[k];
-        const float mi = b1 * mp[k] + omb1 * gi;
-        const float r = BELIEF ? (gi - mi) : gi;
-        const float vi = b2 * vp[k] + omb2 * (r * r);
-        mp[k] = mi;
-        vp[k] = vi;
-        const float den = __fsqrt_rn(quot(vi, d2, r2)) + eps;      // >= eps: normal range
-        pp[k] += quot(neg_lr * quot(mi, d1, r1), den, rcp_approx(den));
     }
 }
 

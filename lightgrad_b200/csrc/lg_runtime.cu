@@ -148,6 +148,10 @@ void tmp_free(void* p) {
     else g_cache->put(p);
 }
 
+void comm_defer_free(void* p) {
+    if (p) g_comm_deferred.push_back(p);
+}
+
 // called once the compute stream has been ordered after the collective stream (lg_nccl_wait)
 void comm_release_deferred() {
     for (void* p : g_comm_deferred) g_cache->put(p);
@@ -198,7 +202,14 @@ static int do_init(int device) {
                          prop.minor);
     g_sms = prop.multiProcessorCount;
     LG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    LG_CUDA(cudaStreamCreateWithFlags(&g_comm, cudaStreamNonBlocking));
+    {
+        // the collective stream gets the highest priority: its few small CTAs (NCCL, or the multicast exchange kernel)
+        // are placed ahead of the next compute kernel's CTAs whenever an SM has room
+        int lo_prio = 0, hi_prio = 0;
+        LG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        static const bool flat = getenv("LG_COMM_NO_PRIORITY") != nullptr;
+        LG_CUDA(cudaStreamCreateWithPriority(&g_comm, cudaStreamNonBlocking, flat ? lo_prio : hi_prio));
+    }
     LG_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
     LG_CUDA(cudaEventCreateWithFlags(&g_ev_side_fork, cudaEventDisableTiming));
     LG_CUDA(cudaEventCreateWithFlags(&g_ev_side_join, cudaEventDisableTiming));

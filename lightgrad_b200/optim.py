@@ -48,6 +48,24 @@ class _Arena(object):
             p._grad = g
         self.seg_end = None
 
+    def rebase(self, params, param_ptr, grad_ptr, keep=None):
+        """Move both arenas to memory the caller provides (the NVLink multicast region of the data-parallel
+        wrapper): contents are copied, the parameter / gradient objects keep their identity and become views of the
+        new arenas.  Captured CUDA graphs that recorded the old addresses must be re-captured."""
+        rt = self.rt
+        new_p = rt.ExternalBuffer(param_ptr, max(self.total, 1) * 4, keep)
+        new_g = rt.ExternalBuffer(grad_ptr, max(self.total, 1) * 4, keep)
+        self.adopt_grads(params)
+        rt.api.memcpy_d2d(new_p.ptr, self.param_buf.ptr, self.total * 4)
+        rt.api.memcpy_d2d(new_g.ptr, self.grad_buf.ptr, self.total * 4)
+        rt.synchronize()
+        self.param_buf, self.grad_buf = new_p, new_g
+        for p, o in zip(params, self.offsets):
+            n = p.numel()
+            p._set_data(rt.ArenaSlice(new_p, o * 4, n * 4))
+            p._offset = 0
+            p._grad = self.T(rt.ArenaSlice(new_g, o * 4, n * 4), p.shape, None, 0, np.float32, False)
+
     def state(self):
         b = self.rt.Buffer(max(self.total, 1) * 4)
         self.rt.api.memset(b.ptr, 0, self.total * 4)
@@ -123,6 +141,7 @@ class Optimizer(object):
             if self.arena is not None:
                 self.arena.adopt_grads(self.parameters)
                 self._fused_step(self.arena)
+                self.arena.param_buf._bf16 = None      # a bf16 staging copy of the parameters is stale now
             else:
                 for i, p in enumerate(self.parameters):
                     p += self.compute_delta(p.grad, i)
@@ -154,6 +173,16 @@ class SGD(Optimizer):
             self._delta = a.state()
         a.rt.api.sgd_step(a.param_buf.ptr, a.grad_buf.ptr, self._delta.ptr if self._delta is not None else None,
                           a.total, float(self.lr), float(self.momentum))
+
+    def _mc_exchange_range(self, a, region, i0, i1, lo, hi, rank, world, last):
+        """Parameters i0 .. i1-1 = arena elements [lo, hi): gradient reduce-scatter, SGD update of this rank's share
+        and parameter all-gather in one kernel over the NVLink multicast region (lg_mc_exchange_step)."""
+        if self.momentum != 0.0 and self._delta is None:
+            self._delta = a.state()
+        goff, poff, foff = region
+        a.rt.api.mc_exchange_step(2, goff, poff, foff, lo, hi, rank, world,
+                                  self._delta.ptr if self._delta is not None else None, None, 0, None, None,
+                                  float(self.lr), 0.0, 0.0, 0.0, float(self.momentum), i0, 0)
 
 
 class Adam(Optimizer):
@@ -212,6 +241,21 @@ class Adam(Optimizer):
         a.rt.api.adam_step(self._belief, a.param_buf.ptr + lo * 4, a.grad_buf.ptr + lo * 4, self._m.ptr + lo * 4,
                            self._v.ptr + lo * 4, hi - lo, i1 - i0, seg.ptr + i0 * 8, self._t_dev.ptr, float(self.lr),
                            float(self.b1), float(self.b2), float(self.eps), lo, i0, P if last else 0)
+        if last:
+            self.t += P
+
+    def _mc_exchange_range(self, a, region, i0, i1, lo, hi, rank, world, last):
+        """Parameters i0 .. i1-1 = arena elements [lo, hi): gradient reduce-scatter through the NVLink switch, Adam on
+        this rank's 1/world share, all-gather of the new parameters -- one kernel (lg_mc_exchange_step).  Step
+        counter and bias corrections as in ``_fused_step_range``."""
+        P = len(self.parameters)
+        if self._m is None:
+            self._init_state(a)
+        seg = a.segments(self.parameters)
+        goff, poff, foff = region
+        a.rt.api.mc_exchange_step(self._belief, goff, poff, foff, lo, hi, rank, world, self._m.ptr, self._v.ptr,
+                                  i1 - i0, seg.ptr + i0 * 8, self._t_dev.ptr, float(self.lr), float(self.b1),
+                                  float(self.b2), float(self.eps), 0.0, i0, P if last else 0)
         if last:
             self.t += P
 

@@ -5,8 +5,11 @@ lightgrad/autograd/func.py:18-20).  Only the batch axis of examp
 examples/bert.py shards naturally, so the exchange step is exactly one collective per iteration: an
 averaging all-reduce of the parameter gradients, between ``loss.backward()`` and ``optimizer.step()``.
 
-  * cuda backend: the optimizer keeps all gradients in one flat fp32 arena (optim._Arena), so the
-    exchange is a single in-place ncclAllReduce(avg) over NVLink on that arena (C-ABI lg_nccl_*).
+  * cuda backend: the optimizer keeps all gradients in one flat fp32 arena (optim._Arena).  Default exchange
+    ("nvls"): both arenas move into an NVLink multicast region and every bucket of gradients is reduce-scattered
+    through the switch, updated by the optimizer on the owning rank's 1/N share and all-gathered as new parameters
+    by ONE kernel that runs next to the GEMMs of backward (C-ABI lg_mc_*, csrc/lg_mc.cu).  Fallback / explicit
+    ``LG_DP_EXCHANGE=nccl``: in-place ncclAllReduce(avg) per bucket (C-ABI lg_nccl_*), then the optimizer.
   * any other backend (the CPU oracle in the gloo tests): gradients are averaged tensor by tensor
     through ``comm.allreduce_avg_numpy``.
 
@@ -89,6 +92,43 @@ def default_comm():
     return GlooComm()
 
 
+def _pass_fd(comm, fd):
+    """Hand rank 0's file descriptor to every other rank of this node (SCM_RIGHTS over a unix socket).  Returns the
+    local descriptor number on every rank."""
+    import socket
+    if comm.world == 1:
+        return fd
+    if comm.rank == 0:
+        path = '/tmp/lg_mc_%d_%s.sock' % (os.getpid(), os.environ.get('MASTER_PORT', '0'))
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(path)
+        srv.listen(comm.world)
+        comm.broadcast_bytes(path.encode(), root=0)
+        try:
+            srv.settimeout(120)
+            for _ in range(comm.world - 1):
+                conn, _addr = srv.accept()
+                socket.send_fds(conn, [b'fd'], [fd])
+                conn.recv(1)                       # the peer has the descriptor
+                conn.close()
+        finally:
+            srv.close()
+            os.unlink(path)
+        return fd
+    path = comm.broadcast_bytes(None, root=0).decode()
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    c.settimeout(120)
+    c.connect(path)
+    _msg, fds, _flags, _addr = socket.recv_fds(c, 16, 1)
+    c.send(b'k')
+    c.close()
+    return fds[0]
+
+
 def shard_rows(n_rows, rank, world):
     """Contiguous, equal slice [lo, hi) of the batch for ``rank``."""
     assert n_rows % world == 0, "global batch %d is not divisible by %d ranks" % (n_rows, world)
@@ -106,12 +146,16 @@ class DataParallel(object):
         optimizer.step()
     """
 
-    def __init__(self, model, optimizer, comm=None, broadcast=True):
+    def __init__(self, model, optimizer, comm=None, broadcast=True, exchange=None):
+        """``exchange``: 'nvls' | 'nccl' | 'auto' (default: $LG_DP_EXCHANGE or 'auto' = nvls when the GPUs offer NVLink
+        multicast and the optimizer has a fused exchange kernel, else nccl)."""
         self.model, self.optimizer = model, optimizer
         self.comm = comm if comm is not None else default_comm()
         self.rank, self.world = self.comm.rank, self.comm.world
         self.arena = getattr(optimizer, 'arena', None)
         self._nccl = False
+        self.exchange = 'nccl'
+        self._mc = None
         if self.world > 1 and self.arena is not None:
             rt = self.arena.rt
             ident = None
@@ -123,16 +167,85 @@ class DataParallel(object):
             idbuf = np.frombuffer(ident, dtype=np.uint8).copy()
             rt.api.nccl_init(idbuf.ctypes.data, self.world, self.rank)
             self._nccl = True
+        want = (exchange or os.environ.get('LG_DP_EXCHANGE', 'auto')).lower()
+        single = self.world == 1 and want == 'nvls'          # a team of one: exercises the whole path on one GPU
+        if self.arena is not None and want in ('auto', 'nvls') and (self._nccl or single) \
+                and hasattr(optimizer, '_mc_exchange_range'):
+            if self._setup_multicast():
+                self.exchange = 'nvls'
+            elif want == 'nvls' and self.rank == 0:
+                import sys
+                sys.stderr.write("lightgrad_b200: NVLink multicast exchange unavailable, using NCCL all-reduce\n")
         if broadcast and self.world > 1:
             self.broadcast_parameters()
 
     def shard(self, n_rows):
         return shard_rows(n_rows, self.rank, self.world)
 
+    def _all_ok(self, ok):
+        """True only when every rank says so."""
+        return self.comm.max_float(0.0 if ok else 1.0) == 0.0
+
+    def _setup_multicast(self):
+        """Create the multicast region (rank 0 creates the object, the others import it), bind this GPU's memory to
+        it and move both optimizer arenas there.  Every rank takes the same decision; on any failure all fall back."""
+        import ctypes as C
+        a = self.arena
+        api = a.rt.api
+        yes = C.c_int(0)
+        try:
+            api.mc_supported(C.byref(yes))
+        except Exception:
+            yes.value = 0
+        if not self._all_ok(bool(yes.value)):
+            return False
+        region, goff, poff, foff = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        created, err = False, None
+        try:
+            api.mc_region_bytes(a.total * 4, self.world, C.byref(region), C.byref(goff), C.byref(poff), C.byref(foff))
+            fd = C.c_int(-1)
+            if self.rank == 0:
+                api.mc_create(region.value, self.world, C.byref(fd))
+                created = True
+        except Exception as exc:
+            err = exc
+        if not self._all_ok(err is None):
+            if created:
+                api.mc_release()
+            return False
+        try:
+            local_fd = _pass_fd(self.comm, fd.value)
+            if self.rank != 0:
+                api.mc_import(local_fd, region.value, self.world)
+                created = True
+            if local_fd >= 0:
+                os.close(local_fd)
+            api.mc_add_device()
+        except Exception as exc:
+            err = exc
+        if not self._all_ok(err is None):          # (also the barrier cuMulticastBindMem needs: every device was added)
+            if created:
+                api.mc_release()
+            return False
+        local, mcva = C.c_void_p(0), C.c_void_p(0)
+        try:
+            api.mc_bind(C.byref(local), C.byref(mcva))
+        except Exception as exc:
+            err = exc
+        if not self._all_ok(err is None):
+            api.mc_release()
+            return False
+        a.rebase(self.optimizer.parameters, local.value + poff.value, local.value + goff.value, keep=self)
+        self._mc = (goff.value, poff.value, foff.value)
+        self._buckets = None
+        self.comm.barrier()
+        return True
+
     def broadcast_parameters(self, root=0):
         if self._nccl:
             a = self.arena
             a.rt.api.nccl_broadcast(a.param_buf.ptr, a.total * 4, root)
+            a.param_buf._bf16 = None
             return
         for p in self.optimizer.parameters:
             data = self.comm.broadcast_bytes(p.numpy().tobytes() if self.rank == root else None, root=root)
@@ -148,6 +261,10 @@ class DataParallel(object):
         # Measured (2 GPUs, local batch 128): 30.56 ms pipelined vs 30.44 ms plain -- whatever runs on the
         # communication stream competes with the persistent one-CTA-per-SM GEMMs of backward for the same SMs, so
         # moving the optimizer there buys nothing today.  Off unless LG_DP_PIPELINED_STEP=1.
+        if self.exchange == 'nvls':
+            # gradient reduce-scatter + optimizer + parameter all-gather, one kernel per bucket, overlapped with backward
+            self.backward(loss, bucket_bytes, _step_buckets=True)
+            return
         fused = getattr(self.optimizer, '_fused_step_range', None)
         if self.world == 1 or not self._nccl or fused is None or os.environ.get('LG_DP_NO_OVERLAP') \
                 or not os.environ.get('LG_DP_PIPELINED_STEP'):
@@ -165,7 +282,8 @@ class DataParallel(object):
         The optimizer (compute stream) waits for the communication stream at the end."""
         if bucket_bytes is None:
             bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '64')) << 20
-        if self.world == 1 or not self._nccl or os.environ.get('LG_DP_NO_OVERLAP'):
+        nvls_step = _step_buckets and self.exchange == 'nvls'
+        if not nvls_step and (self.world == 1 or not self._nccl or os.environ.get('LG_DP_NO_OVERLAP')):
             loss.backward()
             self.sync_gradients()
             return
@@ -173,8 +291,8 @@ class DataParallel(object):
         a, params = self.arena, self.optimizer.parameters
         a.adopt_grads(params)
         if getattr(self, '_buckets', None) is None:
-            ends = [o + p.numel() for p, o in zip(params, a.offsets)]
-            ends[-1] = a.total
+            # a parameter's slot runs to the next parameter's (64-element aligned) offset: the zero padding travels along
+            ends = list(a.offsets[1:]) + [a.total]
             self._bucket_of, self._buckets = [], []      # per param -> bucket; bucket -> [lo, hi, n_params]
             lo, count = 0, 0
             for i, hi in enumerate(ends):
@@ -200,6 +318,10 @@ class DataParallel(object):
             launched[b] = True
             n_launched[0] += 1
             api.nccl_fork()                                   # comm stream waits for the gradients written so far
+            if nvls_step:
+                self.optimizer._mc_exchange_range(a, self._mc, first_param[b], first_param[b] + count, lo, hi,
+                                                  self.rank, self.world, last=n_launched[0] == n_buckets)
+                return
             api.nccl_allreduce_f32(a.grad_buf.ptr + lo * 4, hi - lo, 1, 1)
             if _step_buckets:
                 # the optimizer update of this bucket, behind its all-reduce on the communication stream
@@ -236,6 +358,8 @@ class DataParallel(object):
             if not launched[b]:
                 launch(b)
         api.nccl_wait()                                       # compute stream waits for every bucket
+        if _step_buckets:
+            a.param_buf._bf16 = None                          # the parameters changed: a bf16 staging copy is stale
 
     def sync_gradients(self):
         """Average ``.grad`` of every parameter over the ranks (in place)."""
@@ -254,9 +378,35 @@ class DataParallel(object):
 
     def exchange_report(self, rt, comm, barrier, reps=5):
         """The gradient exchange on its own (timed with CUDA events, max over ranks), for bench.py's `comm` object."""
+        a = self.arena
+        if self.exchange == 'nvls':
+            # the exchange kernel alone over the whole arena, without an update (kind 3: parameters written back as read)
+            goff, poff, foff = self._mc
+            nbytes = a.total * 4
+
+            def run():
+                rt.api.nccl_fork()
+                rt.api.mc_exchange_step(3, goff, poff, foff, 0, a.total, self.rank, self.world, None, None, 0, None,
+                                        None, 0.0, 0.0, 0.0, 0.0, 0.0, 0, 0)
+                rt.api.nccl_wait()
+            for _ in range(2):
+                run()
+            barrier()
+            c0 = rt.Event().record()
+            for _ in range(reps):
+                run()
+            c1 = rt.Event().record()
+            c1.synchronize()
+            ms = comm.max_float(c0.elapsed_ms(c1)) / reps
+            return {'exchange': 'nvls', 'exchange_bytes_per_gpu_each_way': int(nbytes), 'exchange_ms_alone': round(ms, 3),
+                    # per GPU the switch pulls the whole gradient arena (reduce-scatter) and pushes the whole
+                    # parameter arena (all-gather): bytes / time is the NVLink rate per direction
+                    'nvlink_gbps_per_direction': round(nbytes / (ms / 1e3) / 1e9, 1),
+                    'note': 'multimem.ld_reduce reduce-scatter + multimem.st all-gather of the whole arena (no optimizer '
+                            'update), alone on the GPU; in the step this work is fused with Adam and runs per bucket '
+                            'next to the GEMMs of backward'}
         if not self._nccl:
             return {}
-        a = self.arena
         nbytes = a.total * 4
         for _ in range(2):
             rt.api.nccl_allreduce_f32(a.grad_buf.ptr, a.total, 1, 0)
@@ -267,7 +417,7 @@ class DataParallel(object):
         c1 = rt.Event().record()
         c1.synchronize()
         ms = comm.max_float(c0.elapsed_ms(c1)) / reps
-        return {'allreduce_bytes': int(nbytes), 'allreduce_ms_alone': round(ms, 3),
+        return {'exchange': 'nccl', 'allreduce_bytes': int(nbytes), 'allreduce_ms_alone': round(ms, 3),
                 'allreduce_busbw_gbps': round(2.0 * (self.world - 1) / self.world * nbytes / (ms / 1e3) / 1e9, 1),
                 'note': 'ncclAllReduce of the whole gradient arena, alone on the GPU'}
 
@@ -276,6 +426,13 @@ class DataParallel(object):
         ncclCommDestroy.  Captured steps that hold NCCL nodes must have been destroyed before (StepGraph.destroy).
         ncclCommDestroy is called from a helper thread with a deadline: if a peer has already gone it can wait
         forever, and a clean interpreter exit matters more than returning NCCL's resources to a dying process."""
+        if self._mc is not None:
+            rt = self.arena.rt
+            rt.synchronize()
+            self.comm.barrier()              # nobody unbinds while a peer may still write through the switch
+            self._mc = None
+            self.exchange = 'nccl'
+            rt.api.mc_release()
         if not self._nccl:
             return
         import threading

@@ -13,7 +13,18 @@ import numpy as np
 from lightgrad_b200.autograd.cuda import runtime as rt
 
 NP = {rt.F32: np.float32, rt.F64: np.float64, rt.I32: np.int32, rt.I64: np.int64, rt.I16: np.int16,
-      rt.U8: np.uint8, rt.I8: np.int8}
+      rt.U8: np.uint8, rt.I8: np.int8, rt.BF16: np.uint16}     # bf16 staging copies: raw 16-bit patterns
+
+
+def _to_bf16(f):
+    """float32 -> bf16 bit patterns, round to nearest even (what lg_cast does)."""
+    u = np.ascontiguousarray(f, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return (u >> 16).astype(np.uint16)
+
+
+def _from_bf16(h):
+    return (np.asarray(h).astype(np.uint32) << 16).view(np.float32)
 
 
 def _lst(a, n=None):
@@ -176,7 +187,14 @@ class FakeDevice(object):
     def cast(self, sd, dd, nd, shape, src, ss, dst, ds):
         self.launches += 1
         shape = _lst(shape, nd)
-        _arr(dst, dd, shape, _lst(ds, nd))[...] = _arr(src, sd, shape, _lst(ss, nd)).astype(NP[dd])
+        x = _arr(src, sd, shape, _lst(ss, nd))
+        if dd == rt.BF16:
+            assert sd == rt.F32
+            _arr(dst, dd, shape, _lst(ds, nd))[...] = _to_bf16(x).reshape(x.shape)
+            return
+        if sd == rt.BF16:
+            x = _from_bf16(x)
+        _arr(dst, dd, shape, _lst(ds, nd))[...] = x.astype(NP[dd])
 
     # ---- reductions
     def reduce(self, op, dt, x, out, outer, red, inner, scale):
@@ -205,6 +223,12 @@ class FakeDevice(object):
         d = dref._obj
         A = _arr(a, dt, [d.batch0, d.batch1, d.M, d.K], [d.sa_b0, d.sa_b1, d.sa_m, d.sa_k])
         B = _arr(b, dt, [d.batch0, d.batch1, d.K, d.N], [d.sb_b0, d.sb_b1, d.sb_k, d.sb_n])
+        if dt == rt.BF16:
+            # bf16 operands (staging copies), fp32 accumulation and result -- only in the bf16 tensor-core mode
+            assert mode == rt.GEMM_BF16_TC and self.gemm_tc_supported(mode, dt, dref)
+            A, B, dt = _from_bf16(A), _from_bf16(B), rt.F32
+        else:
+            assert mode != rt.GEMM_BF16_TC, "bf16 mode takes bf16 operands"
         Cm = _arr(c, dt, [d.batch0, d.batch1, d.M, d.N], [d.sc_b0, d.sc_b1, d.sc_m, d.sc_n])
         r = A @ B
         if bias:
@@ -224,6 +248,8 @@ class FakeDevice(object):
     def gemm_epilogue(self, mode, dt, dref, a, b, c, bias, epi, aux, aux_ld, alpha):
         d = dref._obj
         self.gemm(mode, dt, dref, a, b, c, bias, 0)
+        if dt == rt.BF16:
+            dt = rt.F32
         f = NP[dt]
         if epi >= 3:
             Cm = _arr(c, dt, [d.batch0, d.batch1, d.M, d.N], [d.sc_b0, d.sc_b1, d.sc_m, 1])
@@ -260,7 +286,22 @@ class FakeDevice(object):
     def side_join(self): pass
 
     def gemm_tc_supported(self, mode, dt, dref):
-        return 1 if mode != rt.GEMM_FP32_SIMT and dt == rt.F32 else 0
+        if mode == rt.GEMM_TF32_TC:
+            return 1 if dt == rt.F32 else 0
+        if mode != rt.GEMM_BF16_TC or dt not in (rt.F32, rt.BF16):
+            return 0
+        # the library's rules for the bf16 kernel: operand strides 16-byte multiples of bf16, not tiny
+        d = dref._obj
+        q = 8
+        a_ok = (d.sa_k == 1 and (d.sa_m % q == 0 or d.M == 1)) or (d.sa_m == 1 and (d.sa_k % q == 0 or d.K == 1))
+        b_ok = (d.sb_k == 1 and (d.sb_n % q == 0 or d.N == 1)) or (d.sb_n == 1 and (d.sb_k % q == 0 or d.K == 1))
+        c_ok = d.sc_n == 1 and (d.sc_m % 4 == 0 or d.M == 1)
+        for n, st, m in ((d.batch1, d.sa_b1, q), (d.batch0, d.sa_b0, q), (d.batch1, d.sb_b1, q), (d.batch0, d.sb_b0, q),
+                         (d.batch1, d.sc_b1, 4), (d.batch0, d.sc_b0, 4)):
+            if n > 1 and (st <= 0 or st % m):
+                return 0
+        big = d.M * d.N * d.K * d.batch0 * d.batch1 >= 64 * 64 * 64 * 8
+        return 1 if (a_ok and b_ok and c_ok and big) else 0
 
     def prof_gemm(self, enable): pass
 
@@ -391,6 +432,51 @@ class FakeDevice(object):
     def nccl_wait(self): pass
     def nccl_fork(self): pass
     def nccl_destroy(self): pass
+
+    # ---- NVLink multicast exchange: a team of ONE device (both mappings are the same host block; the reduce-scatter
+    #      and all-gather are identities), which is what the host logic needs: region layout, arena migration, bucket
+    #      ranges and optimizer arguments
+    def mc_supported(self, yes):
+        yes._obj.value = 1
+
+    def mc_region_bytes(self, arena_bytes, world, region, goff, poff, foff):
+        gran = 1 << 16
+        a = (int(arena_bytes) + gran - 1) // gran * gran
+        goff._obj.value, poff._obj.value, foff._obj.value, region._obj.value = 0, a, 2 * a, 2 * a + gran
+
+    def mc_create(self, nbytes, world, fd):
+        assert world == 1, "the test double has one device"
+        self._mc_bytes, fd._obj.value = int(nbytes), -1
+
+    def mc_import(self, fd, nbytes, world):
+        raise AssertionError("the test double has one device")
+
+    def mc_add_device(self): pass
+
+    def mc_bind(self, local_ref, mc_ref):
+        buf = np.zeros(self._mc_bytes + 256, dtype=np.uint8)
+        addr = (buf.ctypes.data + 255) // 256 * 256
+        self._mc_block, self._mc_base = buf, addr
+        local_ref._obj.value = mc_ref._obj.value = addr
+
+    def mc_release(self):
+        self._mc_block = None
+
+    def mc_exchange_step(self, kind, goff, poff, foff, lo, hi, rank, world, m, v, n_seg, seg_end, t_dev, lr, b1, b2,
+                         eps, momentum, seg_offset, t_advance):
+        assert world == 1 and rank == 0 and lo % 4 == 0 and hi % 4 == 0
+        n = hi - lo
+        if n == 0:
+            return
+        g = self._mc_base + goff + lo * 4
+        p = self._mc_base + poff + lo * 4
+        if kind <= 1:
+            self.adam_step(kind, p, g, int(m) + lo * 4, int(v) + lo * 4, n, n_seg, seg_end, t_dev, lr, b1, b2, eps, lo,
+                           seg_offset, t_advance)
+        elif kind == 2:
+            self.sgd_step(p, g, (int(m) + lo * 4) if (m and momentum != 0.0) else None, n, lr, momentum)
+        else:
+            self.launches += 1
 
 
 def install():

@@ -1,0 +1,110 @@
+"""Gradient exchange fused with the optimizer over NVLink multicast (csrc/lg_mc.cu, DataParallel exchange='nvls').
+
+A team of ONE device exercises the whole path -- multicast object, region layout, arena migration, per-bucket
+reduce-scatter / update / all-gather kernel with its cross-GPU flags, step counter -- and must leave exactly the
+parameters that ``loss.backward(); optimizer.step()`` leaves (the reduce-scatter of one device is the identity).
+Runs on the numpy test double in the CPU suite (host logic) and on the real device with `-m gpu`; the two-GPU
+version is tests/test_parallel_gpu.py."""
+import numpy as np
+import pytest
+import lightgrad_b200 as light
+import lightgrad_b200.nn as nn
+from lightgrad_b200 import CudaTensor, parallel
+from examples import bert
+
+CFG = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2, vocab_size=50,
+           max_position_embeddings=16, type_vocab_size=2)
+
+
+def _build(make_opt):
+    with nn.use_tensor(CudaTensor):
+        np.random.seed(3)
+        model = bert.BertForMaskedLM(**CFG)
+    return model, make_opt(model.parameters())
+
+
+def _run(make_opt, bucket_bytes, steps=3):
+    ids, labels = bert.synthetic_batch(2, 8, CFG['vocab_size'])
+    model, opt = _build(make_opt)
+    dp = None
+    if bucket_bytes is not None:
+        dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm(), exchange='nvls')
+        if dp.exchange != 'nvls':
+            pytest.skip("NVLink multicast objects are not available on this device")
+    x = CudaTensor.from_numpy(ids, requires_grad=False)
+    y = CudaTensor.from_numpy(labels, requires_grad=False)
+    for _ in range(steps):
+        loss = light.loss.cross_entropy(model(x).reshape(-1, CFG['vocab_size']), y)
+        opt.zero_grad()
+        if dp is None:
+            loss.backward()
+            opt.step()
+        else:
+            dp.backward_and_step(loss, bucket_bytes=bucket_bytes)
+    out = [p.numpy() for p in model.parameters()], getattr(opt, 't', None), loss.item()
+    if dp is not None:
+        dp.close()
+    return out
+
+
+OPTIMIZERS = {
+    'adam': lambda ps: light.optim.Adam(ps, lr=1e-2),
+    'adabelief': lambda ps: light.optim.AdaBelief(ps, lr=1e-2),
+    'sgd': lambda ps: light.optim.SGD(ps, lr=1e-2),
+    'sgd_momentum': lambda ps: light.optim.SGD(ps, lr=1e-2, momentum=0.9),
+}
+
+
+def _check(name):
+    want, t_want, loss_want = _run(OPTIMIZERS[name], None)
+    for bucket_bytes in (1, 4096, 1 << 30):
+        got, t_got, loss_got = _run(OPTIMIZERS[name], bucket_bytes)
+        assert t_got == t_want
+        assert loss_got == loss_want
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('name', sorted(OPTIMIZERS))
+def test_team_of_one_exchange_equals_plain_step_host_logic(fake_device, name):
+    _check(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(OPTIMIZERS))
+def test_team_of_one_exchange_equals_plain_step_on_device(cuda, name):
+    _check(name)
+
+
+@pytest.mark.gpu
+def test_exchange_step_inside_a_captured_graph(cuda):
+    """The exchange kernels keep their cross-GPU epochs on the device, so a captured step replays correctly."""
+    from lightgrad_b200.autograd.cuda.graph import StepGraph
+    ids, labels = bert.synthetic_batch(2, 8, CFG['vocab_size'])
+    x = CudaTensor.from_numpy(ids, requires_grad=False)
+    y = CudaTensor.from_numpy(labels, requires_grad=False)
+
+    def run(graph):
+        model, opt = _build(OPTIMIZERS['adam'])
+        dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm(), exchange='nvls')
+        if dp.exchange != 'nvls':
+            pytest.skip("NVLink multicast objects are not available on this device")
+
+        def step():
+            loss = light.loss.cross_entropy(model(x).reshape(-1, CFG['vocab_size']), y)
+            opt.zero_grad()
+            dp.backward_and_step(loss, bucket_bytes=4096)
+            return loss
+        if graph:
+            sg = StepGraph(step, warmup=0)          # capture runs the step once
+            for _ in range(3):
+                sg.replay()
+            sg.destroy()
+        else:
+            for _ in range(4):
+                step()
+        out = [p.numpy() for p in model.parameters()]
+        dp.close()
+        return out
+    for a, b in zip(run(True), run(False)):
+        np.testing.assert_array_equal(a, b)
