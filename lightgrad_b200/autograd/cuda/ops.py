@@ -99,6 +99,28 @@ def _stage_for_side_stream(tensors):
 rt.side_prepare = _stage_for_side_stream
 
 
+# In bf16 mode every matmul belongs to a class -- F forward product, X gradient w.r.t. the activation (the chain the
+# error travels along), W gradient w.r.t. a weight (ends in the optimizer), A the small batched attention products --
+# and only the classes named in LG_BF16_CLASSES multiply bf16 operands; the others run in tf32 on the fp32 data.
+# Default: attention stays tf32 (2 % of the flops; softmax probabilities keep 10 mantissa bits).
+_BF16_CLASSES = set(os.environ.get('LG_BF16_CLASSES', 'FXW').upper())
+
+
+def set_bf16_classes(classes):
+    """Which matmul classes ('F', 'X', 'W', 'A') multiply bf16 operands in bf16 mode.  Returns the previous set."""
+    global _BF16_CLASSES
+    prev = ''.join(sorted(_BF16_CLASSES))
+    _BF16_CLASSES = set(classes.upper())
+    return prev
+
+
+def _mode_for(cls, mode=None):
+    m = _matmul_mode if mode is None else mode
+    if m == rt.GEMM_BF16_TC and cls not in _BF16_CLASSES:
+        return rt.GEMM_TF32_TC
+    return m
+
+
 def _launch_gemm(mode, code, d, a, b, out, bias, accumulate):
     """lg_gemm in the selected mode; in bf16 mode through the staging copies, or -- when the tensor-core kernel
     cannot take the problem (tiny, or strides that are not 16-byte multiples of bf16) -- exactly, on the fp32 data."""
@@ -746,7 +768,7 @@ def _collapse_batch(shape, strides_list):
     return [d[0] for d in out], [[d[1][k] for d in out] for k in range(len(strides_list))]
 
 
-def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
+def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None, cls='F'):
     """out[..., M, N] = a[..., M, K] @ b[..., K, N] for float CudaTensors of >= 2 dims (views welcome)."""
     M, K = a._shape[-2:]
     K2, N = b._shape[-2:]
@@ -754,8 +776,9 @@ def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
         raise ValueError("matmul: shapes %s and %s are not aligned" % (a._shape, b._shape))
     ba, bb = a._shape[:-2], b._shape[:-2]
     bshape = _bshape(ba, bb)
+    mode = _mode_for(cls, mode)
     if out is None:
-        use_mode = _matmul_mode if mode is None else mode
+        use_mode = mode
         if use_mode != rt.GEMM_FP32_SIMT and N % 4 != 0 and N >= 64 and a._code == rt.F32:
             # TMA needs 16-byte aligned row strides: pad the leading dimension and hand back a view
             ld = (N + 31) // 32 * 32
@@ -775,7 +798,7 @@ def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
                                        _bstrides(b2._view(bb, b2._strides[:-2]), bshape), sc])[0]) > 2:
             a2 = _ew1(EW['COPY'], a._view(bshape + (M, K), tuple(sa) + a._strides[-2:]))
             b2 = _ew1(EW['COPY'], b._view(bshape + (K, N), tuple(sb) + b._strides[-2:]))
-        return _gemm(a2, b2, out, bias, accumulate, mode)
+        return _gemm(a2, b2, out, bias, accumulate, mode, cls)
     while len(cshape) < 2:
         cshape.insert(0, 1)
         csa.insert(0, 0)
@@ -790,7 +813,7 @@ def _gemm(a, b, out=None, bias=None, accumulate=False, mode=None):
         if K == 0:
             out._fill_value(0)
         else:
-            _launch_gemm(_matmul_mode if mode is None else mode, a._code, d, a, b, out, bias, accumulate)
+            _launch_gemm(mode, a._code, d, a, b, out, bias, accumulate)
     return out
 
 
@@ -832,21 +855,21 @@ def _empty_like_layout(ref):
     return out
 
 
-def _gemm_like(ref, x, y):
+def _gemm_like(ref, x, y, cls='F'):
     """x @ y written in the memory layout of ``ref`` (the operand this is the gradient of), so that the
     transpose / reshape backward that follows stays a view instead of a strided copy."""
     if ref._contig or ref._shape[:-2] != _bshape(x._shape[:-2], y._shape[:-2]) or ref._code != x._code:
-        return _gemm(x, y)
+        return _gemm(x, y, cls=cls)
     out = _empty_like_layout(ref)
     if out is None:
-        return _gemm(x, y)
+        return _gemm(x, y, cls=cls)
     if out._strides[-1] == 1:
-        return _gemm(x, y, out=out)
+        return _gemm(x, y, out=out, cls=cls)
     if out._strides[-2] == 1:
         # column-major result: compute the transposed product into the transposed view
-        _gemm(_swap_last(y), _swap_last(x), out=_swap_last(out))
+        _gemm(_swap_last(y), _swap_last(x), out=_swap_last(out), cls=cls)
         return out
-    return _gemm(x, y)
+    return _gemm(x, y, cls=cls)
 
 
 def _swap_last(t):
@@ -902,11 +925,11 @@ class dot(Function):
         if len(b._shape) == 2 and len(a._shape) > 2:
             # dA = g @ b^T per row; dB = A2d^T @ g2d : the batch sum is folded into the GEMM's K dim
             g2, a2 = _fold_rows(g), _fold_rows(a)
-            da = _with_shape(_gemm(g2, _swap_last(b)), a._shape)
-            db = _gemm(_swap_last(a2), g2)
+            da = _with_shape(_gemm(g2, _swap_last(b), cls='X'), a._shape)
+            db = _gemm(_swap_last(a2), g2, cls='W')
         else:
-            da = _gemm_like(a, g, _swap_last(b))
-            db = _gemm_like(b, _swap_last(a), g)
+            da = _gemm_like(a, g, _swap_last(b), cls='X')
+            db = _gemm_like(b, _swap_last(a), g, cls='X')
             da, db = _unbroadcast(da, a._shape), _unbroadcast(db, b._shape)
         if ctx.va:
             da = da.reshape(da._shape[-1])
@@ -939,10 +962,10 @@ class linear(Function):
             # x already holds a gradient from another consumer (residual branch): dX is reduce-added into it by
             # the GEMM epilogue instead of being materialised and added by a separate pass
             rt.side_join_if_written(xg)
-            _gemm(g2, weight, out=_fold_rows(xg), accumulate=True)
+            _gemm(g2, weight, out=_fold_rows(xg), accumulate=True, cls='X')
             dx = Function.ACCUMULATED
         else:
-            dx = _with_shape(_gemm(g2, weight), xshape)
+            dx = _with_shape(_gemm(g2, weight, cls='X'), xshape)
         wg = _direct_grad(weight, g2._code)
         bias = ctx._parents[2] if has_bias else None
         bg = _direct_grad(bias, g2._code) if has_bias else None
@@ -953,23 +976,23 @@ class linear(Function):
             # arena: no temporary, no add pass).  Nothing else in backward waits for them, so they are issued on
             # the side stream and overlap the dX chain.
             with rt.side_stream(g2, x2, writes=(wg,) if bg is None else (wg, bg)):
-                _gemm(_swap_last(g2), x2, out=wg, accumulate=True)
+                _gemm(_swap_last(g2), x2, out=wg, accumulate=True, cls='W')
                 if bg is not None:
                     rt.api.reduce_pitched(RED['SUM'], g2._code, g2.ptr, bg.ptr, 1, g2._shape[0], g2._shape[1],
                                           g2._strides[0], 1.0, 1)
             return (dx, Function.ACCUMULATED, Function.ACCUMULATED) if has_bias else (dx, Function.ACCUMULATED)
         if wg is not None:
             rt.side_join_if_written(wg)       # a weight shared with another layer may have side-stream writes pending
-            _gemm(_swap_last(g2), x2, out=wg, accumulate=True)
+            _gemm(_swap_last(g2), x2, out=wg, accumulate=True, cls='W')
             dw = Function.ACCUMULATED
         else:
-            dw = _gemm(_swap_last(g2), x2)
+            dw = _gemm(_swap_last(g2), x2, cls='W')
         if has_bias:
             return dx, dw, _reduce(RED['SUM'], g2, (0,), False)
         return dx, dw
 
 
-def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False):
+def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False, cls='F'):
     """outs[g] (+)= As[g] @ Bs[g] (+ biases[g]) for up to 4 problems of identical shape and strides, as one
     launch.  Naming the same tensor in every ``outs`` slot makes it one K-concatenated product
     out = sum_g As[g] @ Bs[g].  Operands: 2-D, or N-D with batch dims that collapse to <= 2 strides."""
@@ -998,7 +1021,7 @@ def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False):
     arr = C.c_void_p * n
     for o in outs:
         _written(o)
-    mode, code = _matmul_mode, a._code
+    mode, code = _mode_for(cls), a._code
     pa, pb = [t.ptr for t in As], [t.ptr for t in Bs]
     if mode == rt.GEMM_BF16_TC:
         ok = code == rt.F32 and not (accumulate and biases is not None) and \
@@ -1015,7 +1038,7 @@ def _gemm_grouped(As, Bs, outs, biases=None, accumulate=False):
     return outs
 
 
-def _gemm_epilogue(a, b, out, bias, epi, aux):
+def _gemm_epilogue(a, b, out, bias, epi, aux, cls='F'):
     """One plain 2-D product with an activation fused into the GEMM epilogue (lg_gemm_epilogue):
     epi 1: out = a @ b + bias and aux = gelu(out);   epi 2: out = (a @ b) * gelu'(aux)."""
     M, K = a._shape
@@ -1026,7 +1049,7 @@ def _gemm_epilogue(a, b, out, bias, epi, aux):
     _written(out)
     if epi == 1:
         _written(aux)
-    mode, code, pa, pb = _matmul_mode, a._code, a.ptr, b.ptr
+    mode, code, pa, pb = _mode_for(cls), a._code, a.ptr, b.ptr
     if mode == rt.GEMM_BF16_TC:
         ok = code == rt.F32 and rt.api.gemm_tc_supported(mode, rt.BF16, C.byref(d))
         if ok:
@@ -1054,17 +1077,18 @@ def _attention_gemm(a, b, out, epi, alpha, aux=None):
     d = rt.GemmDesc(M, N, K, B0, B1, a._strides[0], a._strides[1], a._strides[2], a._strides[3],
                     b._strides[0], b._strides[1], b._strides[2], b._strides[3],
                     out._strides[0], out._strides[1], out._strides[2], 1)
+    mode = _mode_for('A')
     code, pa, pb = a._code, a.ptr, b.ptr
-    if _matmul_mode == rt.GEMM_BF16_TC:
+    if mode == rt.GEMM_BF16_TC:
         code = rt.BF16
-    if not rt.api.gemm_tc_supported(_matmul_mode, code, C.byref(d)):
+    if not rt.api.gemm_tc_supported(mode, code, C.byref(d)):
         return False
     if code == rt.BF16:
         pa, pb = _bf16_ptr(a), _bf16_ptr(b)
         if (pa | pb) & 15:
             return False
     _written(out)
-    rt.api.gemm_epilogue(_matmul_mode, code, C.byref(d), pa, pb, out.ptr, None, epi,
+    rt.api.gemm_epilogue(mode, code, C.byref(d), pa, pb, out.ptr, None, epi,
                          aux.ptr if aux is not None else None, N, float(alpha))
     return True
 
@@ -1105,27 +1129,27 @@ class mlp_gelu(Function):
             g2 = g2.contiguous()
         code = x2._code
         dh = CudaTensor._new(h._shape, h._dtype)
-        _gemm_epilogue(g2, w2, dh, None, 2, h)                     # dh = (dY W2) * gelu'(h)
+        _gemm_epilogue(g2, w2, dh, None, 2, h, cls='X')            # dh = (dY W2) * gelu'(h)
         xg = _direct_grad(xin, code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
         if xg is not None:
             rt.side_join_if_written(xg)
-            _gemm(dh, w1, out=_fold_rows(xg), accumulate=True)
+            _gemm(dh, w1, out=_fold_rows(xg), accumulate=True, cls='X')
             dx = Function.ACCUMULATED
         else:
-            dx = _with_shape(_gemm(dh, w1), xshape)
+            dx = _with_shape(_gemm(dh, w1, cls='X'), xshape)
         grads = [_direct_grad(p, code) for p in (w1, b1, w2, b2)]
         if all(g is not None for g in grads) and min(w1._shape[0], w2._shape[0]) > 1:
             w1g, b1g, w2g, b2g = grads
             with rt.side_stream(g2, dh, act, x2, writes=tuple(grads)):
-                _gemm(_swap_last(g2), act, out=w2g, accumulate=True)
+                _gemm(_swap_last(g2), act, out=w2g, accumulate=True, cls='W')
                 rt.api.reduce_pitched(RED['SUM'], code, g2.ptr, b2g.ptr, 1, g2._shape[0], g2._shape[1],
                                       g2._strides[0], 1.0, 1)
-                _gemm(_swap_last(dh), x2, out=w1g, accumulate=True)
+                _gemm(_swap_last(dh), x2, out=w1g, accumulate=True, cls='W')
                 rt.api.reduce_pitched(RED['SUM'], code, dh.ptr, b1g.ptr, 1, dh._shape[0], dh._shape[1],
                                       dh._strides[0], 1.0, 1)
             return (dx,) + (Function.ACCUMULATED,) * 4
-        return (dx, _gemm(_swap_last(dh), x2), _reduce(RED['SUM'], dh, (0,), False),
-                _gemm(_swap_last(g2), act), _reduce(RED['SUM'], g2, (0,), False))
+        return (dx, _gemm(_swap_last(dh), x2, cls='W'), _reduce(RED['SUM'], dh, (0,), False),
+                _gemm(_swap_last(g2), act, cls='W'), _reduce(RED['SUM'], g2, (0,), False))
 
 
 def _direct_grad(p, code):
@@ -1167,11 +1191,11 @@ class self_attention(Function):
         scale = 1.0 / float(np.sqrt(dh))
         probs = CudaTensor._new((b, heads, s, s), x._dtype)
         if not _attention_gemm(q, _swap_last(k), probs, 3, scale):      # softmax fused into the score GEMM's epilogue
-            scores = _gemm(q, _swap_last(k))
+            scores = _gemm(q, _swap_last(k), cls='A')
             rt.api.softmax_fwd(x._code, scores.ptr, probs.ptr, scores._numel // s, s, scale)
             del scores
         out = CudaTensor._new((b, s, H), x._dtype)
-        _gemm(probs, v, out=out._view(hv[0], hv[1]))
+        _gemm(probs, v, out=out._view(hv[0], hv[1]), cls='A')
         probs._temp = qkv._temp = False
         ctx.save_for_backward(x2, qkv, probs, (b, s, H, heads, scale), x._shape)
         return out
@@ -1188,14 +1212,14 @@ class self_attention(Function):
         go = g._view(hv[0], hv[1])
         dqkv = CudaTensor._new((3, rows, H), x2._dtype)
         dq, dk, dv = (dqkv._view(hv[0], hv[1], i * rows * H) for i in range(3))
-        _gemm(_swap_last(probs), go, out=dv)                            # dV = P^T dO
+        _gemm(_swap_last(probs), go, out=dv, cls='A')                   # dV = P^T dO
         ds = CudaTensor._new(probs._shape, x2._dtype)
         if not _attention_gemm(go, _swap_last(v), ds, 4, scale, aux=probs):   # dS straight from the dP GEMM's epilogue
-            dp = _gemm(go, _swap_last(v))                               # dP = dO V^T
+            dp = _gemm(go, _swap_last(v), cls='A')                      # dP = dO V^T
             rt.api.softmax_bwd(x2._code, probs.ptr, dp.ptr, ds.ptr, probs._numel // s, s, scale)
             del dp
-        _gemm(ds, k, out=dq)                                            # dQ = dS K
-        _gemm(_swap_last(ds), q, out=dk)                                # dK = dS^T Q
+        _gemm(ds, k, out=dq, cls='A')                                   # dQ = dS K
+        _gemm(_swap_last(ds), q, out=dk, cls='A')                       # dK = dS^T Q
         parts = [dqkv._view((rows, H), (H, 1), i * rows * H) for i in range(3)]
         ws = (wq, wk, wv)
         xin = ctx._parents[0]
@@ -1203,11 +1227,11 @@ class self_attention(Function):
         if xg is not None:
             # dX = sum_g dY_g W_g added into the gradient x already received through the residual branch
             rt.side_join_if_written(xg)
-            _gemm_grouped(parts, list(ws), [_fold_rows(xg)] * 3, accumulate=True)
+            _gemm_grouped(parts, list(ws), [_fold_rows(xg)] * 3, accumulate=True, cls='X')
             dx = Function.ACCUMULATED
         else:
             dx = CudaTensor._new((rows, H), x2._dtype)
-            _gemm_grouped(parts, list(ws), [dx] * 3)                    # dX = sum_g dY_g W_g
+            _gemm_grouped(parts, list(ws), [dx] * 3, cls='X')           # dX = sum_g dY_g W_g
             dx = _with_shape(dx, xshape)
         wgs = [_direct_grad(w, x2._code) for w in ws]
         bgs = [_direct_grad(bias, x2._code) for bias in (bq, bk, bv)]
@@ -1215,16 +1239,16 @@ class self_attention(Function):
         if all(w is not None for w in wgs) and all(b is not None for b in bgs) and H > 1:
             # dW_g += dY_g^T X and db_g += colsum(dY_g), straight into the arena, on the side stream
             with rt.side_stream(dqkv, x2, writes=tuple(wgs) + tuple(bgs)):
-                _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True)
+                _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True, cls='W')
                 for part, bg in zip(parts, bgs):
                     rt.api.reduce_pitched(RED['SUM'], part._code, part.ptr, bg.ptr, 1, rows, H, H, 1.0, 1)
             return (dx,) + (Function.ACCUMULATED,) * 6
         if all(w is not None for w in wgs):
-            _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True)
+            _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True, cls='W')
             dws = [Function.ACCUMULATED] * 3
         else:
             dws = [CudaTensor._new((H, H), x2._dtype) for _ in range(3)]
-            _gemm_grouped(pt, [x2] * 3, dws)
+            _gemm_grouped(pt, [x2] * 3, dws, cls='W')
         dbs = []
         for part, bg in zip(parts, bgs):
             if bg is not None and H > 1:

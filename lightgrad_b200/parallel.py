@@ -155,6 +155,7 @@ class DataParallel(object):
         self.arena = getattr(optimizer, 'arena', None)
         self._nccl = False
         self.exchange = 'nccl'
+        self.exchange_note = ''            # why the multicast exchange is not in use, when it was asked for
         self._mc = None
         if self.world > 1 and self.arena is not None:
             rt = self.arena.rt
@@ -175,7 +176,8 @@ class DataParallel(object):
                 self.exchange = 'nvls'
             elif want == 'nvls' and self.rank == 0:
                 import sys
-                sys.stderr.write("lightgrad_b200: NVLink multicast exchange unavailable, using NCCL all-reduce\n")
+                sys.stderr.write("lightgrad_b200: NVLink multicast exchange unavailable (%s), using NCCL all-reduce\n"
+                                 % self.exchange_note)
         if broadcast and self.world > 1:
             self.broadcast_parameters()
 
@@ -195,9 +197,11 @@ class DataParallel(object):
         yes = C.c_int(0)
         try:
             api.mc_supported(C.byref(yes))
-        except Exception:
+        except Exception as exc:
             yes.value = 0
+            self.exchange_note = 'lg_mc_supported: %s' % exc
         if not self._all_ok(bool(yes.value)):
+            self.exchange_note = self.exchange_note or 'the device / driver reports no multicast support on some rank'
             return False
         region, goff, poff, foff = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
         created, err = False, None
@@ -210,6 +214,7 @@ class DataParallel(object):
         except Exception as exc:
             err = exc
         if not self._all_ok(err is None):
+            self.exchange_note = 'creating the multicast object failed: %s' % err
             if created:
                 api.mc_release()
             return False
@@ -224,6 +229,7 @@ class DataParallel(object):
         except Exception as exc:
             err = exc
         if not self._all_ok(err is None):          # (also the barrier cuMulticastBindMem needs: every device was added)
+            self.exchange_note = 'sharing / joining the multicast object failed: %s' % err
             if created:
                 api.mc_release()
             return False
@@ -233,6 +239,7 @@ class DataParallel(object):
         except Exception as exc:
             err = exc
         if not self._all_ok(err is None):
+            self.exchange_note = 'binding memory to the multicast object failed: %s' % err
             api.mc_release()
             return False
         a.rebase(self.optimizer.parameters, local.value + poff.value, local.value + goff.value, keep=self)

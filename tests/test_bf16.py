@@ -38,8 +38,11 @@ def _check_product(a, b, ta=False, tb=False, tol_exact=2e-5):
     want16 = _bf16_round(a).astype(np.float64) @ _bf16_round(b).astype(np.float64)
     want = a.astype(np.float64) @ b.astype(np.float64)
     scale = np.abs(want).max()
-    assert np.abs(got - want16).max() <= tol_exact * scale, (a.shape, b.shape, ta, tb, np.abs(got - want16).max() / scale)
-    assert np.abs(got - want).max() <= 5e-3 * scale
+    # operand strides that are not 16-byte multiples of bf16 (a 30522-wide row-major B) cannot go through TMA as
+    # bf16: that product runs exactly, on the fp32 data -- agreeing with the unrounded product instead
+    e16, e32 = np.abs(got - want16).max() / scale, np.abs(got - want).max() / scale
+    assert min(e16, e32) <= tol_exact, (a.shape, b.shape, ta, tb, e16, e32)
+    assert e32 <= 5e-3
 
 
 @pytest.mark.gpu

@@ -30,7 +30,7 @@ def _run(make_opt, bucket_bytes, steps=3):
     if bucket_bytes is not None:
         dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm(), exchange='nvls')
         if dp.exchange != 'nvls':
-            pytest.skip("NVLink multicast objects are not available on this device")
+            pytest.skip("NVLink multicast objects are not available on this device: " + dp.exchange_note)
     x = CudaTensor.from_numpy(ids, requires_grad=False)
     y = CudaTensor.from_numpy(labels, requires_grad=False)
     for _ in range(steps):
