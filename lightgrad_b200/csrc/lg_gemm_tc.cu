@@ -21,11 +21,10 @@
 // (64-element chunks, 8-row groups) where tf32 needs the 32-byte-base variant.  Operands are bf16 copies staged
 // by the host layer (lg_cast / fused producer epilogues); accumulation and the result stay fp32.
 // Roofline: tensor pipe (TF32 dense = half the bf16 rate).  Algorithmic flops 2*M*N*K.
-#include "lg_common.cuh"
-#include <cuda.h>
-#include <cudaTypedefs.h>
+#include "lg_tc.cuh"
 
 using namespace lg;
+using namespace lg::tc;
 
 namespace {
 
@@ -46,161 +45,6 @@ constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, taking alternate 32-column chunks
 constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
 constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 32 fp32, per warp, double buffered
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// try_wait suspends the thread for a bounded time per call; the outer loop is capped so that a protocol bug
-// surfaces as a trapped launch (an error the host sees) instead of a hung GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (!done && spins > (1u << 24)) __trap();
-    }
-}
-
-// every tensor map is rank 4: (contiguous dim, strided dim, batch1, batch0); plain 2-D problems use batch = 1
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-        "[%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-// MN-major operands whose row pitch covers the extent rounded up to 32 use a rank-5 "chunked" map
-// (32 contiguous elements, k rows, 32-element chunk index, batch1, batch0): ONE box fills the whole stage in the
-// [chunk][k][32] order the UMMA descriptor expects, instead of one 4 KB box per chunk (the producer thread
-// and the TMA unit were the bottleneck of the MN-major kernels with 5..10 small boxes per k-block).
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-        "[%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-// same load, delivered to the same shared-memory offset (and signalling the same mbarrier offset) in every
-// CTA of the cluster named by `mask`
-__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                               int c3, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
-        "{%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-// ---- CTA-pair (cta_group::2) helpers ------------------------------------------------------------
-// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the
-// shared::cluster address cleared), executed by both CTAs of the pair for their own halves
-__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                                int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-        "%5, %6}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                                int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-        "%5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 raddr;\n\t"
-        "mapa.shared::cluster.u32 raddr, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(rank)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
-                                                  int c3) {
-    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                     map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-
-// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4, [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [46,48) version=1,
-//   [61,64) layout type (2 = SWIZZLE_128B)
-//   fp32/tf32 operands that are MN-major must use layout type 1 (SWIZZLE_128B_BASE32B: 32-byte chunks
-//   permuted over 4-row groups) -- the only MN-major layout the tf32 tensor core accepts
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate; operand format 2 = tf32, 1 = bf16
-template <int ES>
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, bool a_mn, bool b_mn) {
-    constexpr uint32_t fmt = ES == 4 ? 2u : 1u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-template <int ES, int CG>
-__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    if constexpr (ES == 4 && CG == 1)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
-                     "r"(idesc), "r"(accum) : "memory");
-    else if constexpr (ES == 4 && CG == 2)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
-                     "r"(idesc), "r"(accum) : "memory");
-    else if constexpr (ES == 2 && CG == 1)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
-                     "r"(idesc), "r"(accum) : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db),
-                     "r"(idesc), "r"(accum) : "memory");
-}
 
 // SMs the persistent GEMM grids may occupy (lg_gemm_sm_limit): a data-parallel step leaves a few SMs to the
 // collective's CTAs, so that a one-CTA-per-SM grid is never forced into a second wave by them
@@ -267,19 +111,6 @@ struct TcMaps {
 // this one is staged), + bias, 128B-swizzled staging buffer, TMA store / reduce-add.  The bias slice of a chunk
 // is fetched one chunk ahead with one coalesced load per warp and broadcast by shuffles, so no global-memory
 // latency sits between the TMEM read and the store.
-__device__ __forceinline__ void tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
-
 __device__ __forceinline__ float bias_slice(const float* bias, int col, int N) {
     return (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
 }
@@ -1019,21 +850,6 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-
-int load_encode() {
-    if (g_encode) return 0;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-        cudaGetLastError();
-        return set_error("cuTensorMapEncodeTiled is not available from the driver");
-    }
-    g_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-    return 0;
-}
-
 // rank-4 tensor map (es = element size: 4 fp32, 2 bf16): dim0 = contiguous extent, dim1 = strided extent,
 // dim2 = batch1, dim3 = batch0
 struct BatchDims {

@@ -78,7 +78,8 @@ def main():
         g_err = max(float(np.abs(g - r).max()) for g, r in zip(grads, ref_grads)) / gmax
         pmax = max(float(np.abs(p).max()) for p in ref_params)
         p_err = max(float(np.abs(p - r).max()) for p, r in zip(params, ref_params)) / pmax
-        result = {'world': world, 'mode': mode, 'exchange': getattr(dp, 'exchange', 'nccl'), 'global_batch': BATCH,
+        result = {'world': world, 'mode': mode, 'exchange': getattr(dp, 'exchange', 'nccl'),
+                  'exchange_note': getattr(dp, 'exchange_note', ''), 'global_batch': BATCH,
                   'grad_rel_err': g_err, 'param_rel_err_after_%d_steps' % STEPS: p_err,
                   'local_losses': losses, 'global_losses': ref_losses}
     # every rank holds the same parameters after the exchange
