@@ -262,6 +262,22 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
                      const void* g, void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols,
                      int accumulate);
 
+/* Multi-head self-attention core of BertSelfAttention (examples/bert.py:68-88 of the reference) as ONE kernel per
+ * direction: per (batch, head) tile  out = softmax(scale * Q K^T) V  with the scores and probabilities kept on chip
+ * (tcgen05 tf32 products, TMEM accumulators, softmax in registers).
+ *   qkv   (3, batch*seq, heads*head_dim) contiguous: the stacked Q, K, V projections; head h of a token is the
+ *         head_dim values at column h*head_dim (the reference's reshape(b, s, h, d).transpose(0, 2, 1, 3) as a view)
+ *   out   (batch*seq, heads*head_dim): heads merged back, the reference's context.transpose(0, 2, 1, 3).reshape
+ *   lse   (batch*heads*seq): scale * rowmax + ln(rowsum) per query, saved for backward
+ *   lg_attention_bwd recomputes the probabilities from qkv and lse and writes dQ, dK, dV in qkv's layout.
+ * lg_attention_supported: 1 when the fused kernels take the shape (float32, seq 128, head_dim 64); other shapes use
+ * the batched lg_gemm / lg_gemm_epilogue path. */
+int lg_attention_supported(int dtype, int64_t seq, int64_t head_dim);
+int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
+                     double scale, void* out, void* lse);
+int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout, const void* lse, int64_t batch,
+                     int64_t seq, int64_t heads, int64_t head_dim, double scale, void* dqkv);
+
 /* ---- optimizers (replaces the per-parameter python loops of optim.py) ----------------------- */
 /* all tensors of one optimizer live in flat fp32 arenas; `seg_end_dev[i]` (device, int64) is the
  * exclusive end offset of tensor i.  Tensor i uses step count t = *t_dev + i + 1 in its bias
@@ -317,6 +333,12 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
                         double lr, double beta1, double beta2, double eps, double momentum, int seg_offset,
                         int t_advance);
 int lg_mc_release(void);
+/* measurement aid (LG_MC_TRACE=1 in the environment): lg_mc_trace_mark stamps the position of the current stream;
+ * lg_mc_trace_read drains the device and returns, in launch order, records of 4 x uint64 {entered, all ranks met,
+ * finished, bucket bytes} per exchange launch (GPU global timer, ns) and {t, 0, 0, 0} per mark.  Captured launches keep
+ * their record, so after a graph replay the trace is that replay's timeline; reset != 0 clears it. */
+int lg_mc_trace_mark(void);
+int lg_mc_trace_read(uint64_t* out, int max_records, int* n_records, int reset);
 
 #ifdef __cplusplus
 }

@@ -1152,6 +1152,14 @@ class mlp_gelu(Function):
                 _gemm(_swap_last(g2), act, cls='W'), _reduce(RED['SUM'], g2, (0,), False))
 
 
+def _fused_attention_ok(code, s, dh):
+    """The one-kernel attention runs tf32 products: used in the tensor-core modes (in bf16 mode when the attention
+    class stays tf32), never in the exact-fp32 mode."""
+    if 'attn_fused' in _DISABLED or _mode_for('A') != rt.GEMM_TF32_TC:
+        return False
+    return bool(rt.api.attention_supported(code, s, dh))
+
+
 def _direct_grad(p, code):
     """The parameter's existing gradient buffer when a kernel may add into it in place, else None."""
     if 'dx_acc' in _DISABLED and p.ctx is not None:
@@ -1189,6 +1197,14 @@ class self_attention(Function):
         hv = (b, heads, s, dh), (s * H, dh, H, 1)                      # per-head view of a (rows, H) matrix
         q, k, v = (qkv._view(hv[0], hv[1], g * rows * H) for g in range(3))
         scale = 1.0 / float(np.sqrt(dh))
+        if _fused_attention_ok(x._code, s, dh):
+            # scores, softmax and context in one kernel per (batch, head): the probabilities never leave the chip
+            out = CudaTensor._new((b, s, H), x._dtype)
+            lse = CudaTensor._new((b * heads * s,), x._dtype)
+            rt.api.attention_fwd(x._code, qkv.ptr, b, s, heads, dh, scale, out.ptr, lse.ptr)
+            qkv._temp = out._temp = lse._temp = False
+            ctx.save_for_backward(x2, qkv, (out, lse), (b, s, H, heads, scale), x._shape)
+            return out._view(out._shape, out._strides)
         probs = CudaTensor._new((b, heads, s, s), x._dtype)
         if not _attention_gemm(q, _swap_last(k), probs, 3, scale):      # softmax fused into the score GEMM's epilogue
             scores = _gemm(q, _swap_last(k), cls='A')
@@ -1212,6 +1228,11 @@ class self_attention(Function):
         go = g._view(hv[0], hv[1])
         dqkv = CudaTensor._new((3, rows, H), x2._dtype)
         dq, dk, dv = (dqkv._view(hv[0], hv[1], i * rows * H) for i in range(3))
+        if isinstance(probs, tuple):
+            # fused path: dQ, dK, dV from one residency of Q, K, V, dO (probabilities recomputed from the saved LSE)
+            out, lse = probs
+            rt.api.attention_bwd(x2._code, qkv.ptr, out.ptr, g.ptr, lse.ptr, b, s, heads, dh, scale, dqkv.ptr)
+            return self_attention._projection_backward(ctx, dqkv, x2, rows, H, xshape)
         _gemm(_swap_last(probs), go, out=dv, cls='A')                   # dV = P^T dO
         ds = CudaTensor._new(probs._shape, x2._dtype)
         if not _attention_gemm(go, _swap_last(v), ds, 4, scale, aux=probs):   # dS straight from the dP GEMM's epilogue
@@ -1220,6 +1241,12 @@ class self_attention(Function):
             del dp
         _gemm(ds, k, out=dq, cls='A')                                   # dQ = dS K
         _gemm(_swap_last(ds), q, out=dk, cls='A')                       # dK = dS^T Q
+        return self_attention._projection_backward(ctx, dqkv, x2, rows, H, xshape)
+
+    @staticmethod
+    def _projection_backward(ctx, dqkv, x2, rows, H, xshape):
+        """dX, dW_g, db_g of the three projections from the stacked (3, rows, H) gradient of Q, K, V."""
+        wq, bq, wk, bk, wv, bv = ctx._parents[1:7]
         parts = [dqkv._view((rows, H), (H, 1), i * rows * H) for i in range(3)]
         ws = (wq, wk, wv)
         xin = ctx._parents[0]

@@ -97,6 +97,9 @@ _SIGNATURES = {
     'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_add_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int],
+    'lg_attention_supported': [C.c_int, C.c_int64, C.c_int64],
+    'lg_attention_fwd': [C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, _vp, _vp],
+    'lg_attention_bwd': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, _vp],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
     'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp,
                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int],
@@ -117,6 +120,8 @@ _SIGNATURES = {
                             C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                             C.c_int],
     'lg_mc_release': [],
+    'lg_mc_trace_mark': [],
+    'lg_mc_trace_read': [_vp, C.c_int, C.POINTER(C.c_int), C.c_int],
 }
 
 _lib = None
@@ -164,8 +169,8 @@ def load():
         fn = getattr(_lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-        if name == 'lg_gemm_tc_supported':
-            setattr(a, name[3:], fn)
+        if name in ('lg_gemm_tc_supported', 'lg_attention_supported'):
+            setattr(a, name[3:], fn)       # predicates: the return value is the answer, not a status
         else:
             setattr(a, name[3:], _Checked(fn, name))
     a.raw = _lib

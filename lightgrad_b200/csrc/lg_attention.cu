@@ -1,0 +1,536 @@
+// Fused multi-head self-attention for sm_100a: one CTA per (batch, head) tile, seq = 128, head_dim = 64.
+//
+// Replaces, for BertSelfAttention of the reference (examples/bert.py:68-88: scores = Q K^T / sqrt(d); softmax;
+// context = P V), the six batched GEMM launches per layer of the composed path and their (b, h, s, s) round trips
+// through HBM (scores / probabilities 25 MB per layer at batch 32).  Everything between the projections stays on
+// chip:
+//
+//   forward   S = Q K^T (tcgen05 kind::tf32, TMEM) -> row softmax in registers -> P as a K-major smem operand
+//             (over the Q / K tiles, which are dead by then) -> O = P V (TMEM) -> O / rowsum, LSE saved
+//   backward  S = Q K^T and dP = dO V^T recomputed into TMEM from one residency of Q, K, V, dO;
+//             P = exp(alpha S - LSE), dS = alpha P (dP - D), D = rowsum(dO o O);
+//             dV = P^T dO, dQ = dS K, dK = dS^T Q -- P^T / dS / dS^T are written to shared memory by the threads that
+//             own the rows (the transposes cost one conflict-free 4-byte store per element), the MN-major B operands
+//             (dO, K, Q with the head dimension contiguous) are fetched by TMA in the 32-byte-base swizzle the tf32
+//             tensor core needs.  The probabilities never exist in HBM.
+//
+// Operands are the fp32 tensors the projections wrote (the stacked (3, rows, H) Q / K / V buffer, per-head tiles
+// addressed through TMA coordinates); products are tf32 x tf32 -> fp32, exactly like the GEMMs they replace.
+// Roofline: HBM.  Algorithmic bytes per tile: forward 3 x 32 KB read + 32 KB written; backward 5 x 32 KB read
+// (Q, K, V, dO, O) + 3 x 32 KB written.
+#include "lg_tc.cuh"
+
+using namespace lg;
+using namespace lg::tc;
+
+namespace {
+
+constexpr int SEQ = 128, HD = 64;
+constexpr int TILE_BYTES = SEQ * HD * 4;         // 32 KB: one (128 x 64) fp32 operand tile
+constexpr int KB_BYTES = SEQ * 128;              // 16 KB: 128 rows x one 128-byte swizzle row (32 fp32 of K)
+constexpr int ATT_THREADS = 192;                 // warp 0: TMA + MMA issue (one lane); warp 1: TMEM; warps 2..5: rows
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// A (128 x 128 of K, four 16 KB k-blocks, K-major SWIZZLE_128B) times a K-major B tile of N rows
+template <int N, int KBLOCKS>
+__device__ __forceinline__ void mma_kmajor(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
+    constexpr uint32_t idesc = umma_idesc<4>(128, N, false, false);
+#pragma unroll
+    for (int kb = 0; kb < KBLOCKS; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_issue<4, 1>(d_tmem, umma_desc(a_addr + kb * KB_BYTES + ks * 32, 16, 1024, 2),
+                             umma_desc(b_addr + kb * (N * 128) + ks * 32, 16, 1024, 2), idesc, (kb | ks) ? 1u : 0u);
+}
+// A (128 x 128 of K, K-major) times an MN-major B tile (K = 128 rows of 64 contiguous values: two 32-value chunks,
+// each 128 rows x 128 bytes in the 32-byte-base swizzle; a k-step is 8 rows = 1024 bytes)
+__device__ __forceinline__ void mma_mn_b(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
+    constexpr uint32_t idesc = umma_idesc<4>(128, HD, false, true);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_issue<4, 1>(d_tmem, umma_desc(a_addr + kb * KB_BYTES + ks * 32, 16, 1024, 2),
+                             umma_desc(b_addr + (kb * 4 + ks) * 1024, SEQ * 128, 512, 1), idesc, (kb | ks) ? 1u : 0u);
+}
+
+// row `row` of a K-major (128 rows x 32 fp32 per k-block) operand: this thread's 32 values of k-block `kb`
+__device__ __forceinline__ void store_row_chunk(uint8_t* base, int kb, int row, const float (&x)[32]) {
+    uint8_t* p = base + kb * KB_BYTES + row * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(p + ((j ^ (row & 7)) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+}
+// the TRANSPOSE: this thread owns source row `row` (= column `row` of the operand); x[k] goes to operand row r0 + k.
+// The 32 lanes of a warp own 32 consecutive source rows, i.e. 128 contiguous bytes of each operand row: no conflicts.
+__device__ __forceinline__ void store_col_chunk(uint8_t* base, int row, int r0, const float (&x)[32]) {
+    uint8_t* p = base + (row >> 5) * KB_BYTES + (row & 3) * 4;
+    const int c = (row & 31) >> 2;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int r = r0 + k;
+        *reinterpret_cast<float*>(p + r * 128 + ((c ^ (r & 7)) << 4)) = x[k];
+    }
+}
+
+struct AttnParams {
+    int batch, heads, rows;          // rows = batch * SEQ
+    float scale_log2e;               // alpha * log2(e)
+    float scale;
+    float* out;                      // forward: (rows, H) result
+    float* lse;                      // (batch * heads * SEQ): alpha * rowmax + ln(rowsum) (natural log)
+    const float* o;                  // backward: forward result
+    const float* dout;
+    float* dqkv;                     // backward: (3, rows, H)
+};
+
+struct AttnMaps {
+    CUtensorMap qkv_k;    // stacked (3 * rows, H) Q/K/V buffer, box 32 x 128, SWIZZLE_128B       (K-major operand tiles)
+    CUtensorMap qkv_mn;   // same memory, SWIZZLE_128B_ATOM_32B                                     (MN-major operand tiles)
+    CUtensorMap do_k;     // (rows, H) gradient of the result, SWIZZLE_128B
+    CUtensorMap do_mn;    // same, SWIZZLE_128B_ATOM_32B
+};
+
+// ======================================= forward =========================================================
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
+    LG_PDL_TRIGGER();
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                       // 32 KB  (later, with sK: the 64 KB probability operand)
+    uint8_t* sK = smem + TILE_BYTES;          // 32 KB
+    uint8_t* sV = smem + 2 * TILE_BYTES;      // 32 KB  MN-major
+    uint64_t* bars = (uint64_t*)(smem + 3 * TILE_BYTES);
+    uint64_t* b_qk = bars;        // Q, K landed
+    uint64_t* b_v = bars + 1;     // V landed
+    uint64_t* b_s = bars + 2;     // S = Q K^T complete
+    uint64_t* b_p = bars + 3;     // probabilities staged (128 arrivals)
+    uint64_t* b_o = bars + 4;     // O = P V complete
+    uint64_t* b_done = bars + 5;  // rows stored, TMEM / smem reusable (128 arrivals)
+    uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = p.heads * HD;
+    const int tiles = p.batch * p.heads;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(b_qk, 1); mbar_init(b_v, 1); mbar_init(b_s, 1); mbar_init(b_p, 128); mbar_init(b_o, 1);
+        mbar_init(b_done, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;          // S: columns 0..127, O: columns 128..191
+    LG_PDL_WAIT();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const uint32_t ph = it & 1;
+                const int b = tile / p.heads, h = tile - b * p.heads;
+                const int r0 = b * SEQ, c0 = h * HD;
+                if (it > 0) mbar_wait(b_done, ph ^ 1);           // previous tile's rows are out: smem and TMEM are free
+                mbar_expect_tx(b_qk, 2 * TILE_BYTES);
+                tma_load_2d(&maps.qkv_k, b_qk, sQ, c0, r0);
+                tma_load_2d(&maps.qkv_k, b_qk, sQ + KB_BYTES, c0 + 32, r0);
+                tma_load_2d(&maps.qkv_k, b_qk, sK, c0, p.rows + r0);
+                tma_load_2d(&maps.qkv_k, b_qk, sK + KB_BYTES, c0 + 32, p.rows + r0);
+                mbar_expect_tx(b_v, TILE_BYTES);
+                tma_load_2d(&maps.qkv_mn, b_v, sV, c0, 2 * p.rows + r0);
+                tma_load_2d(&maps.qkv_mn, b_v, sV + KB_BYTES, c0 + 32, 2 * p.rows + r0);
+                mbar_wait(b_qk, ph);
+                tc_fence_after();
+                mma_kmajor<SEQ, 2>(tmem, smem_u32(sQ), smem_u32(sK));
+                umma_commit(b_s);
+                mbar_wait(b_p, ph);
+                mbar_wait(b_v, ph);
+                tc_fence_after();
+                mma_mn_b(tmem + 128, smem_u32(sQ), smem_u32(sV));
+                umma_commit(b_o);
+            }
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3;                      // TMEM lane quarter of this warp
+        const int row = 32 * q + lane;
+        const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int b = tile / p.heads, h = tile - b * p.heads;
+            mbar_wait(b_s, ph);
+            tc_fence_after();
+            // pass 1: row maximum
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(v, t_row + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) m = fmaxf(m, __uint_as_float(v[k]));
+            }
+            // pass 2: exp(alpha (s - max)) as ex2 of a single fma; the unnormalised values are the A operand of P V
+            const float mneg = -m * p.scale_log2e;
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                float x[32];
+                tmem_ld32(v, t_row + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    x[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2e, mneg));
+                    sum += x[k];
+                }
+                store_row_chunk(sQ, c, row, x);      // Q and K tiles are dead: S is complete
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(b_p);
+            p.lse[(size_t)tile * SEQ + row] = m * p.scale + __logf(sum);
+            const float inv = 1.0f / sum;
+            mbar_wait(b_o, ph);
+            tc_fence_after();
+            float* orow = p.out + (size_t)(b * SEQ + row) * H + h * HD;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(v, t_row + 128 + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4*>(orow + c * 32)[j] =
+                        make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                                    __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+            }
+            tc_fence_before();
+            mbar_arrive(b_done);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+    }
+}
+
+// ======================================= backward ========================================================
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
+    LG_PDL_TRIGGER();
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sX = smem;                        // 64 KB: Q_k | K_k, then P^T, then dS^T
+    uint8_t* sY = smem + 2 * TILE_BYTES;       // 64 KB: dO_k | V_k, then dS
+    uint8_t* sZ1 = smem + 4 * TILE_BYTES;      // 32 KB: dO (MN-major), then Q (MN-major)
+    uint8_t* sZ2 = smem + 5 * TILE_BYTES;      // 32 KB: K (MN-major)
+    uint64_t* bars = (uint64_t*)(smem + 6 * TILE_BYTES);
+    uint64_t* b_ld1 = bars;         // Q_k, K_k, dO_k, V_k landed
+    uint64_t* b_ld2 = bars + 1;     // dO_mn, K_mn landed
+    uint64_t* b_sdp = bars + 2;     // S and dP complete
+    uint64_t* b_op1 = bars + 3;     // P^T and dS staged (128 arrivals)
+    uint64_t* b_dvdq = bars + 4;    // dV and dQ complete
+    uint64_t* b_ld3 = bars + 5;     // Q_mn landed
+    uint64_t* b_op2 = bars + 6;     // dS^T staged (128 arrivals)
+    uint64_t* b_dk = bars + 7;      // dK complete
+    uint64_t* b_done = bars + 8;    // rows stored (128 arrivals)
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = p.heads * HD;
+    const int tiles = p.batch * p.heads;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(b_ld1, 1); mbar_init(b_ld2, 1); mbar_init(b_sdp, 1); mbar_init(b_op1, 128); mbar_init(b_dvdq, 1);
+        mbar_init(b_ld3, 1); mbar_init(b_op2, 128); mbar_init(b_dk, 1); mbar_init(b_done, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.do_k));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.do_mn));
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;   // S 0..127 | dP 128..255 | dV 256..319 | dQ 320..383 | dK 384..447
+    LG_PDL_WAIT();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const uint32_t ph = it & 1;
+                const int b = tile / p.heads, h = tile - b * p.heads;
+                const int r0 = b * SEQ, c0 = h * HD;
+                if (it > 0) mbar_wait(b_done, ph ^ 1);
+                mbar_expect_tx(b_ld1, 4 * TILE_BYTES);
+                tma_load_2d(&maps.qkv_k, b_ld1, sX, c0, r0);                                   // Q
+                tma_load_2d(&maps.qkv_k, b_ld1, sX + KB_BYTES, c0 + 32, r0);
+                tma_load_2d(&maps.qkv_k, b_ld1, sX + TILE_BYTES, c0, p.rows + r0);             // K
+                tma_load_2d(&maps.qkv_k, b_ld1, sX + TILE_BYTES + KB_BYTES, c0 + 32, p.rows + r0);
+                tma_load_2d(&maps.do_k, b_ld1, sY, c0, r0);                                    // dO
+                tma_load_2d(&maps.do_k, b_ld1, sY + KB_BYTES, c0 + 32, r0);
+                tma_load_2d(&maps.qkv_k, b_ld1, sY + TILE_BYTES, c0, 2 * p.rows + r0);         // V
+                tma_load_2d(&maps.qkv_k, b_ld1, sY + TILE_BYTES + KB_BYTES, c0 + 32, 2 * p.rows + r0);
+                mbar_expect_tx(b_ld2, 2 * TILE_BYTES);
+                tma_load_2d(&maps.do_mn, b_ld2, sZ1, c0, r0);
+                tma_load_2d(&maps.do_mn, b_ld2, sZ1 + KB_BYTES, c0 + 32, r0);
+                tma_load_2d(&maps.qkv_mn, b_ld2, sZ2, c0, p.rows + r0);
+                tma_load_2d(&maps.qkv_mn, b_ld2, sZ2 + KB_BYTES, c0 + 32, p.rows + r0);
+                mbar_wait(b_ld1, ph);
+                tc_fence_after();
+                mma_kmajor<SEQ, 2>(tmem, smem_u32(sX), smem_u32(sX + TILE_BYTES));             // S  = Q K^T
+                mma_kmajor<SEQ, 2>(tmem + 128, smem_u32(sY), smem_u32(sY + TILE_BYTES));       // dP = dO V^T
+                umma_commit(b_sdp);
+                mbar_wait(b_op1, ph);
+                mbar_wait(b_ld2, ph);
+                tc_fence_after();
+                mma_mn_b(tmem + 256, smem_u32(sX), smem_u32(sZ1));                             // dV = P^T dO
+                mma_mn_b(tmem + 320, smem_u32(sY), smem_u32(sZ2));                             // dQ = dS K
+                umma_commit(b_dvdq);
+                mbar_wait(b_dvdq, ph);                                                         // Z1 (and X) are free
+                mbar_expect_tx(b_ld3, TILE_BYTES);
+                tma_load_2d(&maps.qkv_mn, b_ld3, sZ1, c0, r0);                                 // Q, MN-major
+                tma_load_2d(&maps.qkv_mn, b_ld3, sZ1 + KB_BYTES, c0 + 32, r0);
+                mbar_wait(b_op2, ph);
+                mbar_wait(b_ld3, ph);
+                tc_fence_after();
+                mma_mn_b(tmem + 384, smem_u32(sX), smem_u32(sZ1));                             // dK = dS^T Q
+                umma_commit(b_dk);
+            }
+        }
+    } else if (warp >= 2) {
+        const int q = warp & 3;
+        const int row = 32 * q + lane;
+        const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int b = tile / p.heads, h = tile - b * p.heads;
+            const size_t grow = (size_t)(b * SEQ + row) * H + h * HD;
+            // D = rowsum(dO o O) and the row's LSE, fetched while the loads and the first products are in flight
+            float dsum = 0.f;
+            {
+                const float4* po = reinterpret_cast<const float4*>(p.o + grow);
+                const float4* pg = reinterpret_cast<const float4*>(p.dout + grow);
+#pragma unroll
+                for (int j = 0; j < HD / 4; ++j) {
+                    const float4 a = __ldg(po + j), g = __ldg(pg + j);
+                    dsum += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+                }
+            }
+            const float lneg = -p.lse[(size_t)tile * SEQ + row] * 1.4426950408889634f;
+            mbar_wait(b_sdp, ph);
+            tc_fence_after();
+            // pass A: P^T -> X (transposed), dS -> Y (row form)
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t s[32], g[32];
+                float pv[32], ds[32];
+                tmem_ld32(s, t_row + c * 32);
+                tmem_ld32(g, t_row + 128 + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    pv[k] = ex2(fmaf(__uint_as_float(s[k]), p.scale_log2e, lneg));
+                    ds[k] = p.scale * pv[k] * (__uint_as_float(g[k]) - dsum);
+                }
+                store_col_chunk(sX, row, c * 32, pv);
+                store_row_chunk(sY, c, row, ds);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(b_op1);
+            mbar_wait(b_dvdq, ph);
+            tc_fence_after();
+            // pass B: dS^T -> X (dV has consumed P^T)
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t s[32], g[32];
+                float ds[32];
+                tmem_ld32(s, t_row + c * 32);
+                tmem_ld32(g, t_row + 128 + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float pk = ex2(fmaf(__uint_as_float(s[k]), p.scale_log2e, lneg));
+                    ds[k] = p.scale * pk * (__uint_as_float(g[k]) - dsum);
+                }
+                store_col_chunk(sX, row, c * 32, ds);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(b_op2);
+            // dV (rows = keys) and dQ (rows = queries) while dK is being formed
+            float* dq = p.dqkv + grow;
+            float* dk = p.dqkv + (size_t)p.rows * H + grow;
+            float* dv = p.dqkv + 2 * (size_t)p.rows * H + grow;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32], w[32];
+                tmem_ld32(v, t_row + 256 + c * 32);
+                tmem_ld32(w, t_row + 320 + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    reinterpret_cast<uint4*>(dv + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    reinterpret_cast<uint4*>(dq + c * 32)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                }
+            }
+            mbar_wait(b_dk, ph);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(v, t_row + 384 + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<uint4*>(dk + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            tc_fence_before();
+            mbar_arrive(b_done);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+int make_map_2d(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t ld, CUtensorMapSwizzle swz) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)SEQ};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+constexpr size_t FWD_SMEM = 3 * TILE_BYTES + 128 + 1024;
+constexpr size_t BWD_SMEM = 6 * TILE_BYTES + 128 + 1024;
+
+int check_shape(const char* who, int dtype, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
+    LG_REQUIRE(dtype == LG_F32 && seq == SEQ && head_dim == HD && batch >= 1 && heads >= 1 &&
+                   batch * heads < (1 << 30) && batch * seq < (1ll << 30),
+               "%s: the fused kernel takes float32, seq = %d, head_dim = %d (ask lg_attention_supported first)", who, SEQ, HD);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lg_attention_supported(int dtype, int64_t seq, int64_t head_dim) {
+    static const bool off = getenv("LG_NO_FUSED_ATTENTION") != nullptr;
+    return (!off && dtype == LG_F32 && seq == SEQ && head_dim == HD) ? 1 : 0;
+}
+
+int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
+                     double scale, void* out, void* lse) {
+    LG_INIT();
+    if (check_shape("lg_attention_fwd", dtype, batch, seq, heads, head_dim)) return 1;
+    LG_REQUIRE((((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, "lg_attention_fwd: buffers must be 16-byte aligned");
+    if (load_encode()) return 1;
+    const int64_t rows = batch * seq, H = heads * head_dim;
+    AttnMaps maps;
+    if (make_map_2d(&maps.qkv_k, qkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map_2d(&maps.qkv_mn, qkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    maps.do_k = maps.qkv_k;
+    maps.do_mn = maps.qkv_mn;
+    AttnParams p = {};
+    p.batch = (int)batch;
+    p.heads = (int)heads;
+    p.rows = (int)rows;
+    p.scale = (float)scale;
+    p.scale_log2e = (float)(scale * 1.4426950408889634);
+    p.out = (float*)out;
+    p.lse = (float*)lse;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LG_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+        attr_done = true;
+    }
+    const int tiles = (int)(batch * heads);
+    const int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+    attention_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, stream()>>>(maps, p);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout, const void* lse, int64_t batch,
+                     int64_t seq, int64_t heads, int64_t head_dim, double scale, void* dqkv) {
+    LG_INIT();
+    if (check_shape("lg_attention_bwd", dtype, batch, seq, heads, head_dim)) return 1;
+    LG_REQUIRE((((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv) & 15) == 0,
+               "lg_attention_bwd: buffers must be 16-byte aligned");
+    if (load_encode()) return 1;
+    const int64_t rows = batch * seq, H = heads * head_dim;
+    AttnMaps maps;
+    if (make_map_2d(&maps.qkv_k, qkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map_2d(&maps.qkv_mn, qkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    if (make_map_2d(&maps.do_k, dout, H, rows, H, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map_2d(&maps.do_mn, dout, H, rows, H, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    AttnParams p = {};
+    p.batch = (int)batch;
+    p.heads = (int)heads;
+    p.rows = (int)rows;
+    p.scale = (float)scale;
+    p.scale_log2e = (float)(scale * 1.4426950408889634);
+    p.lse = (float*)lse;
+    p.o = (const float*)out;
+    p.dout = (const float*)dout;
+    p.dqkv = (float*)dqkv;
+    static bool attr_done = false;
+    if (!attr_done) {
+        LG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+        attr_done = true;
+    }
+    const int tiles = (int)(batch * heads);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    attention_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, stream()>>>(maps, p);
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

@@ -33,6 +33,7 @@ namespace {
 constexpr int MC_MAX_CTAS = 1024;
 constexpr int MC_THREADS = 128;
 constexpr size_t MC_FLAG_BYTES = 2 * MC_MAX_CTAS * sizeof(unsigned int);
+constexpr int TRACE_MAX = 4096;
 
 struct Drv {
     bool loaded = false;
@@ -92,6 +93,8 @@ struct Region {
     CUdeviceptr local = 0, mcva = 0;
     unsigned int* epochs = nullptr;   // plain device memory: launches seen so far, per CTA index
     int grid = 0;                // CTAs of every exchange launch (identical on all ranks)
+    unsigned long long* trace = nullptr;   // LG_MC_TRACE=1: 4 x u64 per record, TRACE_MAX records (device memory)
+    int trace_n = 0;
 } rg;
 
 CUmulticastObjectProp mc_prop(size_t bytes, int world) {
@@ -127,6 +130,11 @@ __device__ __forceinline__ void mc_st(float* mc_addr, const float4& v) {
 __device__ __forceinline__ void mc_arrive(unsigned int* mc_flag) {
     asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_flag), "r"(1u) : "memory");
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -161,21 +169,33 @@ struct McArgs {
     const float* c1;           // per-tensor bias corrections (adam_prep_kernel): c1 | c2 | 1/c1 | 1/c2
     const float* c2;
     float neg_lr, b1, b2, omb1, omb2, eps, inv_world, momentum;
+    unsigned long long* trace;  // LG_MC_TRACE: {entered, all ranks met, finished} of CTA 0 in globaltimer ns, or nullptr
 };
+
+// a time stamp on whatever stream it is launched on (LG_MC_TRACE: where the compute stream is while buckets run)
+__global__ void mc_mark_kernel(unsigned long long* slot) {
+    LG_PDL_TRIGGER();
+    *slot = globaltimer_ns();
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a) {
     LG_PDL_TRIGGER();
     // ---- every rank's gradients of this bucket are final once its kernel runs (stream order on that rank):
     //      meet the CTAs of this index on all ranks
-    __shared__ unsigned int s_epoch;
+    // (no shared memory at all: next to a tensor-core GEMM CTA an SM has room for the 1 KB every CTA reserves, not more)
+    unsigned int epoch = 0;                                  // thread 0 only
     if (threadIdx.x == 0) {
-        const unsigned int e = a.epochs[blockIdx.x] + 1;
-        a.epochs[blockIdx.x] = e;
-        s_epoch = e;
+        epoch = a.epochs[blockIdx.x] + 1;
+        a.epochs[blockIdx.x] = epoch;
+        if (a.trace && blockIdx.x == 0) {
+            a.trace[0] = globaltimer_ns();
+            a.trace[3] = (unsigned long long)(a.hi - a.lo) * 4;
+        }
         __threadfence_system();                              // this rank's earlier writes precede its arrival
         mc_arrive(a.mc_flags + blockIdx.x);
-        mc_wait(a.flags + blockIdx.x, e * (unsigned)a.world);
+        mc_wait(a.flags + blockIdx.x, epoch * (unsigned)a.world);
+        if (a.trace && blockIdx.x == 0) a.trace[1] = globaltimer_ns();
     }
     __syncthreads();
     // ---- this rank's share of the bucket: vectors [v0, v1)
@@ -233,7 +253,8 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
     if (threadIdx.x == 0) {
         __threadfence_system();
         mc_arrive(a.mc_flags + MC_MAX_CTAS + blockIdx.x);
-        mc_wait(a.flags + MC_MAX_CTAS + blockIdx.x, s_epoch * (unsigned)a.world);
+        mc_wait(a.flags + MC_MAX_CTAS + blockIdx.x, epoch * (unsigned)a.world);
+        if (a.trace && blockIdx.x == 0) a.trace[2] = globaltimer_ns();
     }
 }
 
@@ -348,9 +369,42 @@ int lg_mc_bind(void** local_ptr, void** mc_ptr) {
     rg.grid = env ? atoi(env) : sm_count();
     if (rg.grid < 1) rg.grid = 1;
     if (rg.grid > MC_MAX_CTAS) rg.grid = MC_MAX_CTAS;
+    if (getenv("LG_MC_TRACE")) {
+        LG_CUDA(cudaMalloc((void**)&rg.trace, (size_t)TRACE_MAX * 4 * sizeof(unsigned long long)));
+        LG_CUDA(cudaMemset(rg.trace, 0, (size_t)TRACE_MAX * 4 * sizeof(unsigned long long)));
+    }
     rg.bound = true;
     *local_ptr = (void*)rg.local;
     *mc_ptr = (void*)rg.mcva;
+    return 0;
+}
+
+// LG_MC_TRACE=1: lg_mc_trace_mark stamps the CURRENT stream's position in time; lg_mc_trace_read drains the device and
+// copies out up to max_records records of 4 x uint64 {entered, all ranks met, finished, bytes} (globaltimer ns; a mark
+// is {t, 0, 0, 0}) in launch order.  Launches captured into a CUDA graph keep their slots, so after a replay the trace
+// is that replay's timeline; reset != 0 clears the trace (only when no captured step will be replayed any more).
+int lg_mc_trace_mark(void) {
+    LG_INIT();
+    if (!rg.trace || rg.trace_n >= TRACE_MAX) return 0;
+    mc_mark_kernel<<<1, 1, 0, stream()>>>(rg.trace + 4 * (size_t)rg.trace_n);
+    ++rg.trace_n;
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+int lg_mc_trace_read(uint64_t* out, int max_records, int* n_records, int reset) {
+    LG_INIT();
+    *n_records = 0;
+    if (!rg.trace) return 0;
+    LG_CUDA(cudaDeviceSynchronize());
+    const int n = rg.trace_n < max_records ? rg.trace_n : max_records;
+    if (n > 0) LG_CUDA(cudaMemcpy(out, rg.trace, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) {
+        // (not while a captured step that recorded slots is still going to be replayed)
+        LG_CUDA(cudaMemset(rg.trace, 0, (size_t)TRACE_MAX * 4 * sizeof(unsigned long long)));
+        rg.trace_n = 0;
+    }
+    *n_records = n;
     return 0;
 }
 
@@ -366,6 +420,7 @@ int lg_mc_release(void) {
         drv.cuMemAddressFree(rg.local, rg.bytes);
         drv.cuMemRelease(rg.mem);
         cudaFree(rg.epochs);
+        if (rg.trace) cudaFree(rg.trace);
     }
     drv.cuMemRelease(rg.mc);
     rg = Region();
@@ -412,6 +467,11 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
     a.eps = (float)eps;
     a.inv_world = 1.0f / (float)world;
     a.momentum = (float)momentum;
+    a.trace = nullptr;
+    if (rg.trace && rg.trace_n < TRACE_MAX) {
+        a.trace = rg.trace + 4 * (size_t)rg.trace_n;     // (a captured launch keeps its slot: every replay rewrites it)
+        ++rg.trace_n;
+    }
     float* corr = nullptr;
     if (kind <= 1) {
         LG_REQUIRE(n_seg >= 1 && seg_end_dev && t_dev && m && v, "lg_mc_exchange_step: Adam needs its state and segments");

@@ -361,6 +361,8 @@ class DataParallel(object):
             Gradients.leaf_hook = prev
             if reserve > 0:
                 api.gemm_sm_limit(0)
+        if self._mc is not None and os.environ.get('LG_MC_TRACE'):
+            api.mc_trace_mark()                               # (measurement aid) the compute stream finished backward
         for b in range(len(self._buckets)):                   # parameters the loss does not reach
             if not launched[b]:
                 launch(b)

@@ -305,6 +305,41 @@ class FakeDevice(object):
 
     def prof_gemm(self, enable): pass
 
+    # ---- fused attention: same contract as the kernels (fp32, seq 128, head_dim 64)
+    def attention_supported(self, dt, seq, hd):
+        return 1 if (dt == rt.F32 and seq == 128 and hd == 64) else 0
+
+    @staticmethod
+    def _heads(x, b, s, h, d):
+        return x.reshape(b, s, h, d).transpose(0, 2, 1, 3)
+
+    def attention_fwd(self, dt, qkv, b, s, h, d, scale, out, lse):
+        self.launches += 1
+        X = _arr(qkv, dt, [3, b * s, h * d])
+        q, k, v = (self._heads(X[i], b, s, h, d) for i in range(3))
+        sc = np.float32(scale) * (q @ k.transpose(0, 1, 3, 2))
+        m = sc.max(axis=-1, keepdims=True)
+        e = np.exp(sc - m)
+        z = e.sum(axis=-1, keepdims=True)
+        o = (e / z) @ v
+        _arr(out, dt, [b, s, h, d])[...] = o.transpose(0, 2, 1, 3)
+        _arr(lse, dt, [b, h, s])[...] = (m + np.log(z))[..., 0]
+
+    def attention_bwd(self, dt, qkv, out, dout, lse, b, s, h, d, scale, dqkv):
+        self.launches += 1
+        X = _arr(qkv, dt, [3, b * s, h * d])
+        q, k, v = (self._heads(X[i], b, s, h, d) for i in range(3))
+        o = self._heads(_arr(out, dt, [b * s, h * d]), b, s, h, d)
+        do = self._heads(_arr(dout, dt, [b * s, h * d]), b, s, h, d)
+        L = _arr(lse, dt, [b, h, s])[..., None]
+        p = np.exp(np.float32(scale) * (q @ k.transpose(0, 1, 3, 2)) - L)
+        dp = do @ v.transpose(0, 1, 3, 2)
+        ds = np.float32(scale) * p * (dp - (do * o).sum(axis=-1, keepdims=True))
+        G = _arr(dqkv, dt, [3, b, s, h, d])
+        G[0] = (ds @ k).transpose(0, 2, 1, 3)
+        G[1] = (ds.transpose(0, 1, 3, 2) @ q).transpose(0, 2, 1, 3)
+        G[2] = (p.transpose(0, 1, 3, 2) @ do).transpose(0, 2, 1, 3)
+
     def prof_gemm_read(self, ms, n, fl):
         ms._obj.value, n._obj.value, fl._obj.value = 0.0, 0, 0.0
 
@@ -461,6 +496,11 @@ class FakeDevice(object):
 
     def mc_release(self):
         self._mc_block = None
+
+    def mc_trace_mark(self): pass
+
+    def mc_trace_read(self, out, max_records, n, reset):
+        n._obj.value = 0
 
     def mc_exchange_step(self, kind, goff, poff, foff, lo, hi, rank, world, m, v, n_seg, seg_end, t_dev, lr, b1, b2,
                          eps, momentum, seg_offset, t_advance):

@@ -102,8 +102,9 @@ def _oracle_attention(T, x, wq, bq, wk, bk, wv, bv, heads):
 
 # (4,100,128,2): ragged rows inside the fused softmax epilogue; (4,64,128,2): its 64-column tile; (2,132,128,2): too
 # long for the row epilogue -> separate softmax kernels
+# (2,128,128,2) and (3,128,768,12): seq 128 x head_dim 64 -> the one-kernel attention (lg_attention_fwd / _bwd) in tf32 mode
 @pytest.mark.parametrize("cfg", [(2, 16, 64, 4), (3, 128, 256, 4), (2, 24, 96, 3), (4, 100, 128, 2), (4, 64, 128, 2),
-                                 (2, 132, 128, 2)])
+                                 (2, 132, 128, 2), (2, 128, 128, 2), (3, 128, 768, 12)])
 @pytest.mark.parametrize("preset_grads", [False, True])
 def test_self_attention_matches_oracle(mode, cfg, preset_grads):
     b, s, H, heads = cfg
@@ -327,3 +328,36 @@ def test_tied_embedding_and_projection_weight(mode, preset_grads):
     tol = _tol(mode) * (10 if mode == 'fp32' else 1)
     assert rel(got_y, want_y) <= tol
     assert rel(got_g, want_g) <= tol
+
+
+@pytest.mark.gpu
+def test_fused_attention_kernel_equals_the_composed_path_at_bert_batch(cuda):
+    """384 (batch, head) tiles -- more than the persistent grids hold at once, so every CTA loops over several tiles --
+    against the batched-GEMM path with the same tf32 products (lg_gemm + softmax epilogues)."""
+    b, s, H, heads = 32, 128, 768, 12
+    rs = np.random.RandomState(11)
+    x = rs.uniform(-1, 1, (b, s, H)).astype(np.float32)
+    ws = [(rs.uniform(-1, 1, (H, H)) / math.sqrt(H)).astype(np.float32) for _ in range(3)]
+    bs = [rs.uniform(-0.1, 0.1, (H,)).astype(np.float32) for _ in range(3)]
+    up = rs.uniform(-1, 1, (b, s, H)).astype(np.float32)
+    prev = ops.set_matmul_mode('tf32')
+    try:
+        def run(fused):
+            (ops._DISABLED.discard if fused else ops._DISABLED.add)('attn_fused')
+            X = CudaTensor.from_numpy(x)
+            W = [CudaTensor.from_numpy(w) for w in ws]
+            B = [CudaTensor.from_numpy(v) for v in bs]
+            n0 = rt.launch_count()
+            out = X.self_attention(W[0], B[0], W[1], B[1], W[2], B[2], heads=heads)
+            (out * CudaTensor.from_numpy(up, requires_grad=False)).sum().backward()
+            return out.numpy(), [X.grad.numpy()] + [p.grad.numpy() for p in W + B], rt.launch_count() - n0
+        want_out, want_g, n_composed = run(False)
+        got_out, got_g, n_fused = run(True)
+    finally:
+        ops._DISABLED.discard('attn_fused')
+        ops.set_matmul_mode(prev)
+    assert n_fused < n_composed                       # 2 launches instead of 6 batched GEMMs
+    assert rel(got_out, want_out) <= 2e-3
+    gmax = max(float(np.abs(g).max()) for g in want_g)
+    for g, w in zip(got_g, want_g):
+        assert float(np.abs(g - w).max()) <= 2e-3 * max(float(np.abs(w).max()), 1e-3 * gmax)
