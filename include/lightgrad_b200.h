@@ -224,6 +224,16 @@ int lg_prof_gemm_read(double* total_ms, uint64_t* launches, double* total_flops)
 /* 1 if the tensor-core kernel can take this problem in `mode` without a fallback */
 int lg_gemm_tc_supported(int mode, int dtype, const LgGemmDesc* d);
 
+/* ---- convolution lowering (replaces the window view + python fold loop of cpu/ops.py:298-355) ------------------
+ * n window dims (1..4) over the trailing dims of a contiguous (lead, in_0..in_{n-1}) block; kernel extents k_d,
+ * strides s_d, positions pos_d = (in_d - k_d) / s_d + 1.  `cols` is contiguous (lead, pos_0..pos_{n-1}, k_0..k_{n-1}).
+ *   lg_im2col: cols[l, p, k] = x[l, p*s + k]                     (unfold: the matmul operand of conv forward)
+ *   lg_col2im: dx[l, i] = sum_{p*s + k = i} cols[l, p, k]        (fold: input gradient of conv backward; a gather) */
+int lg_im2col(int dtype, int n, int64_t lead, const int64_t* in_dims, const int64_t* k_dims, const int64_t* strides,
+              const void* x, void* cols);
+int lg_col2im(int dtype, int n, int64_t lead, const int64_t* in_dims, const int64_t* k_dims, const int64_t* strides,
+              const void* cols, void* dx);
+
 /* ---- indexing (replaces cpu getitem/setitem with integer-array indices) -------------------- */
 /* rows: out[i, :] = src[idx[i], :]; src rows `row_stride` elements apart, row_len contiguous */
 int lg_gather_rows(int dtype, int idx_dtype, const void* src, int64_t n_src_rows, int64_t row_stride,

@@ -1647,59 +1647,68 @@ CudaTensor.fused_cross_entropy_backward = staticmethod(cross_entropy_backward)
 
 
 # ---------------------------------------------------------------------------------------------------
-# convolution (cpu/ops.py:298-356): im2col as a strided window view + the GEMM above
-def _window_view(t, kshape, strides):
-    n = len(kshape)
-    shape = t._shape[:-n] + tuple((d - k) // s + 1 for d, k, s in zip(t._shape[-n:], kshape, strides)) + tuple(kshape)
-    st = t._strides[:-n] + tuple(ts * ws for ts, ws in zip(t._strides[-n:], strides)) + t._strides[-n:]
-    return t._view(shape, st)
+# convolution (cpu/ops.py:298-356 of the reference): unfold (lg_im2col) + matmul; backward = two matmuls + fold
+# (lg_col2im, a gather: one launch instead of one strided add per kernel offset)
+def _conv_geometry(t_shape, k_shape, strides):
+    """(leading extent, window input dims, positions per window dim) of ``n = len(k_shape)`` trailing dims."""
+    n = len(k_shape)
+    in_dims = tuple(t_shape[-n:])
+    for d, k, s in zip(in_dims, k_shape, strides):
+        if k > d or s < 1:
+            raise ValueError("conv: kernel %s with strides %s does not fit an input of %s" % (k_shape, strides, in_dims))
+    pos = tuple((d - k) // s + 1 for d, k, s in zip(in_dims, k_shape, strides))
+    return _prod(t_shape[:-n]), in_dims, pos
 
 
 @CudaTensor.register_op()
 class conv(Function):
     def forward(ctx, t, kernel, strides=1):
+        """``t``: (..., C, *spatial); ``kernel``: (out_channels, C, *k).  The channel dim is a window dim with kernel
+        extent C and stride 1, exactly as in the reference, so any number of spatial dims up to 3 works."""
         t, kernel = _promote(t, kernel)
-        n, m = len(kernel._shape) - 1, len(t._shape)
-        strides = ((strides,) * n) if isinstance(strides, int) else \
-            ((1,) + tuple(strides) if len(strides) == n - 1 else tuple(strides))
-        assert m >= n == len(strides)
-        kshape = kernel._shape[1:]
-        win = _window_view(t, kshape, strides)
-        lead = win._shape[:-n]
-        cols = _ew1(EW['COPY'], win)                       # im2col gather (one strided copy)
-        flat_x = cols._view((_prod(lead), _prod(kshape)), None)
-        flat_w = kernel.contiguous()._view((kernel._shape[0], _prod(kshape)), None)
-        y = _gemm(flat_x, _swap_last(flat_w))              # (positions, out_channels)
-        flat_x._mark_shared()
-        ctx.save_for_backward(flat_x, flat_w, t._shape, kernel._shape, strides, lead)
-        y = _with_shape(y, lead + (kernel._shape[0],))
-        # move the channel axis to where the collapsed input-channel axis was, then drop that axis
-        nd = len(y._shape)
+        n = len(kernel._shape) - 1
+        if isinstance(strides, (int, np.integer)):
+            strides = (int(strides),) * n
+        elif len(strides) == n - 1:
+            strides = (1,) + tuple(int(s) for s in strides)
+        else:
+            strides = tuple(int(s) for s in strides)
+        if not (len(t._shape) >= n == len(strides)) or n > 4:
+            raise ValueError("conv: input %s, kernel %s, strides %s do not go together" % (t._shape, kernel._shape, strides))
+        k_shape = kernel._shape[1:]
+        lead, in_dims, pos = _conv_geometry(t._shape, k_shape, strides)
+        n_pos, n_k, out_c = _prod(pos), _prod(k_shape), kernel._shape[0]
+        x = t.contiguous()
+        cols = CudaTensor._new((lead * n_pos, n_k), x._dtype)
+        if cols._numel:
+            rt.api.im2col(x._code, n, lead, i64arr(in_dims), i64arr(k_shape), i64arr(strides), x.ptr, cols.ptr)
+        flat_w = kernel.contiguous()._view((out_c, n_k), None)
+        y = _gemm(cols, _swap_last(flat_w))                  # (lead * positions, out_channels)
+        cols._mark_shared()
+        ctx.save_for_backward(cols, flat_w, t._shape, kernel._shape, strides, (lead, in_dims, pos))
+        # (..., 1, *spatial positions, out_channels) -> channels take the place of the collapsed channel dim
+        full = tuple(t._shape[:-n]) + pos + (out_c,)
+        y = _with_shape(y, full)
+        nd = len(full)
         perm = list(range(nd))
-        perm[-n - 1], perm[-1] = perm[-1], perm[-n - 1]
+        perm[nd - n - 1], perm[nd - 1] = perm[nd - 1], perm[nd - n - 1]
         y = y.transpose(*perm)
         assert y._shape[-1] == 1
         return y._view(y._shape[:-1], y._strides[:-1])
 
     def backward(ctx, out_grad):
-        flat_x, flat_w, in_shape, w_shape, strides, lead = ctx.get_saved_tensors()
+        cols, flat_w, in_shape, w_shape, strides, (lead, in_dims, pos) = ctx.get_saved_tensors()
         n = len(w_shape) - 1
-        g = out_grad if out_grad._code == flat_x._code else out_grad.astype(flat_x._dtype)
+        g = out_grad if out_grad._code == cols._code else out_grad.astype(cols._dtype)
         nd = len(g._shape)
+        # channels last again: (..., *positions, out_channels) -> (lead * positions, out_channels)
         perm = [i for i in range(nd) if i != nd - n] + [nd - n]
-        flat_g = g.transpose(*perm).contiguous()._view((_prod(g._shape) // w_shape[0], w_shape[0]), None)
-        flat_xg = _gemm(flat_g, flat_w)                     # (positions, in_c*k*k)
-        w_grad = _with_shape(_gemm(_swap_last(flat_g), flat_x), w_shape)
-        # col2im: add every kernel-offset plane back into the input gradient (windows overlap)
-        x_grad = CudaTensor.zeros(in_shape, dtype=flat_x._dtype, requires_grad=False)
-        xw = _window_view(x_grad, w_shape[1:], strides)
-        src = _with_shape(flat_xg, xw._shape)
-        k_nd = len(w_shape[1:])
-        for pos in np.ndindex(*w_shape[1:]):
-            sel = (slice(None),) * (len(xw._shape) - k_nd) + tuple(pos)
-            dst = _basic_view(xw, list(sel))
-            _ewn(EW['ADD'], (dst, _basic_view(src, list(sel))), out=dst)
-        x_grad._temp = True
+        flat_g = g.transpose(*perm).contiguous()._view((lead * _prod(pos), w_shape[0]), None)
+        dcols = _gemm(flat_g, flat_w, cls='X')               # gradient of the unfolded input
+        w_grad = _with_shape(_gemm(_swap_last(flat_g), cols, cls='W'), w_shape)
+        x_grad = CudaTensor._new(in_shape, cols._dtype, requires_grad=False)
+        if x_grad._numel:
+            rt.api.col2im(cols._code, n, lead, i64arr(in_dims), i64arr(w_shape[1:]), i64arr(strides), dcols.ptr, x_grad.ptr)
         return x_grad, w_grad
 
 

@@ -86,6 +86,8 @@ _SIGNATURES = {
     'lg_gemm_sm_limit': [C.c_int],
     'lg_prof_gemm': [C.c_int],
     'lg_prof_gemm_read': [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)],
+    'lg_im2col': [C.c_int, C.c_int, C.c_int64, _i64p, _i64p, _i64p, _vp, _vp],
+    'lg_col2im': [C.c_int, C.c_int, C.c_int64, _i64p, _i64p, _i64p, _vp, _vp],
     'lg_gather_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp],
     'lg_scatter_add_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp],
     'lg_scatter_set_rows': [C.c_int, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, C.c_double],

@@ -343,6 +343,31 @@ class FakeDevice(object):
     def prof_gemm_read(self, ms, n, fl):
         ms._obj.value, n._obj.value, fl._obj.value = 0.0, 0, 0.0
 
+    # ---- convolution lowering
+    @staticmethod
+    def _windows(x, n, k, s):
+        shape = x.shape[:-n] + tuple((d - kk) // ss + 1 for d, kk, ss in zip(x.shape[-n:], k, s)) + tuple(k)
+        strides = x.strides[:-n] + tuple(ts * ss for ts, ss in zip(x.strides[-n:], s)) + x.strides[-n:]
+        return np.lib.stride_tricks.as_strided(x, shape=shape, strides=strides)
+
+    def im2col(self, dt, n, lead, in_dims, k_dims, strides, x, cols):
+        self.launches += 1
+        ind, k, s = _lst(in_dims, n), _lst(k_dims, n), _lst(strides, n)
+        X = _arr(x, dt, [lead] + ind)
+        win = self._windows(X, n, k, s)
+        _arr(cols, dt, win.shape)[...] = win
+
+    def col2im(self, dt, n, lead, in_dims, k_dims, strides, cols, dx):
+        self.launches += 1
+        ind, k, s = _lst(in_dims, n), _lst(k_dims, n), _lst(strides, n)
+        DX = _arr(dx, dt, [lead] + ind)
+        DX[...] = 0
+        win = self._windows(DX, n, k, s)
+        Cm = _arr(cols, dt, win.shape)
+        for kidx in np.ndindex(*k):
+            sel = (slice(None),) * (1 + n) + tuple(kidx)
+            win[sel] += Cm[sel]          # one kernel offset at a time: the windows of one offset never overlap
+
     # ---- indexing
     def gather_rows(self, dt, idt, src, n_src, row_stride, idx, n_idx, row_len, out):
         self.launches += 1
