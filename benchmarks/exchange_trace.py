@@ -66,10 +66,12 @@ def main():
         t0 = rec[0, 0]
         marks = [r for r in rec if r[1] == 0 and r[2] == 0]
         buckets = [r for r in rec if r[2] != 0]
-        end_bwd = marks[-1][0]
+        end_step = marks[-1][0]
         out = {'exchange': dp.exchange, 'world': comm.world, 'per_gpu_batch': a.batch, 'mode': a.mode,
                'forward_starts_us': 0.0, 'backward_starts_us': round((marks[1][0] - t0) / 1e3, 1),
-               'step_ends_us': round((end_bwd - t0) / 1e3, 1),
+               # the compute stream's last backward kernel has run (stamp queued right after loss.backward())
+               'backward_compute_ends_us': round((marks[2][0] - t0) / 1e3, 1) if len(marks) >= 4 else None,
+               'step_ends_us': round((end_step - t0) / 1e3, 1),
                'buckets': [{'mbytes': round(r[3] / 1e6, 1), 'entered_us': round((r[0] - t0) / 1e3, 1),
                             'all_ranks_met_us': round((r[1] - t0) / 1e3, 1), 'finished_us': round((r[2] - t0) / 1e3, 1),
                             'busy_us': round((r[2] - r[1]) / 1e3, 1)} for r in buckets]}

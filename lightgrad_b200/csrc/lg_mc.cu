@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
     const int64_t v1 = v0 + per < nv ? v0 + per : nv;
     const int64_t base = a.lo >> 2;
     const int64_t stride = (int64_t)gridDim.x * MC_THREADS;
-    constexpr int U = 4;                                     // independent 16-byte switch reductions in flight per thread
+    // independent 16-byte switch reductions in flight per thread; chosen so that the kernel stays under the ~88
+    // registers per thread that are free on an SM beside a tensor-core GEMM CTA (128 threads x 88 = 11.3 K of 11.7 K)
+    constexpr int U = KIND == 2 ? 4 : 8;
     int seg = 0;
     for (int64_t i0 = v0 + (int64_t)blockIdx.x * MC_THREADS + threadIdx.x; i0 < v1; i0 += stride * U) {
         // the switch reductions have the long latency (NVLink round trip): all U are issued first; the local

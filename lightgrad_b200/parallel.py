@@ -288,7 +288,9 @@ class DataParallel(object):
         parameters in reverse registration order, so buckets complete from the tail of the arena.
         The optimizer (compute stream) waits for the communication stream at the end."""
         if bucket_bytes is None:
-            bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '64')) << 20
+            # the multicast exchange pays ~20 us per bucket but leaves only the LAST bucket (the first layer's parameters
+            # and the word embeddings, whose gradients are final when backward ends) exposed: small buckets
+            bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '24' if self.exchange == 'nvls' else '64')) << 20
         nvls_step = _step_buckets and self.exchange == 'nvls'
         if not nvls_step and (self.world == 1 or not self._nccl or os.environ.get('LG_DP_NO_OVERLAP')):
             loss.backward()
@@ -297,7 +299,8 @@ class DataParallel(object):
         from .autograd import Gradients
         a, params = self.arena, self.optimizer.parameters
         a.adopt_grads(params)
-        if getattr(self, '_buckets', None) is None:
+        if getattr(self, '_buckets', None) is None or getattr(self, '_bucket_bytes', None) != bucket_bytes:
+            self._bucket_bytes = bucket_bytes
             # a parameter's slot runs to the next parameter's (64-element aligned) offset: the zero padding travels along
             ends = list(a.offsets[1:]) + [a.total]
             self._bucket_of, self._buckets = [], []      # per param -> bucket; bucket -> [lo, hi, n_params]
