@@ -112,29 +112,29 @@ struct AttnMaps {
 };
 
 // ======================================= forward =========================================================
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// One persistent CTA per SM, two operand sets: while the tile in one set is being computed, TMA fills the other with
+// the next tile's Q, K, V (a (batch, head) tile is 96 KB of operands for ~3 us of dependent work: without the prefetch
+// every CTA would first wait for its share of HBM bandwidth and then compute with the memory system idle).
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     LG_PDL_TRIGGER();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sQ = smem;                       // 32 KB  (later, with sK: the 64 KB probability operand)
-    uint8_t* sK = smem + TILE_BYTES;          // 32 KB
-    uint8_t* sV = smem + 2 * TILE_BYTES;      // 32 KB  MN-major
-    uint64_t* bars = (uint64_t*)(smem + 3 * TILE_BYTES);
-    uint64_t* b_qk = bars;        // Q, K landed
-    uint64_t* b_v = bars + 1;     // V landed
-    uint64_t* b_s = bars + 2;     // S = Q K^T complete
-    uint64_t* b_p = bars + 3;     // probabilities staged (128 arrivals)
-    uint64_t* b_o = bars + 4;     // O = P V complete
-    uint64_t* b_done = bars + 5;  // rows stored, TMEM / smem reusable (128 arrivals)
-    uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+    // set s at smem + s * 96 KB: Q (32 KB; with K: the 64 KB probability operand once S is complete) | K | V (MN-major)
+    uint64_t* bars = (uint64_t*)(smem + 6 * TILE_BYTES);
+    uint64_t* b_qk = bars;        // [2] Q, K of a set landed
+    uint64_t* b_v = bars + 2;     // [2] V of a set landed
+    uint64_t* b_s = bars + 4;     // S = Q K^T complete
+    uint64_t* b_p = bars + 5;     // probabilities staged (128 arrivals)
+    uint64_t* b_o = bars + 6;     // O = P V complete
+    uint32_t* tmem_slot = (uint32_t*)(bars + 7);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.heads * HD;
     const int tiles = p.batch * p.heads;
 
     if (warp == 0 && lane == 0) {
-        mbar_init(b_qk, 1); mbar_init(b_v, 1); mbar_init(b_s, 1); mbar_init(b_p, 128); mbar_init(b_o, 1);
-        mbar_init(b_done, 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(b_qk + i, 1); mbar_init(b_v + i, 1); }
+        mbar_init(b_s, 1); mbar_init(b_p, 128); mbar_init(b_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
@@ -152,28 +152,38 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
+            auto load_tile = [&](int tile, int set) {
                 const int b = tile / p.heads, h = tile - b * p.heads;
                 const int r0 = b * SEQ, c0 = h * HD;
-                if (it > 0) mbar_wait(b_done, ph ^ 1);           // previous tile's rows are out: smem and TMEM are free
-                mbar_expect_tx(b_qk, 2 * TILE_BYTES);
-                tma_load_2d(&maps.qkv_k, b_qk, sQ, c0, r0);
-                tma_load_2d(&maps.qkv_k, b_qk, sQ + KB_BYTES, c0 + 32, r0);
-                tma_load_2d(&maps.qkv_k, b_qk, sK, c0, p.rows + r0);
-                tma_load_2d(&maps.qkv_k, b_qk, sK + KB_BYTES, c0 + 32, p.rows + r0);
-                mbar_expect_tx(b_v, TILE_BYTES);
-                tma_load_2d(&maps.qkv_mn, b_v, sV, c0, 2 * p.rows + r0);
-                tma_load_2d(&maps.qkv_mn, b_v, sV + KB_BYTES, c0 + 32, 2 * p.rows + r0);
-                mbar_wait(b_qk, ph);
+                uint8_t* sQ = smem + set * 3 * TILE_BYTES;
+                uint8_t* sK = sQ + TILE_BYTES;
+                uint8_t* sV = sQ + 2 * TILE_BYTES;
+                mbar_expect_tx(b_qk + set, 2 * TILE_BYTES);
+                tma_load_2d(&maps.qkv_k, b_qk + set, sQ, c0, r0);
+                tma_load_2d(&maps.qkv_k, b_qk + set, sQ + KB_BYTES, c0 + 32, r0);
+                tma_load_2d(&maps.qkv_k, b_qk + set, sK, c0, p.rows + r0);
+                tma_load_2d(&maps.qkv_k, b_qk + set, sK + KB_BYTES, c0 + 32, p.rows + r0);
+                mbar_expect_tx(b_v + set, TILE_BYTES);
+                tma_load_2d(&maps.qkv_mn, b_v + set, sV, c0, 2 * p.rows + r0);
+                tma_load_2d(&maps.qkv_mn, b_v + set, sV + KB_BYTES, c0 + 32, 2 * p.rows + r0);
+            };
+            if ((int)blockIdx.x < tiles) load_tile(blockIdx.x, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const int set = it & 1;
+                const uint32_t ph = it & 1, ph_set = (it >> 1) & 1;
+                uint8_t* sQ = smem + set * 3 * TILE_BYTES;
+                mbar_wait(b_qk + set, ph_set);
                 tc_fence_after();
-                mma_kmajor<SEQ, 2>(tmem, smem_u32(sQ), smem_u32(sK));
+                mma_kmajor<SEQ, 2>(tmem, smem_u32(sQ), smem_u32(sQ + TILE_BYTES));
                 umma_commit(b_s);
+                // the other set was last read by the P V product of the previous tile
+                if (it > 0) mbar_wait(b_o, ph ^ 1);
+                if (tile + (int)gridDim.x < tiles) load_tile(tile + gridDim.x, set ^ 1);
                 mbar_wait(b_p, ph);
-                mbar_wait(b_v, ph);
+                mbar_wait(b_v + set, ph_set);
                 tc_fence_after();
-                mma_mn_b(tmem + 128, smem_u32(sQ), smem_u32(sV));
+                mma_mn_b(tmem + 128, smem_u32(sQ), smem_u32(sQ + 2 * TILE_BYTES));
                 umma_commit(b_o);
             }
         }
@@ -185,6 +195,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
             const int b = tile / p.heads, h = tile - b * p.heads;
+            uint8_t* sP = smem + (it & 1) * 3 * TILE_BYTES;
             mbar_wait(b_s, ph);
             tc_fence_after();
             // pass 1: row maximum
@@ -211,7 +222,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                     x[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2e, mneg));
                     sum += x[k];
                 }
-                store_row_chunk(sQ, c, row, x);      // Q and K tiles are dead: S is complete
+                store_row_chunk(sP, c, row, x);      // Q and K tiles of this set are dead: S is complete
             }
             fence_async_smem();
             tc_fence_before();
@@ -232,8 +243,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                         make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
                                     __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
             }
-            tc_fence_before();
-            mbar_arrive(b_done);
+            tc_fence_before();       // the next tile's P V product overwrites these columns only after this warp's next b_p
         }
     }
     tc_fence_before();
@@ -252,18 +262,17 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sX = smem;                        // 64 KB: Q_k | K_k, then P^T, then dS^T
     uint8_t* sY = smem + 2 * TILE_BYTES;       // 64 KB: dO_k | V_k, then dS
-    uint8_t* sZ1 = smem + 4 * TILE_BYTES;      // 32 KB: dO (MN-major), then Q (MN-major)
+    uint8_t* sZ1 = smem + 4 * TILE_BYTES;      // 32 KB: dO (MN-major)
     uint8_t* sZ2 = smem + 5 * TILE_BYTES;      // 32 KB: K (MN-major)
-    uint64_t* bars = (uint64_t*)(smem + 6 * TILE_BYTES);
+    uint8_t* sZ3 = smem + 6 * TILE_BYTES;      // 32 KB: Q (MN-major)
+    uint64_t* bars = (uint64_t*)(smem + 7 * TILE_BYTES);
     uint64_t* b_ld1 = bars;         // Q_k, K_k, dO_k, V_k landed
-    uint64_t* b_ld2 = bars + 1;     // dO_mn, K_mn landed
+    uint64_t* b_ld2 = bars + 1;     // dO_mn, K_mn, Q_mn landed
     uint64_t* b_sdp = bars + 2;     // S and dP complete
     uint64_t* b_op1 = bars + 3;     // P^T and dS staged (128 arrivals)
     uint64_t* b_dvdq = bars + 4;    // dV and dQ complete
-    uint64_t* b_ld3 = bars + 5;     // Q_mn landed
     uint64_t* b_op2 = bars + 6;     // dS^T staged (128 arrivals)
     uint64_t* b_dk = bars + 7;      // dK complete
-    uint64_t* b_done = bars + 8;    // rows stored (128 arrivals)
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.heads * HD;
@@ -271,7 +280,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
 
     if (warp == 0 && lane == 0) {
         mbar_init(b_ld1, 1); mbar_init(b_ld2, 1); mbar_init(b_sdp, 1); mbar_init(b_op1, 128); mbar_init(b_dvdq, 1);
-        mbar_init(b_ld3, 1); mbar_init(b_op2, 128); mbar_init(b_dk, 1); mbar_init(b_done, 128);
+        mbar_init(b_op2, 128); mbar_init(b_dk, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
@@ -291,12 +300,11 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
+            // all seven operand tiles of a (batch, head) tile in one go; the next tile's loads are issued as soon as
+            // this tile's last product has consumed the shared memory, i.e. while the row threads still store results
+            auto load_tile = [&](int tile) {
                 const int b = tile / p.heads, h = tile - b * p.heads;
                 const int r0 = b * SEQ, c0 = h * HD;
-                if (it > 0) mbar_wait(b_done, ph ^ 1);
                 mbar_expect_tx(b_ld1, 4 * TILE_BYTES);
                 tma_load_2d(&maps.qkv_k, b_ld1, sX, c0, r0);                                   // Q
                 tma_load_2d(&maps.qkv_k, b_ld1, sX + KB_BYTES, c0 + 32, r0);
@@ -306,11 +314,18 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 tma_load_2d(&maps.do_k, b_ld1, sY + KB_BYTES, c0 + 32, r0);
                 tma_load_2d(&maps.qkv_k, b_ld1, sY + TILE_BYTES, c0, 2 * p.rows + r0);         // V
                 tma_load_2d(&maps.qkv_k, b_ld1, sY + TILE_BYTES + KB_BYTES, c0 + 32, 2 * p.rows + r0);
-                mbar_expect_tx(b_ld2, 2 * TILE_BYTES);
-                tma_load_2d(&maps.do_mn, b_ld2, sZ1, c0, r0);
+                mbar_expect_tx(b_ld2, 3 * TILE_BYTES);
+                tma_load_2d(&maps.do_mn, b_ld2, sZ1, c0, r0);                                  // dO, MN-major
                 tma_load_2d(&maps.do_mn, b_ld2, sZ1 + KB_BYTES, c0 + 32, r0);
-                tma_load_2d(&maps.qkv_mn, b_ld2, sZ2, c0, p.rows + r0);
+                tma_load_2d(&maps.qkv_mn, b_ld2, sZ2, c0, p.rows + r0);                        // K, MN-major
                 tma_load_2d(&maps.qkv_mn, b_ld2, sZ2 + KB_BYTES, c0 + 32, p.rows + r0);
+                tma_load_2d(&maps.qkv_mn, b_ld2, sZ3, c0, r0);                                 // Q, MN-major
+                tma_load_2d(&maps.qkv_mn, b_ld2, sZ3 + KB_BYTES, c0 + 32, r0);
+            };
+            if ((int)blockIdx.x < tiles) load_tile(blockIdx.x);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                const uint32_t ph = it & 1;
                 mbar_wait(b_ld1, ph);
                 tc_fence_after();
                 mma_kmajor<SEQ, 2>(tmem, smem_u32(sX), smem_u32(sX + TILE_BYTES));             // S  = Q K^T
@@ -322,15 +337,14 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 mma_mn_b(tmem + 256, smem_u32(sX), smem_u32(sZ1));                             // dV = P^T dO
                 mma_mn_b(tmem + 320, smem_u32(sY), smem_u32(sZ2));                             // dQ = dS K
                 umma_commit(b_dvdq);
-                mbar_wait(b_dvdq, ph);                                                         // Z1 (and X) are free
-                mbar_expect_tx(b_ld3, TILE_BYTES);
-                tma_load_2d(&maps.qkv_mn, b_ld3, sZ1, c0, r0);                                 // Q, MN-major
-                tma_load_2d(&maps.qkv_mn, b_ld3, sZ1 + KB_BYTES, c0 + 32, r0);
                 mbar_wait(b_op2, ph);
-                mbar_wait(b_ld3, ph);
                 tc_fence_after();
-                mma_mn_b(tmem + 384, smem_u32(sX), smem_u32(sZ1));                             // dK = dS^T Q
+                mma_mn_b(tmem + 384, smem_u32(sX), smem_u32(sZ3));                             // dK = dS^T Q
                 umma_commit(b_dk);
+                if (tile + (int)gridDim.x < tiles) {
+                    mbar_wait(b_dk, ph);             // every operand of this tile has been consumed
+                    load_tile(tile + gridDim.x);
+                }
             }
         }
     } else if (warp >= 2) {
@@ -422,8 +436,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 for (int j = 0; j < 8; ++j)
                     reinterpret_cast<uint4*>(dk + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            tc_fence_before();
-            mbar_arrive(b_done);
+            tc_fence_before();       // (the next tile's dV / dQ / dK products need this warp's next arrivals first)
         }
     }
     tc_fence_before();
@@ -447,8 +460,8 @@ int make_map_2d(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, 
     return 0;
 }
 
-constexpr size_t FWD_SMEM = 3 * TILE_BYTES + 128 + 1024;
-constexpr size_t BWD_SMEM = 6 * TILE_BYTES + 128 + 1024;
+constexpr size_t FWD_SMEM = 6 * TILE_BYTES + 128 + 1024;
+constexpr size_t BWD_SMEM = 7 * TILE_BYTES + 128 + 1024;
 
 int check_shape(const char* who, int dtype, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
     LG_REQUIRE(dtype == LG_F32 && seq == SEQ && head_dim == HD && batch >= 1 && heads >= 1 &&
@@ -492,7 +505,7 @@ int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int
         attr_done = true;
     }
     const int tiles = (int)(batch * heads);
-    const int grid = tiles < 2 * sm_count() ? tiles : 2 * sm_count();
+    const int grid = tiles < sm_count() ? tiles : sm_count();
     attention_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, stream()>>>(maps, p);
     LG_CHECK_LAUNCH();
     return 0;

@@ -79,6 +79,49 @@ __global__ void __launch_bounds__(256) ew_flat_kernel(const T* __restrict__ a, c
         out[j] = Op::apply(a[j], NIN > 1 ? b[j] : T(0), NIN > 2 ? c[j] : T(0), alpha);
 }
 
+// flat, chunked: a CTA walks contiguous chunks of 256 x U vectors (U x 4 KB of every operand) instead of U
+// grid-strided vectors per thread -- the 1-read / 1-write streams of the unary operators (relu, exp, gelu) then touch
+// one contiguous read region and one contiguous write region per CTA at a time
+template <class Op, typename T, int NIN, int V, int U>
+__global__ void __launch_bounds__(256) ew_flat_chunk_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                            const T* __restrict__ c, T* __restrict__ out, int64_t n,
+                                                            T alpha) {
+    LG_PDL_TRIGGER();
+    using VT = Vec<T, V>;
+    const int64_t nv = n / V;
+    const VT* av = reinterpret_cast<const VT*>(a);
+    const VT* bv = reinterpret_cast<const VT*>(b);
+    const VT* cv = reinterpret_cast<const VT*>(c);
+    VT* ov = reinterpret_cast<VT*>(out);
+    constexpr int64_t CH = 256 * U;
+    for (int64_t base = (int64_t)blockIdx.x * CH; base < nv; base += (int64_t)gridDim.x * CH) {
+        VT ra[U], rb[U], rc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * 256 + threadIdx.x;
+            if (i < nv) {
+                ra[u] = LG_EW_LD(av + i);
+                if (NIN > 1) rb[u] = LG_EW_LD(bv + i);
+                if (NIN > 2) rc[u] = LG_EW_LD(cv + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * 256 + threadIdx.x;
+            if (i < nv) {
+                VT r;
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    r.v[k] = Op::apply(ra[u].v[k], NIN > 1 ? rb[u].v[k] : T(0), NIN > 2 ? rc[u].v[k] : T(0), alpha);
+                LG_EW_ST(ov + i, r);
+            }
+        }
+    }
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t j = nv * V + tid; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        out[j] = Op::apply(a[j], NIN > 1 ? b[j] : T(0), NIN > 2 ? c[j] : T(0), alpha);
+}
+
 // ---- nd_vec -------------------------------------------------------------------------------------
 // inner (last) dim: every operand has stride 1 or 0 there, out has stride 1, inner % V == 0.
 template <class Op, typename T, int NIN, int V, typename I>
@@ -250,8 +293,18 @@ int ew_launch(const void* a_, const void* b_, const void* c_, void* out_, const 
         bool al = true;
         for (int k = 0; k < 4; ++k)
             if (ptrs[k] && !aligned16(ptrs[k])) al = false;
-        if (al) {
-            int grid = grid_for((total / V + 3) / 4 + 1, 256, 8);
+        // LG_EW_FLAT_MODE (tuning knob): 0 grid-strided vectors (default), 1 / 2 contiguous chunks of 4 / 8 vectors per
+        // thread; LG_EW_BPS: CTAs per SM of the grid
+        static const int flat_mode = getenv("LG_EW_FLAT_MODE") ? atoi(getenv("LG_EW_FLAT_MODE")) : 0;
+        static const int bps = getenv("LG_EW_BPS") ? atoi(getenv("LG_EW_BPS")) : 8;
+        if (al && flat_mode == 1) {
+            int grid = grid_for((total / V + 3) / 4 + 1, 256, bps);
+            ew_flat_chunk_kernel<Op, T, NIN, V, 4><<<grid, 256, 0, stream()>>>(a, b, c, out, total, alpha);
+        } else if (al && flat_mode == 2) {
+            int grid = grid_for((total / V + 7) / 8 + 1, 256, bps);
+            ew_flat_chunk_kernel<Op, T, NIN, V, 8><<<grid, 256, 0, stream()>>>(a, b, c, out, total, alpha);
+        } else if (al) {
+            int grid = grid_for((total / V + 3) / 4 + 1, 256, bps);
             ew_flat_kernel<Op, T, NIN, V><<<grid, 256, 0, stream()>>>(a, b, c, out, total, alpha);
         } else {
             int grid = grid_for((total + 3) / 4 + 1, 256, 8);
