@@ -2,8 +2,8 @@
 //
 // Replaces the reference's `atom` JIT generator (opencl/kernels.py:24-195), which emits one
 // element per work-item and recomputes ndim div/mod chains for every operand.  Here:
-//   * flat   -- all operands contiguous: 128-bit vector accesses, 4 independent vectors in flight
-//               per thread, grid sized from the SM count (HBM-streaming path, the roofline case);
+//   * flat   -- all operands contiguous: 128-bit vector accesses, 8 independent vectors in flight per thread over
+//               contiguous 32 KB chunks per CTA, grid sized from the SM count (HBM-streaming path, the roofline case);
 //   * nd_vec -- broadcast / strided outer dims with a unit-or-zero inner stride: one 128-bit vector
 //               per thread along the inner dim (bias adds, (R,1) statistics, head split/merge copies);
 //   * nd_any -- arbitrary strides, one element per thread (transposed views, slices with steps).
@@ -293,10 +293,12 @@ int ew_launch(const void* a_, const void* b_, const void* c_, void* out_, const 
         bool al = true;
         for (int k = 0; k < 4; ++k)
             if (ptrs[k] && !aligned16(ptrs[k])) al = false;
-        // LG_EW_FLAT_MODE (tuning knob): 0 grid-strided vectors (default), 1 / 2 contiguous chunks of 4 / 8 vectors per
-        // thread; LG_EW_BPS: CTAs per SM of the grid
-        static const int flat_mode = getenv("LG_EW_FLAT_MODE") ? atoi(getenv("LG_EW_FLAT_MODE")) : 0;
-        static const int bps = getenv("LG_EW_BPS") ? atoi(getenv("LG_EW_BPS")) : 8;
+        // LG_EW_FLAT_MODE: 2 (default) contiguous chunks of 8 vectors per thread, 1 chunks of 4, 0 grid-strided vectors;
+        // LG_EW_BPS: CTAs per SM the grid is sized for.  Measured at 2^26-2^28 fp32 (profiles/r2_ew_flat_variants.txt):
+        // grid-strided x4 at 8 CTAs/SM (round 1): relu 5.8-6.0, exp 5.7, gelu 5.6-5.7, add 6.3-6.45 TB/s;
+        // chunks of 8 at 16 CTAs/SM: relu 6.3-6.4, exp 6.3-6.4, gelu 6.2-6.3, add 6.63 TB/s.
+        static const int flat_mode = getenv("LG_EW_FLAT_MODE") ? atoi(getenv("LG_EW_FLAT_MODE")) : 2;
+        static const int bps = getenv("LG_EW_BPS") ? atoi(getenv("LG_EW_BPS")) : 16;
         if (al && flat_mode == 1) {
             int grid = grid_for((total / V + 3) / 4 + 1, 256, bps);
             ew_flat_chunk_kernel<Op, T, NIN, V, 4><<<grid, 256, 0, stream()>>>(a, b, c, out, total, alpha);
