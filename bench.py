@@ -136,8 +136,8 @@ def make_step(model, opt, dp, light):
         loss = light.loss.cross_entropy(logits.reshape(-1, model.vocab_size), labels)
         opt.zero_grad()
         if dp is not None:
-            # backward with the bucketed gradient all-reduce overlapped (+ LG_DP_PIPELINED_STEP=1: the optimizer
-            # pipelined behind each bucket's exchange), then the optimizer step
+            # backward with, per bucket of parameters whose gradients are final, the gradient exchange fused with the
+            # optimizer update (N > 1) or the optimizer update alone (N = 1) on the collective stream, beside backward
             dp.backward_and_step(loss)
         else:
             loss.backward()
@@ -275,7 +275,10 @@ def main():
     model = build_bert(CudaTensor, cfg)
     opt = light.optim.Adam(model.parameters(), lr=1e-4)
     comm = parallel.default_comm() if world > 1 else parallel.LocalComm()
-    dp = parallel.DataParallel(model, opt, comm=comm) if world > 1 else None
+    # one GPU: the wrapper has nothing to exchange, but it takes the optimizer off the critical path (per-bucket updates
+    # on the collective stream beside backward); LG_BENCH_PLAIN_STEP=1 keeps loss.backward(); optimizer.step()
+    plain = world == 1 and os.environ.get('LG_BENCH_PLAIN_STEP')
+    dp = None if plain else parallel.DataParallel(model, opt, comm=comm)
     step = make_step(model, opt, dp, light)
     light.Gradients.retain_intermediate = False
     graphs = []                                  # every captured step, destroyed in order at teardown
@@ -492,6 +495,8 @@ def main():
             'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'bf16': 'bf16'}[mode], 'data': 'synthetic', 'config': config,
             'loss': round(final_loss, 5),
             'execution': 'eager python dispatch' if args.eager else 'whole step captured once into a CUDA graph, replayed per step',
+            'optimizer_step': ('per-bucket updates on the collective stream, overlapped with backward (exchange %r)' % dp.exchange)
+            if dp is not None else 'optimizer.step() after backward',
             'eager_ms_per_step': round(eager_ms, 3),
             'e2e': {'value': round(e2e, 2), 'unit': 'samples/s', 'h2d_bytes_per_step': int(ids_np.nbytes + labels_np.nbytes),
                     'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_b, 3), 'steps': k_b, 'last_loss': round(float(loss_host), 5)},

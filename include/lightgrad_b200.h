@@ -343,6 +343,14 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
                         double lr, double beta1, double beta2, double eps, double momentum, int seg_offset,
                         int t_advance);
 int lg_mc_release(void);
+/* One GPU: the optimizer update (lg_adam_step / lg_sgd_step arithmetic; kind 0 Adam, 1 AdaBelief, 2 SGD) of arena
+ * elements [lo, hi) by the exchange kernel's single-GPU variant -- 128 threads, no shared memory, <= 88 registers per CTA --
+ * on the collective stream (order it with lg_nccl_fork / lg_nccl_wait): it runs beside the GEMMs of the rest of backward
+ * as soon as a bucket's gradients are final, so the optimizer leaves the critical path.  param / grad / m / v address the
+ * start of the arenas. */
+int lg_bucket_step(int kind, void* param, const void* grad, void* m, void* v, int64_t lo, int64_t hi, int n_seg,
+                   const int64_t* seg_end_dev, int64_t* t_dev, double lr, double beta1, double beta2, double eps,
+                   double momentum, int seg_offset, int t_advance);
 /* measurement aid (LG_MC_TRACE=1 in the environment): lg_mc_trace_mark stamps the position of the current stream;
  * lg_mc_trace_read drains the device and returns, in launch order, records of 4 x uint64 {entered, all ranks met,
  * finished, bucket bytes} per exchange launch (GPU global timer, ns) and {t, 0, 0, 0} per mark.  Captured launches keep

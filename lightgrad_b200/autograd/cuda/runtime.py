@@ -122,6 +122,8 @@ _SIGNATURES = {
                             C.c_int, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                             C.c_int],
     'lg_mc_release': [],
+    'lg_bucket_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp, _vp, C.c_double, C.c_double,
+                       C.c_double, C.c_double, C.c_double, C.c_int, C.c_int],
     'lg_mc_trace_mark': [],
     'lg_mc_trace_read': [_vp, C.c_int, C.POINTER(C.c_int), C.c_int],
 }

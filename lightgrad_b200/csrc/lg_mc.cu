@@ -153,6 +153,7 @@ __device__ __forceinline__ void mc_wait(const unsigned int* local_flag, unsigned
 }
 
 struct McArgs {
+    const float* grad;         // LOCAL variant: this GPU's gradient arena (plain mapping)
     float* mc_grad;            // multicast mapping of the gradient arena
     float* mc_param;           // multicast mapping of the parameter arena
     float* param;              // local mapping of the parameter arena
@@ -178,14 +179,17 @@ __global__ void mc_mark_kernel(unsigned long long* slot) {
     *slot = globaltimer_ns();
 }
 
-template <int KIND>
+// LOCAL = true: the same small-footprint kernel for ONE GPU -- no switch, no flags: the gradients are read from the
+// local arena and the parameters written back to it.  What it keeps is the reason to exist: 128 threads, no shared
+// memory, <= 88 registers, so it runs beside the GEMMs of backward and the optimizer leaves the critical path.
+template <int KIND, bool LOCAL>
 __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a) {
     LG_PDL_TRIGGER();
     // ---- every rank's gradients of this bucket are final once its kernel runs (stream order on that rank):
     //      meet the CTAs of this index on all ranks
     // (no shared memory at all: next to a tensor-core GEMM CTA an SM has room for the 1 KB every CTA reserves, not more)
     unsigned int epoch = 0;                                  // thread 0 only
-    if (threadIdx.x == 0) {
+    if (!LOCAL && threadIdx.x == 0) {
         epoch = a.epochs[blockIdx.x] + 1;
         a.epochs[blockIdx.x] = epoch;
         if (a.trace && blockIdx.x == 0) {
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
     const int64_t stride = (int64_t)gridDim.x * MC_THREADS;
     // independent 16-byte switch reductions in flight per thread; chosen so that the kernel stays under the ~88
     // registers per thread that are free on an SM beside a tensor-core GEMM CTA (128 threads x 88 = 11.3 K of 11.7 K)
-    constexpr int U = KIND == 2 ? 4 : 8;
+    constexpr int U = KIND == 2 ? 4 : (LOCAL ? 6 : 8);
     int seg = 0;
     for (int64_t i0 = v0 + (int64_t)blockIdx.x * MC_THREADS + threadIdx.x; i0 < v1; i0 += stride * U) {
         // the switch reductions have the long latency (NVLink round trip): all U are issued first; the local
@@ -217,7 +221,10 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * stride;
-            if (i < v1) g[u] = mc_ld_reduce(a.mc_grad + ((base + i) << 2));
+            if (i < v1) {
+                if (LOCAL) g[u] = __ldg(reinterpret_cast<const float4*>(a.grad) + base + i);
+                else g[u] = mc_ld_reduce(a.mc_grad + ((base + i) << 2));
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -246,13 +253,14 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
                 }
                 p.x += d.x; p.y += d.y; p.z += d.z; p.w += d.w;
             }
-            mc_st(a.mc_param + ((base + i) << 2), p);     // every GPU's copy of the parameters, this one included
+            if (LOCAL) reinterpret_cast<float4*>(a.param)[base + i] = p;
+            else mc_st(a.mc_param + ((base + i) << 2), p);   // every GPU's copy of the parameters, this one included
         }
     }
     // ---- done: nobody may reuse the gradients (next step's zero fill) or read the parameters (next forward) of
     //      this bucket before all ranks have finished reading / writing them
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (!LOCAL && threadIdx.x == 0) {
         __threadfence_system();
         mc_arrive(a.mc_flags + MC_MAX_CTAS + blockIdx.x);
         mc_wait(a.flags + MC_MAX_CTAS + blockIdx.x, epoch * (unsigned)a.world);
@@ -485,15 +493,72 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
         count_launch();
     }
     switch (kind) {
-        case 0: mc_exchange_kernel<0><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
-        case 1: mc_exchange_kernel<1><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
-        case 2: mc_exchange_kernel<2><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
-        default: mc_exchange_kernel<3><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
+        case 0: mc_exchange_kernel<0, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
+        case 1: mc_exchange_kernel<1, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
+        case 2: mc_exchange_kernel<2, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
+        default: mc_exchange_kernel<3, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
     }
     if (corr) {
         // the collective stream still reads it: hand it back once the compute stream has joined (lg_nccl_wait)
         comm_defer_free(corr);
     }
+    LG_CHECK_LAUNCH();
+    return 0;
+}
+
+// One GPU: the optimizer update of arena elements [lo, hi) by the same small-footprint kernel, on the collective
+// stream (ordered by lg_nccl_fork / lg_nccl_wait), so that it runs beside the rest of backward instead of after it.
+// param / grad / m / v address the START of the arenas; kind 0 Adam, 1 AdaBelief, 2 SGD (m = previous deltas when
+// momentum != 0).  Arithmetic, segments and step counter as lg_adam_step / lg_sgd_step.
+int lg_bucket_step(int kind, void* param, const void* grad, void* m, void* v, int64_t lo, int64_t hi, int n_seg,
+                   const int64_t* seg_end_dev, int64_t* t_dev, double lr, double beta1, double beta2, double eps,
+                   double momentum, int seg_offset, int t_advance) {
+    LG_INIT();
+    LG_REQUIRE(kind >= 0 && kind <= 2, "lg_bucket_step: unknown kind %d", kind);
+    LG_REQUIRE(lo % 4 == 0 && hi % 4 == 0 && lo <= hi, "lg_bucket_step: range must be a multiple of 4 elements");
+    LG_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
+               "lg_bucket_step: arenas must be 16-byte aligned");
+    if (hi == lo) return 0;
+    cudaStream_t st = comm_stream();
+    McArgs a = {};
+    a.grad = (const float*)grad;
+    a.param = (float*)param;
+    a.m = (float*)m;
+    a.v = (float*)v;
+    a.lo = lo;
+    a.hi = hi;
+    a.rank = 0;
+    a.world = 1;
+    a.kind = kind;
+    a.n_seg = n_seg;
+    a.seg_end = seg_end_dev;
+    a.neg_lr = (float)(-lr);
+    a.b1 = (float)beta1;
+    a.b2 = (float)beta2;
+    a.omb1 = (float)(1.0 - beta1);
+    a.omb2 = (float)(1.0 - beta2);
+    a.eps = (float)eps;
+    a.inv_world = 1.0f;
+    a.momentum = (float)momentum;
+    a.trace = nullptr;
+    float* corr = nullptr;
+    if (kind <= 1) {
+        LG_REQUIRE(n_seg >= 1 && seg_end_dev && t_dev && m && v, "lg_bucket_step: Adam needs its state and segments");
+        corr = (float*)tmp_alloc(4 * (size_t)n_seg * sizeof(float));
+        if (!corr) return 1;
+        a.c1 = corr;
+        a.c2 = corr + n_seg;
+        adam_prep_kernel<<<1, 256, 0, st>>>(n_seg, t_dev, beta1, beta2, corr, corr + n_seg, seg_offset, t_advance);
+        count_launch();
+    }
+    static const int grid_env = getenv("LG_MC_CTAS") ? atoi(getenv("LG_MC_CTAS")) : 0;
+    const int grid = grid_env > 0 ? (grid_env < MC_MAX_CTAS ? grid_env : MC_MAX_CTAS) : sm_count();
+    switch (kind) {
+        case 0: mc_exchange_kernel<0, true><<<grid, MC_THREADS, 0, st>>>(a); break;
+        case 1: mc_exchange_kernel<1, true><<<grid, MC_THREADS, 0, st>>>(a); break;
+        default: mc_exchange_kernel<2, true><<<grid, MC_THREADS, 0, st>>>(a); break;
+    }
+    if (corr) comm_defer_free(corr);
     LG_CHECK_LAUNCH();
     return 0;
 }

@@ -174,6 +174,14 @@ class SGD(Optimizer):
         a.rt.api.sgd_step(a.param_buf.ptr, a.grad_buf.ptr, self._delta.ptr if self._delta is not None else None,
                           a.total, float(self.lr), float(self.momentum))
 
+    def _bucket_step_range(self, a, i0, i1, lo, hi, last):
+        """Single GPU: SGD update of arena elements [lo, hi) by the small-footprint kernel on the collective stream, so
+        that it runs beside the rest of backward (lg_bucket_step)."""
+        if self.momentum != 0.0 and self._delta is None:
+            self._delta = a.state()
+        a.rt.api.bucket_step(2, a.param_buf.ptr, a.grad_buf.ptr, self._delta.ptr if self._delta is not None else None,
+                             None, lo, hi, 0, None, None, float(self.lr), 0.0, 0.0, 0.0, float(self.momentum), i0, 0)
+
     def _mc_exchange_range(self, a, region, i0, i1, lo, hi, rank, world, last):
         """Parameters i0 .. i1-1 = arena elements [lo, hi): gradient reduce-scatter, SGD update of this rank's share
         and parameter all-gather in one kernel over the NVLink multicast region (lg_mc_exchange_step)."""
@@ -241,6 +249,20 @@ class Adam(Optimizer):
         a.rt.api.adam_step(self._belief, a.param_buf.ptr + lo * 4, a.grad_buf.ptr + lo * 4, self._m.ptr + lo * 4,
                            self._v.ptr + lo * 4, hi - lo, i1 - i0, seg.ptr + i0 * 8, self._t_dev.ptr, float(self.lr),
                            float(self.b1), float(self.b2), float(self.eps), lo, i0, P if last else 0)
+        if last:
+            self.t += P
+
+    def _bucket_step_range(self, a, i0, i1, lo, hi, last):
+        """Single GPU: Adam / AdaBelief on arena elements [lo, hi) (parameters i0 .. i1-1) by the small-footprint kernel
+        on the collective stream -- beside the rest of backward instead of after it (lg_bucket_step).  Step counter
+        and bias corrections as in ``_fused_step_range``."""
+        P = len(self.parameters)
+        if self._m is None:
+            self._init_state(a)
+        seg = a.segments(self.parameters)
+        a.rt.api.bucket_step(self._belief, a.param_buf.ptr, a.grad_buf.ptr, self._m.ptr, self._v.ptr, lo, hi, i1 - i0,
+                             seg.ptr + i0 * 8, self._t_dev.ptr, float(self.lr), float(self.b1), float(self.b2),
+                             float(self.eps), 0.0, i0, P if last else 0)
         if last:
             self.t += P
 

@@ -169,6 +169,11 @@ class DataParallel(object):
             rt.api.nccl_init(idbuf.ctypes.data, self.world, self.rank)
             self._nccl = True
         want = (exchange or os.environ.get('LG_DP_EXCHANGE', 'auto')).lower()
+        if self.world == 1 and want in ('auto', 'local') and self.arena is not None \
+                and hasattr(optimizer, '_bucket_step_range'):
+            # one GPU: nothing to exchange, but the optimizer still leaves the critical path -- every bucket of parameters
+            # is updated by a small-footprint kernel on the collective stream as soon as its gradients are final
+            self.exchange = 'local'
         single = self.world == 1 and want == 'nvls'          # a team of one: exercises the whole path on one GPU
         if self.arena is not None and want in ('auto', 'nvls') and (self._nccl or single) \
                 and hasattr(optimizer, '_mc_exchange_range'):
@@ -268,8 +273,9 @@ class DataParallel(object):
         # Measured (2 GPUs, local batch 128): 30.56 ms pipelined vs 30.44 ms plain -- whatever runs on the
         # communication stream competes with the persistent one-CTA-per-SM GEMMs of backward for the same SMs, so
         # moving the optimizer there buys nothing today.  Off unless LG_DP_PIPELINED_STEP=1.
-        if self.exchange == 'nvls':
-            # gradient reduce-scatter + optimizer + parameter all-gather, one kernel per bucket, overlapped with backward
+        if self.exchange in ('nvls', 'local'):
+            # nvls: gradient reduce-scatter + optimizer + parameter all-gather, one kernel per bucket, overlapped with
+            # backward; local (one GPU): the optimizer alone, same kernel shape, same overlap
             self.backward(loss, bucket_bytes, _step_buckets=True)
             return
         fused = getattr(self.optimizer, '_fused_step_range', None)
@@ -290,9 +296,10 @@ class DataParallel(object):
         if bucket_bytes is None:
             # the multicast exchange pays ~20 us per bucket but leaves only the LAST bucket (the first layer's parameters
             # and the word embeddings, whose gradients are final when backward ends) exposed: small buckets
-            bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '24' if self.exchange == 'nvls' else '64')) << 20
+            bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '24' if self.exchange in ('nvls', 'local') else '64')) << 20
         nvls_step = _step_buckets and self.exchange == 'nvls'
-        if not nvls_step and (self.world == 1 or not self._nccl or os.environ.get('LG_DP_NO_OVERLAP')):
+        local_step = _step_buckets and self.exchange == 'local'
+        if not (nvls_step or local_step) and (self.world == 1 or not self._nccl or os.environ.get('LG_DP_NO_OVERLAP')):
             loss.backward()
             self.sync_gradients()
             return
@@ -331,6 +338,10 @@ class DataParallel(object):
             if nvls_step:
                 self.optimizer._mc_exchange_range(a, self._mc, first_param[b], first_param[b] + count, lo, hi,
                                                   self.rank, self.world, last=n_launched[0] == n_buckets)
+                return
+            if local_step:
+                self.optimizer._bucket_step_range(a, first_param[b], first_param[b] + count, lo, hi,
+                                                  last=n_launched[0] == n_buckets)
                 return
             api.nccl_allreduce_f32(a.grad_buf.ptr + lo * 4, hi - lo, 1, 1)
             if _step_buckets:

@@ -522,6 +522,19 @@ class FakeDevice(object):
     def mc_release(self):
         self._mc_block = None
 
+    def bucket_step(self, kind, p, g, m, v, lo, hi, n_seg, seg_end, t_dev, lr, b1, b2, eps, momentum, seg_offset,
+                    t_advance):
+        assert lo % 4 == 0 and hi % 4 == 0
+        n = hi - lo
+        if n == 0:
+            return
+        if kind <= 1:
+            self.adam_step(kind, int(p) + lo * 4, int(g) + lo * 4, int(m) + lo * 4, int(v) + lo * 4, n, n_seg, seg_end,
+                           t_dev, lr, b1, b2, eps, lo, seg_offset, t_advance)
+        else:
+            self.sgd_step(int(p) + lo * 4, int(g) + lo * 4, (int(m) + lo * 4) if (m and momentum != 0.0) else None, n, lr,
+                          momentum)
+
     def mc_trace_mark(self): pass
 
     def mc_trace_read(self, out, max_records, n, reset):

@@ -23,13 +23,13 @@ def _build(make_opt):
     return model, make_opt(model.parameters())
 
 
-def _run(make_opt, bucket_bytes, steps=3):
+def _run(make_opt, bucket_bytes, steps=3, exchange='nvls'):
     ids, labels = bert.synthetic_batch(2, 8, CFG['vocab_size'])
     model, opt = _build(make_opt)
     dp = None
     if bucket_bytes is not None:
-        dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm(), exchange='nvls')
-        if dp.exchange != 'nvls':
+        dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm(), exchange=exchange)
+        if dp.exchange != exchange:
             pytest.skip("NVLink multicast objects are not available on this device: " + dp.exchange_note)
     x = CudaTensor.from_numpy(ids, requires_grad=False)
     y = CudaTensor.from_numpy(labels, requires_grad=False)
@@ -55,10 +55,10 @@ OPTIMIZERS = {
 }
 
 
-def _check(name):
+def _check(name, exchange='nvls'):
     want, t_want, loss_want = _run(OPTIMIZERS[name], None)
     for bucket_bytes in (1, 4096, 1 << 30):
-        got, t_got, loss_got = _run(OPTIMIZERS[name], bucket_bytes)
+        got, t_got, loss_got = _run(OPTIMIZERS[name], bucket_bytes, exchange=exchange)
         assert t_got == t_want
         assert loss_got == loss_want
         for a, b in zip(got, want):
@@ -74,6 +74,48 @@ def test_team_of_one_exchange_equals_plain_step_host_logic(fake_device, name):
 @pytest.mark.parametrize('name', sorted(OPTIMIZERS))
 def test_team_of_one_exchange_equals_plain_step_on_device(cuda, name):
     _check(name)
+
+
+# one GPU: the optimizer as per-bucket small-footprint kernels on the collective stream, beside backward (exchange 'local')
+@pytest.mark.parametrize('name', sorted(OPTIMIZERS))
+def test_overlapped_optimizer_equals_plain_step_host_logic(fake_device, name):
+    _check(name, exchange='local')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(OPTIMIZERS))
+def test_overlapped_optimizer_equals_plain_step_on_device(cuda, name):
+    _check(name, exchange='local')
+
+
+@pytest.mark.gpu
+def test_overlapped_optimizer_inside_a_captured_graph(cuda):
+    from lightgrad_b200.autograd.cuda.graph import StepGraph
+    ids, labels = bert.synthetic_batch(2, 8, CFG['vocab_size'])
+    x = CudaTensor.from_numpy(ids, requires_grad=False)
+    y = CudaTensor.from_numpy(labels, requires_grad=False)
+
+    def run(graph):
+        model, opt = _build(OPTIMIZERS['adam'])
+        dp = parallel.DataParallel(model, opt, comm=parallel.LocalComm(), exchange='local')
+        assert dp.exchange == 'local'
+
+        def step():
+            loss = light.loss.cross_entropy(model(x).reshape(-1, CFG['vocab_size']), y)
+            opt.zero_grad()
+            dp.backward_and_step(loss, bucket_bytes=4096)
+            return loss
+        if graph:
+            sg = StepGraph(step, warmup=0)
+            for _ in range(3):
+                sg.replay()
+            sg.destroy()
+        else:
+            for _ in range(4):
+                step()
+        return [p.numpy() for p in model.parameters()]
+    for a, b in zip(run(True), run(False)):
+        np.testing.assert_array_equal(a, b)
 
 
 @pytest.mark.gpu
