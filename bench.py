@@ -275,10 +275,14 @@ def main():
     model = build_bert(CudaTensor, cfg)
     opt = light.optim.Adam(model.parameters(), lr=1e-4)
     comm = parallel.default_comm() if world > 1 else parallel.LocalComm()
-    # one GPU: the wrapper has nothing to exchange, but it takes the optimizer off the critical path (per-bucket updates
-    # on the collective stream beside backward); LG_BENCH_PLAIN_STEP=1 keeps loss.backward(); optimizer.step()
-    plain = world == 1 and os.environ.get('LG_BENCH_PLAIN_STEP')
-    dp = None if plain else parallel.DataParallel(model, opt, comm=comm)
+    # one GPU: loss.backward(); optimizer.step().  (LG_BENCH_OVERLAP_STEP=1 runs the optimizer per bucket beside backward
+    # instead, DataParallel exchange='local': measured slower, 8.97 vs 8.53 ms, see parallel.py)
+    if world > 1:
+        dp = parallel.DataParallel(model, opt, comm=comm)
+    elif os.environ.get('LG_BENCH_OVERLAP_STEP'):
+        dp = parallel.DataParallel(model, opt, comm=comm, exchange='local')
+    else:
+        dp = None
     step = make_step(model, opt, dp, light)
     light.Gradients.retain_intermediate = False
     graphs = []                                  # every captured step, destroyed in order at teardown

@@ -978,8 +978,7 @@ class linear(Function):
             with rt.side_stream(g2, x2, writes=(wg,) if bg is None else (wg, bg)):
                 _gemm(_swap_last(g2), x2, out=wg, accumulate=True, cls='W')
                 if bg is not None:
-                    rt.api.reduce_pitched(RED['SUM'], g2._code, g2.ptr, bg.ptr, 1, g2._shape[0], g2._shape[1],
-                                          g2._strides[0], 1.0, 1)
+                    _bias_grad(g2._code, g2.ptr, bg.ptr, g2._shape[0], g2._shape[1], g2._strides[0])
             return (dx, Function.ACCUMULATED, Function.ACCUMULATED) if has_bias else (dx, Function.ACCUMULATED)
         if wg is not None:
             rt.side_join_if_written(wg)       # a weight shared with another layer may have side-stream writes pending
@@ -1142,14 +1141,20 @@ class mlp_gelu(Function):
             w1g, b1g, w2g, b2g = grads
             with rt.side_stream(g2, dh, act, x2, writes=tuple(grads)):
                 _gemm(_swap_last(g2), act, out=w2g, accumulate=True, cls='W')
-                rt.api.reduce_pitched(RED['SUM'], code, g2.ptr, b2g.ptr, 1, g2._shape[0], g2._shape[1],
-                                      g2._strides[0], 1.0, 1)
+                _bias_grad(code, g2.ptr, b2g.ptr, g2._shape[0], g2._shape[1], g2._strides[0])
                 _gemm(_swap_last(dh), x2, out=w1g, accumulate=True, cls='W')
-                rt.api.reduce_pitched(RED['SUM'], code, dh.ptr, b1g.ptr, 1, dh._shape[0], dh._shape[1],
-                                      dh._strides[0], 1.0, 1)
+                _bias_grad(code, dh.ptr, b1g.ptr, dh._shape[0], dh._shape[1], dh._strides[0])
             return (dx,) + (Function.ACCUMULATED,) * 4
         return (dx, _gemm(_swap_last(dh), x2, cls='W'), _reduce(RED['SUM'], dh, (0,), False),
                 _gemm(_swap_last(g2), act, cls='W'), _reduce(RED['SUM'], g2, (0,), False))
+
+
+def _bias_grad(code, g_ptr, out_ptr, rows, cols, ld):
+    """out[cols] += column sums of the (rows, cols) gradient at g_ptr (row pitch ld): a bias gradient added straight
+    into its slot of the gradient arena.  (LG_DISABLE=bias_grad skips it: a timing experiment, the result is wrong.)"""
+    if 'bias_grad' in _DISABLED:
+        return
+    rt.api.reduce_pitched(RED['SUM'], code, g_ptr, out_ptr, 1, rows, cols, ld, 1.0, 1)
 
 
 def _fused_attention_ok(code, s, dh):
@@ -1268,7 +1273,7 @@ class self_attention(Function):
             with rt.side_stream(dqkv, x2, writes=tuple(wgs) + tuple(bgs)):
                 _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True, cls='W')
                 for part, bg in zip(parts, bgs):
-                    rt.api.reduce_pitched(RED['SUM'], part._code, part.ptr, bg.ptr, 1, rows, H, H, 1.0, 1)
+                    _bias_grad(part._code, part.ptr, bg.ptr, rows, H, H)
             return (dx,) + (Function.ACCUMULATED,) * 6
         if all(w is not None for w in wgs):
             _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True, cls='W')
@@ -1279,7 +1284,7 @@ class self_attention(Function):
         dbs = []
         for part, bg in zip(parts, bgs):
             if bg is not None and H > 1:
-                rt.api.reduce_pitched(RED['SUM'], part._code, part.ptr, bg.ptr, 1, rows, H, H, 1.0, 1)
+                _bias_grad(part._code, part.ptr, bg.ptr, rows, H, H)
                 dbs.append(Function.ACCUMULATED)
             else:
                 dbs.append(_reduce(RED['SUM'], part, (0,), False))

@@ -350,6 +350,62 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
     return 0;
 }
 
+// out[c] += scale * sum_r x[r, c] for a float32 (rows, cols) matrix with row pitch ld, SMALL FOOTPRINT: 128 threads, no
+// shared memory, ~40 registers.  This is the bias-gradient column sum of the backward pass (added straight into the
+// gradient arena), issued on the side stream while the compute stream runs one-CTA-per-SM tensor-core GEMMs: the general
+// column reducer above needs 5 KB of shared memory per CTA and therefore waits for a free SM, this one fits into the
+// ~1.9 KB / 11.7 K registers an SM has left beside a GEMM CTA and runs next to it.
+// Every thread owns one 16-byte column group over a slice of the rows (a warp reads 512 contiguous bytes per row,
+// U rows in flight) and adds its four partial sums to the result with atomics (red.global.add.f32).
+__global__ void __launch_bounds__(128) colsum_acc_small_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                               int64_t rows, int nvec, int64_t ld, int64_t rows_per,
+                                                               float scale) {
+    LG_PDL_TRIGGER();
+    constexpr int U = 8;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (int)(g % nvec);
+    const int64_t r0 = (g / nvec) * rows_per;
+    int64_t r1 = r0 + rows_per;
+    if (r1 > rows) r1 = rows;
+    if (r0 >= rows) return;
+    const float4* p = reinterpret_cast<const float4*>(x) + v;
+    const int64_t ldv = ld >> 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t r = r0;
+    for (; r + U <= r1; r += U) {
+        float4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = __ldg(p + (r + u) * ldv);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+    }
+    for (; r < r1; ++r) {
+        const float4 t = __ldg(p + r * ldv);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float* o = out + 4 * (int64_t)v;
+    atomicAdd(o + 0, acc.x * scale);
+    atomicAdd(o + 1, acc.y * scale);
+    atomicAdd(o + 2, acc.z * scale);
+    atomicAdd(o + 3, acc.w * scale);
+}
+
+// returns true when it took the problem
+bool colsum_acc_small(const float* x, float* out, int64_t rows, int64_t cols, int64_t ld, float scale) {
+    static const bool off = getenv("LG_NO_SMALL_COLSUM") != nullptr;
+    if (off || cols % 4 || ld % 4 || !aligned16(x) || rows < 256 || cols > (1 << 20)) return false;
+    const int nvec = (int)(cols / 4);
+    const int64_t threads = (int64_t)lg::sm_count() * 128;      // one CTA per SM: resident beside a GEMM CTA
+    int64_t slices = threads / nvec;
+    if (slices < 1) slices = 1;
+    if (slices > rows / 32) slices = rows / 32;                 // >= 32 rows per thread
+    const int64_t rows_per = (rows + slices - 1) / slices;
+    slices = (rows + rows_per - 1) / rows_per;
+    const int64_t total = slices * nvec;
+    colsum_acc_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream()>>>(x, out, rows, nvec, ld, rows_per, scale);
+    return true;
+}
+
 template <typename T>
 int reduce_op(int op, const void* x, void* out, int64_t outer, int64_t rlen, int64_t inner, double scale, int64_t ld,
               int acc_out = 0) {
@@ -377,6 +433,11 @@ extern "C" int lg_reduce_pitched(int op, int dtype, const void* x, void* out, in
     LG_REQUIRE(ld >= inner && inner >= 1, "lg_reduce_pitched: need ld >= inner >= 1");
     LG_REQUIRE(inner > 1 || ld == 1, "lg_reduce_pitched: a pitch needs inner > 1");
     LG_REQUIRE(!accumulate || op == LG_RED_SUM, "lg_reduce_pitched: accumulate is defined for sums only");
+    if (dtype == LG_F32 && op == LG_RED_SUM && accumulate && outer == 1 && inner > 1 &&
+        colsum_acc_small((const float*)x, (float*)out, rlen, inner, ld, (float)scale)) {
+        LG_CHECK_LAUNCH();
+        return 0;
+    }
     if (dtype == LG_F32) return reduce_op<float>(op, x, out, outer, rlen, inner, scale, ld, accumulate);
     if (dtype == LG_F64) return reduce_op<double>(op, x, out, outer, rlen, inner, scale, ld, accumulate);
     return set_error("lg_reduce_pitched: unsupported dtype %d", dtype);

@@ -214,6 +214,7 @@ class Adam(Optimizer):
         # the step counter lives on the device (and is advanced there) so that a step captured into
         # a CUDA graph keeps counting when it is replayed
         self._t_dev = a.T.from_numpy(np.array([self.t], dtype=np.int64), requires_grad=False)
+        a.segments(self.parameters)          # uploaded now: the first step may already be under CUDA-graph capture
 
     def steps_taken(self):
         """Parameter updates performed so far (``t`` of the reference), read from the device counter when the

@@ -169,10 +169,12 @@ class DataParallel(object):
             rt.api.nccl_init(idbuf.ctypes.data, self.world, self.rank)
             self._nccl = True
         want = (exchange or os.environ.get('LG_DP_EXCHANGE', 'auto')).lower()
-        if self.world == 1 and want in ('auto', 'local') and self.arena is not None \
-                and hasattr(optimizer, '_bucket_step_range'):
-            # one GPU: nothing to exchange, but the optimizer still leaves the critical path -- every bucket of parameters
-            # is updated by a small-footprint kernel on the collective stream as soon as its gradients are final
+        if self.world == 1 and want == 'local' and self.arena is not None and hasattr(optimizer, '_bucket_step_range'):
+            # one GPU, on request only: every bucket of parameters is updated by the small-footprint kernel on the
+            # collective stream as soon as its gradients are final.  Measured on BERT-base batch 32 (profiles/
+            # r2_bench_n1_local_vs_plain.txt): 8.97 ms per step against 8.53 ms for loss.backward(); optimizer.step() --
+            # 3.7 GB of optimizer traffic running beside the GEMMs costs them more L2 / HBM than the overlap saves, so
+            # 'auto' keeps the plain step on one GPU (with N ranks the traffic is 1/N and comes with the exchange)
             self.exchange = 'local'
         single = self.world == 1 and want == 'nvls'          # a team of one: exercises the whole path on one GPU
         if self.arena is not None and want in ('auto', 'nvls') and (self._nccl or single) \
@@ -299,6 +301,19 @@ class DataParallel(object):
             bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '24' if self.exchange in ('nvls', 'local') else '64')) << 20
         nvls_step = _step_buckets and self.exchange == 'nvls'
         local_step = _step_buckets and self.exchange == 'local'
+        if (nvls_step or local_step) and os.environ.get('LG_DP_NO_OVERLAP'):
+            # the whole arena as ONE bucket after backward (A/B switch: how much does running beside backward buy?)
+            loss.backward()
+            a, P = self.arena, len(self.optimizer.parameters)
+            a.adopt_grads(self.optimizer.parameters)
+            a.rt.api.nccl_fork()
+            if nvls_step:
+                self.optimizer._mc_exchange_range(a, self._mc, 0, P, 0, a.total, self.rank, self.world, last=True)
+            else:
+                self.optimizer._bucket_step_range(a, 0, P, 0, a.total, last=True)
+            a.rt.api.nccl_wait()
+            a.param_buf._bf16 = None
+            return
         if not (nvls_step or local_step) and (self.world == 1 or not self._nccl or os.environ.get('LG_DP_NO_OVERLAP')):
             loss.backward()
             self.sync_gradients()
