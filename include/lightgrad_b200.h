@@ -198,7 +198,10 @@ int lg_gemm_grouped(int mode, int dtype, const LgGemmDesc* d, int groups, const 
  * One plain (unbatched) product -- the two halves of gelu(x W1^T + b1) in BertLayer (examples/bert.py:12,150-153
  * of the reference):
  *   LG_EPI_GELU_FWD: c = a b + bias (kept for backward) and aux = gelu(c), both written by the epilogue;
- *   LG_EPI_GELU_BWD: c = (a b) * gelu'(aux), aux = the pre-activation saved by the forward call.
+ *   LG_EPI_GELU_BWD: c = (a b) * gelu'(aux), aux = the pre-activation saved by the forward call; `bias`, if not
+ *                    NULL, is not added: bias[n] += sum over rows of c[:, n] (c is the gradient of the pre-activation,
+ *                    so this is the gradient of the first Linear's bias, accumulated by the epilogue instead of a
+ *                    second pass over c).
  * Batched, N <= 128, tensor-core mode only (check lg_gemm_tc_supported) -- attention of BertSelfAttention
  * (examples/bert.py:78-88):
  *   LG_EPI_SOFTMAX_FWD: c = softmax(alpha * (a b)) along each row            (scores -> probabilities);
@@ -268,9 +271,12 @@ int lg_layernorm_fwd(int dtype, const void* x, const void* gamma, const void* be
  * folded into the normalisation; the sum is written to sum_out (it is the x that lg_layernorm_bwd needs). */
 int lg_add_layernorm_fwd(int dtype, const void* a, const void* b, void* sum_out, const void* gamma, const void* beta,
                          void* y, void* mean, void* rstd, int64_t rows, int64_t cols, double eps);
+/* dx_colsum (cols values, or NULL; float32 rows of <= 1024 elements): overwritten with the column sums of dx -- when x
+ * is the output of a Linear layer (LayerNorm(dense(h) + skip)) they are that layer's bias gradient, formed here instead
+ * of by a pass that reads dx back */
 int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd,
                      const void* g, void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols,
-                     int accumulate);
+                     int accumulate, void* dx_colsum);
 
 /* Multi-head self-attention core of BertSelfAttention (examples/bert.py:68-88 of the reference) as ONE kernel per
  * direction: per (batch, head) tile  out = softmax(scale * Q K^T) V  with the scores and probabilities kept on chip
@@ -279,14 +285,17 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
  *         head_dim values at column h*head_dim (the reference's reshape(b, s, h, d).transpose(0, 2, 1, 3) as a view)
  *   out   (batch*seq, heads*head_dim): heads merged back, the reference's context.transpose(0, 2, 1, 3).reshape
  *   lse   (batch*heads*seq): scale * rowmax + ln(rowsum) per query, saved for backward
- *   lg_attention_bwd recomputes the probabilities from qkv and lse and writes dQ, dK, dV in qkv's layout.
+ *   lg_attention_bwd recomputes the probabilities from qkv and lse and writes dQ, dK, dV in qkv's layout; dbq / dbk /
+ *         dbv (heads*head_dim each, or NULL): the column sums of dQ / dK / dV are ADDED to them -- the bias gradients
+ *         of the three projections, taken from the registers that hold the rows.
  * lg_attention_supported: 1 when the fused kernels take the shape (float32, seq 128, head_dim 64); other shapes use
  * the batched lg_gemm / lg_gemm_epilogue path. */
 int lg_attention_supported(int dtype, int64_t seq, int64_t head_dim);
 int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
                      double scale, void* out, void* lse);
 int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout, const void* lse, int64_t batch,
-                     int64_t seq, int64_t heads, int64_t head_dim, double scale, void* dqkv);
+                     int64_t seq, int64_t heads, int64_t head_dim, double scale, void* dqkv, void* dbq, void* dbk,
+                     void* dbv);
 
 /* ---- optimizers (replaces the per-parameter python loops of optim.py) ----------------------- */
 /* all tensors of one optimizer live in flat fp32 arenas; `seg_end_dev[i]` (device, int64) is the

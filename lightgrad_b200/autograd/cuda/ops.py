@@ -75,10 +75,13 @@ def _bf16_ptr(t):
 
 
 def _written(t):
-    """``t``'s block is about to be modified in place: its staging copy (if any) is stale."""
+    """``t``'s block is about to be modified in place: its staging copy and any column sums a producer left for a
+    matrix in it are stale."""
     root = _root(t)
     if root._bf16 is not None:
         root._bf16 = None
+    if root._colsum is not None:
+        root._colsum = None
 
 
 def drop_staging_copies():
@@ -978,7 +981,7 @@ class linear(Function):
             with rt.side_stream(g2, x2, writes=(wg,) if bg is None else (wg, bg)):
                 _gemm(_swap_last(g2), x2, out=wg, accumulate=True, cls='W')
                 if bg is not None:
-                    _bias_grad(g2._code, g2.ptr, bg.ptr, g2._shape[0], g2._shape[1], g2._strides[0])
+                    _bias_grad(g2._code, g2.ptr, bg.ptr, g2._shape[0], g2._shape[1], g2._strides[0], src=g2)
             return (dx, Function.ACCUMULATED, Function.ACCUMULATED) if has_bias else (dx, Function.ACCUMULATED)
         if wg is not None:
             rt.side_join_if_written(wg)       # a weight shared with another layer may have side-stream writes pending
@@ -1048,7 +1051,7 @@ def _gemm_epilogue(a, b, out, bias, epi, aux, cls='F'):
     _written(out)
     if epi == 1:
         _written(aux)
-    mode, code, pa, pb = _mode_for(cls), a._code, a.ptr, b.ptr
+    mode, code, pa, pb = _mode_for(cls), a._code, a.ptr, b.ptr     # (epi 2: ``bias`` receives the result's column sums)
     if mode == rt.GEMM_BF16_TC:
         ok = code == rt.F32 and rt.api.gemm_tc_supported(mode, rt.BF16, C.byref(d))
         if ok:
@@ -1128,7 +1131,14 @@ class mlp_gelu(Function):
             g2 = g2.contiguous()
         code = x2._code
         dh = CudaTensor._new(h._shape, h._dtype)
-        _gemm_epilogue(g2, w2, dh, None, 2, h, cls='X')            # dh = (dY W2) * gelu'(h)
+        grads = [_direct_grad(p, code) for p in (w1, b1, w2, b2)]
+        fused_ok = all(g is not None for g in grads) and min(w1._shape[0], w2._shape[0]) > 1
+        # dh = (dY W2) * gelu'(h); with the gradient arena in place the same epilogue also adds the column sums of dh
+        # -- the gradient of b1 -- to it, instead of a separate pass over the (rows x intermediate) matrix
+        b1_in_epilogue = fused_ok and 'bias_epi' not in _DISABLED
+        if b1_in_epilogue:
+            rt.side_join_if_written(grads[1])
+        _gemm_epilogue(g2, w2, dh, grads[1] if b1_in_epilogue else None, 2, h, cls='X')
         xg = _direct_grad(xin, code) if isinstance(xin, CudaTensor) and xin._shape == tuple(xshape) else None
         if xg is not None:
             rt.side_join_if_written(xg)
@@ -1136,23 +1146,29 @@ class mlp_gelu(Function):
             dx = Function.ACCUMULATED
         else:
             dx = _with_shape(_gemm(dh, w1, cls='X'), xshape)
-        grads = [_direct_grad(p, code) for p in (w1, b1, w2, b2)]
-        if all(g is not None for g in grads) and min(w1._shape[0], w2._shape[0]) > 1:
+        if fused_ok:
             w1g, b1g, w2g, b2g = grads
             with rt.side_stream(g2, dh, act, x2, writes=tuple(grads)):
                 _gemm(_swap_last(g2), act, out=w2g, accumulate=True, cls='W')
-                _bias_grad(code, g2.ptr, b2g.ptr, g2._shape[0], g2._shape[1], g2._strides[0])
+                _bias_grad(code, g2.ptr, b2g.ptr, g2._shape[0], g2._shape[1], g2._strides[0], src=g2)
                 _gemm(_swap_last(dh), x2, out=w1g, accumulate=True, cls='W')
-                _bias_grad(code, dh.ptr, b1g.ptr, dh._shape[0], dh._shape[1], dh._strides[0])
+                if not b1_in_epilogue:
+                    _bias_grad(code, dh.ptr, b1g.ptr, dh._shape[0], dh._shape[1], dh._strides[0])
             return (dx,) + (Function.ACCUMULATED,) * 4
         return (dx, _gemm(_swap_last(dh), x2, cls='W'), _reduce(RED['SUM'], dh, (0,), False),
                 _gemm(_swap_last(g2), act, cls='W'), _reduce(RED['SUM'], g2, (0,), False))
 
 
-def _bias_grad(code, g_ptr, out_ptr, rows, cols, ld):
+def _bias_grad(code, g_ptr, out_ptr, rows, cols, ld, src=None):
     """out[cols] += column sums of the (rows, cols) gradient at g_ptr (row pitch ld): a bias gradient added straight
-    into its slot of the gradient arena.  (LG_DISABLE=bias_grad skips it: a timing experiment, the result is wrong.)"""
+    into its slot of the gradient arena.  When the kernel that produced the gradient (``src``: LayerNorm backward)
+    left its column sums next to it, they are added instead of reading the matrix back.
+    (LG_DISABLE=bias_grad skips it all: a timing experiment, the result is wrong.)"""
     if 'bias_grad' in _DISABLED:
+        return
+    note = _root(src)._colsum if src is not None else None
+    if note is not None and note[1:] == (g_ptr, rows, cols, ld) and note[0]._code == code:
+        rt.api.ew_flat(EW['ADD'], code, out_ptr, note[0].ptr, None, out_ptr, cols, 0.0)
         return
     rt.api.reduce_pitched(RED['SUM'], code, g_ptr, out_ptr, 1, rows, cols, ld, 1.0, 1)
 
@@ -1236,8 +1252,14 @@ class self_attention(Function):
         if isinstance(probs, tuple):
             # fused path: dQ, dK, dV from one residency of Q, K, V, dO (probabilities recomputed from the saved LSE)
             out, lse = probs
-            rt.api.attention_bwd(x2._code, qkv.ptr, out.ptr, g.ptr, lse.ptr, b, s, heads, dh, scale, dqkv.ptr)
-            return self_attention._projection_backward(ctx, dqkv, x2, rows, H, xshape)
+            bgs = [_direct_grad(bias, x2._code) for bias in (bq, bk, bv)]
+            in_kernel = all(t is not None for t in bgs) and 'bias_epi' not in _DISABLED
+            if in_kernel:
+                for t in bgs:
+                    rt.side_join_if_written(t)
+            rt.api.attention_bwd(x2._code, qkv.ptr, out.ptr, g.ptr, lse.ptr, b, s, heads, dh, scale, dqkv.ptr,
+                                 *([t.ptr for t in bgs] if in_kernel else [None, None, None]))
+            return self_attention._projection_backward(ctx, dqkv, x2, rows, H, xshape, bias_done=in_kernel)
         _gemm(_swap_last(probs), go, out=dv, cls='A')                   # dV = P^T dO
         ds = CudaTensor._new(probs._shape, x2._dtype)
         if not _attention_gemm(go, _swap_last(v), ds, 4, scale, aux=probs):   # dS straight from the dP GEMM's epilogue
@@ -1249,8 +1271,9 @@ class self_attention(Function):
         return self_attention._projection_backward(ctx, dqkv, x2, rows, H, xshape)
 
     @staticmethod
-    def _projection_backward(ctx, dqkv, x2, rows, H, xshape):
-        """dX, dW_g, db_g of the three projections from the stacked (3, rows, H) gradient of Q, K, V."""
+    def _projection_backward(ctx, dqkv, x2, rows, H, xshape, bias_done=False):
+        """dX, dW_g, db_g of the three projections from the stacked (3, rows, H) gradient of Q, K, V
+        (``bias_done``: the attention kernel already added the column sums to the bias gradients)."""
         wq, bq, wk, bk, wv, bv = ctx._parents[1:7]
         parts = [dqkv._view((rows, H), (H, 1), i * rows * H) for i in range(3)]
         ws = (wq, wk, wv)
@@ -1272,8 +1295,9 @@ class self_attention(Function):
             # dW_g += dY_g^T X and db_g += colsum(dY_g), straight into the arena, on the side stream
             with rt.side_stream(dqkv, x2, writes=tuple(wgs) + tuple(bgs)):
                 _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True, cls='W')
-                for part, bg in zip(parts, bgs):
-                    _bias_grad(part._code, part.ptr, bg.ptr, rows, H, H)
+                if not bias_done:
+                    for part, bg in zip(parts, bgs):
+                        _bias_grad(part._code, part.ptr, bg.ptr, rows, H, H)
             return (dx,) + (Function.ACCUMULATED,) * 6
         if all(w is not None for w in wgs):
             _gemm_grouped(pt, [x2] * 3, wgs, accumulate=True, cls='W')
@@ -1283,7 +1307,9 @@ class self_attention(Function):
             _gemm_grouped(pt, [x2] * 3, dws, cls='W')
         dbs = []
         for part, bg in zip(parts, bgs):
-            if bg is not None and H > 1:
+            if bias_done:
+                dbs.append(Function.ACCUMULATED)
+            elif bg is not None and H > 1:
                 _bias_grad(part._code, part.ptr, bg.ptr, rows, H, H)
                 dbs.append(Function.ACCUMULATED)
             else:
@@ -1567,17 +1593,25 @@ def _ln_backward(x, w, mean, rstd, weight, bias, out_grad):
     cols = x._shape[-1]
     rows = x._numel // cols
     dx = CudaTensor._new(x._shape, x._dtype)
+    # column sums of dx, formed by the same kernel: if x came out of a Linear layer (the residual blocks) they are that
+    # layer's bias gradient, and its backward picks them up from the buffer's note instead of re-reading dx
+    cs = None
+    if x._code == rt.F32 and cols % 4 == 0 and 8 <= cols <= 1024 and rows >= 64 and 'bias_epi' not in _DISABLED:
+        cs = CudaTensor._new((cols,), x._dtype, requires_grad=False)
+        _root(dx)._colsum = (cs, dx.ptr, rows, cols, cols)
+    cs_ptr = cs.ptr if cs is not None else None
     wg, bg = weight.grad, bias.grad
     if weight.requires_grad and bias.requires_grad and wg is not None and bg is not None and wg._contig \
             and bg._contig and wg._code == bg._code == x._code and wg._shape == bg._shape == (cols,):
         # d(gamma), d(beta) are added straight into the existing gradients
-        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, wg.ptr, bg.ptr, rows, cols, 1)
+        rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, wg.ptr, bg.ptr, rows, cols, 1,
+                             cs_ptr)
         # (the library sums the per-CTA partials into wg / bg on the side stream)
         rt._side_dirty.add(wg.ptr)
         rt._side_dirty.add(bg.ptr)
         return dx, Function.ACCUMULATED, Function.ACCUMULATED
     dw, db = CudaTensor._new((cols,), x._dtype), CudaTensor._new((cols,), x._dtype)
-    rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols, 0)
+    rt.api.layernorm_bwd(x._code, x.ptr, w.ptr, mean.ptr, rstd.ptr, g.ptr, dx.ptr, dw.ptr, db.ptr, rows, cols, 0, cs_ptr)
     return dx, dw, db
 
 

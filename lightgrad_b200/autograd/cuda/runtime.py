@@ -98,10 +98,11 @@ _SIGNATURES = {
     'lg_cross_entropy_bwd': [C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64],
     'lg_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
     'lg_add_layernorm_fwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double],
-    'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int],
+    'lg_layernorm_bwd': [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp],
     'lg_attention_supported': [C.c_int, C.c_int64, C.c_int64],
     'lg_attention_fwd': [C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, _vp, _vp],
-    'lg_attention_bwd': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, _vp],
+    'lg_attention_bwd': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double, _vp,
+                         _vp, _vp, _vp],
     'lg_sgd_step': [_vp, _vp, _vp, C.c_int64, C.c_double, C.c_double],
     'lg_adam_step': [C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp,
                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int],
@@ -277,11 +278,12 @@ def device_props():
 
 class Buffer(object):
     """Ref-counted device block from the library's caching allocator (analogue of PooledBuffer)."""
-    __slots__ = ('ptr', 'nbytes', '_free', '_bf16', '__weakref__')
+    __slots__ = ('ptr', 'nbytes', '_free', '_bf16', '_colsum', '__weakref__')
 
     def __init__(self, nbytes):
         self.ptr = 0
         self._bf16 = None          # bf16 staging copy of the whole block (bf16 tensor-core matmul mode), or None
+        self._colsum = None        # (tensor, ptr, rows, cols, ld): column sums a producer kernel left for a matrix in here
         a = ensure_device()
         p = _vp()
         a.alloc(int(nbytes), C.byref(p))
@@ -302,10 +304,10 @@ class Buffer(object):
 class ExternalBuffer(object):
     """Device memory this module does not own (a window of the NVLink multicast region): same face as Buffer, never
     freed here; ``keep`` holds whatever must outlive it."""
-    __slots__ = ('ptr', 'nbytes', 'keep', '_bf16', '__weakref__')
+    __slots__ = ('ptr', 'nbytes', 'keep', '_bf16', '_colsum', '__weakref__')
 
     def __init__(self, ptr, nbytes, keep=None):
-        self.ptr, self.nbytes, self.keep, self._bf16 = int(ptr), int(nbytes), keep, None
+        self.ptr, self.nbytes, self.keep, self._bf16, self._colsum = int(ptr), int(nbytes), keep, None, None
 
 
 class ArenaSlice(object):

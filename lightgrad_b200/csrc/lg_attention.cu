@@ -102,7 +102,32 @@ struct AttnParams {
     const float* o;                  // backward: forward result
     const float* dout;
     float* dqkv;                     // backward: (3, rows, H)
+    float* dbias[3];                 // backward: d(bias) of the Q / K / V projections (H each), accumulated; or nullptr
 };
+
+// column sums of a 32 x 32 chunk held one row per lane (see lg_gemm_tc.cu): lane j ends with the sum of column j
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float give = upper ? x[i] : x[i + s];
+            const float keep = upper ? x[i + s] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, give, s);
+        }
+    }
+    return x[0];
+}
+// d(bias)[col0 + lane] += column sum of this warp's 32 rows of a gradient chunk
+__device__ __forceinline__ void bias_grad_chunk(float* dbias, const uint32_t (&v)[32], int col0, int lane) {
+    if (dbias == nullptr) return;
+    float x[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
+    const float sum = warp_transpose_sum(x, lane);
+    atomicAdd(dbias + col0 + lane, sum);
+}
 
 struct AttnMaps {
     CUtensorMap qkv_k;    // stacked (3 * rows, H) Q/K/V buffer, box 32 x 128, SWIZZLE_128B       (K-major operand tiles)
@@ -424,6 +449,10 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                     reinterpret_cast<uint4*>(dv + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     reinterpret_cast<uint4*>(dq + c * 32)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
                 }
+                // the projections' bias gradients are the column sums of dQ / dK / dV: taken from the registers that
+                // hold the rows, not by three kernels that read the matrices back
+                bias_grad_chunk(p.dbias[2], v, h * HD + c * 32, lane);
+                bias_grad_chunk(p.dbias[0], w, h * HD + c * 32, lane);
             }
             mbar_wait(b_dk, ph);
             tc_fence_after();
@@ -435,6 +464,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     reinterpret_cast<uint4*>(dk + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                bias_grad_chunk(p.dbias[1], v, h * HD + c * 32, lane);
             }
             tc_fence_before();       // (the next tile's dV / dQ / dK products need this warp's next arrivals first)
         }
@@ -512,7 +542,8 @@ int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int
 }
 
 int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout, const void* lse, int64_t batch,
-                     int64_t seq, int64_t heads, int64_t head_dim, double scale, void* dqkv) {
+                     int64_t seq, int64_t heads, int64_t head_dim, double scale, void* dqkv, void* dbq, void* dbk,
+                     void* dbv) {
     LG_INIT();
     if (check_shape("lg_attention_bwd", dtype, batch, seq, heads, head_dim)) return 1;
     LG_REQUIRE((((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv) & 15) == 0,
@@ -534,6 +565,9 @@ int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* do
     p.o = (const float*)out;
     p.dout = (const float*)dout;
     p.dqkv = (float*)dqkv;
+    p.dbias[0] = (float*)dbq;
+    p.dbias[1] = (float*)dbk;
+    p.dbias[2] = (float*)dbv;
     static bool attr_done = false;
     if (!attr_done) {
         LG_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));

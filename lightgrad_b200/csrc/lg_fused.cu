@@ -301,8 +301,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
 
 // ---- float32 fast path: one warp per row, the row lives in registers (NV float4 per lane), 128-bit accesses.
 // Valid for cols % 4 == 0 and cols <= NV*128 (BERT: 768 -> NV = 6).
+// (gamma / beta are re-read through L1 for every row instead of living in 2 x NV x 4 registers: at 128 registers per
+//  thread only two CTAs fit on an SM -- ncu: 22 % of the warp slots active, 11.5 us for 50 MB -- with <= 80 it is three)
 template <int NV>
-__global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
+__global__ void __launch_bounds__(256, (NV <= 6 ? 3 : 2)) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                          float* __restrict__ sum_out, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ y,
                                                          float* __restrict__ mean, float* __restrict__ rstd,
@@ -314,15 +316,6 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inv = 1.0f / (float)cols;
     const int nchunks = cols >> 2;
-    float4 gm[NV], bt[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c = lane + 32 * j;
-        if (c < nchunks) {
-            gm[j] = reinterpret_cast<const float4*>(gamma)[c];
-            bt[j] = reinterpret_cast<const float4*>(beta)[c];
-        }
-    }
     for (; row < rows; row += row_step) {
         const float4* p = reinterpret_cast<const float4*>(x + row * cols);
         float4 v[NV];
@@ -367,11 +360,13 @@ __global__ void __launch_bounds__(256) ln_fwd_vec_kernel(const float* __restrict
         for (int j = 0; j < NV; ++j) {
             const int c = lane + 32 * j;
             if (c < nchunks) {
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
                 float4 r;
-                r.x = v[j].x * rs * gm[j].x + bt[j].x;
-                r.y = v[j].y * rs * gm[j].y + bt[j].y;
-                r.z = v[j].z * rs * gm[j].z + bt[j].z;
-                r.w = v[j].w * rs * gm[j].w + bt[j].w;
+                r.x = v[j].x * rs * gm.x + bt.x;
+                r.y = v[j].y * rs * gm.y + bt.y;
+                r.z = v[j].z * rs * gm.z + bt.z;
+                r.w = v[j].w * rs * gm.w + bt.w;
                 o[c] = r;
             }
         }
@@ -388,14 +383,17 @@ template <int NV>
 __global__ void __launch_bounds__(256, (NV <= 6 ? 2 : 1))
 ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ g, float* __restrict__ dx,
-                  float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows, int cols,
-                  int64_t part_ld) {
+                  float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ dxsum_part,
+                  int64_t rows, int cols, int64_t part_ld) {
     LG_PDL_TRIGGER();
-    // [gamma : cols floats][8 warps x cols floats]: gamma is re-read from here every row (keeps it out of the
-    // register file so two CTAs fit on an SM); every warp parks its register partials in its slot at the end
+    // [gamma : cols floats][8 warps x cols floats][8 warps x cols floats, only with dxsum_part]: gamma is re-read from
+    // here every row (keeps it out of the register file so two CTAs fit on an SM); every warp parks its register
+    // partials in its slot at the end; the third region accumulates the column sums of dx, row by row (each lane owns
+    // its columns of its warp's slot: no synchronisation) -- the bias gradient of the Linear layer that produced x
     extern __shared__ unsigned char smem_raw[];
     float* sgamma = reinterpret_cast<float*>(smem_raw);
     float* stage = sgamma + cols;
+    float* sdx = stage + 8 * (size_t)cols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -404,10 +402,13 @@ ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
     for (int c = threadIdx.x; c < nchunks; c += blockDim.x)
         reinterpret_cast<float4*>(sgamma)[c] = reinterpret_cast<const float4*>(gamma)[c];
     float4 ag[NV], ab[NV];
+    float4* my_dx = reinterpret_cast<float4*>(sdx + (size_t)(threadIdx.x >> 5) * cols);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         ag[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = lane + 32 * j;
+        if (dxsum_part != nullptr && c < nchunks) my_dx[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     for (; row < rows; row += row_step) {
@@ -454,6 +455,11 @@ ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
                 r.z = rs * (gv[j].z - s1 - xh[j].z * s2);
                 r.w = rs * (gv[j].w - s1 - xh[j].w * s2);
                 pd[c] = r;
+                if (dxsum_part != nullptr) {
+                    float4 t = my_dx[c];
+                    t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                    my_dx[c] = t;
+                }
             }
         }
     }
@@ -482,6 +488,14 @@ ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += stage[(size_t)w * cols + j];
         dbeta_part[(int64_t)blockIdx.x * part_ld + j] = v;
+    }
+    if (dxsum_part != nullptr) {
+        for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += sdx[(size_t)w * cols + j];
+            dxsum_part[(int64_t)blockIdx.x * part_ld + j] = v;
+        }
     }
 }
 
@@ -755,7 +769,7 @@ static int layernorm_fwd_impl(int dtype, const void* x, const void* res, void* s
 }
 
 int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* mean, const void* rstd, const void* g,
-                     void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols, int accumulate) {
+                     void* dx, void* dgamma, void* dbeta, int64_t rows, int64_t cols, int accumulate, void* dx_colsum) {
     LG_INIT();
     if (rows * cols == 0) return 0;
     size_t es = dtype_size(dtype);
@@ -771,19 +785,34 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
         int64_t cap2 = (int64_t)sm_count() * 2;
         grid = (int)(blocks < cap2 ? blocks : cap2);
     }
-    void* part = tmp_alloc(2 * (size_t)grid * cols * es);
+    // dx_colsum (optional, float32 fast path only): the column sums of dx, overwritten -- when x is the output of a Linear
+    // layer (residual blocks: LayerNorm(dense(h) + skip)) they ARE that layer's bias gradient, and forming them here
+    // saves the pass that would read dx back
+    const bool want_dxsum = dx_colsum != nullptr;
+    LG_REQUIRE(!want_dxsum || fast, "lg_layernorm_bwd: dx_colsum needs the float32 fast path (16-byte aligned rows of <= 1024 floats, cols %% 4 == 0)");
+    void* part = tmp_alloc((want_dxsum ? 3 : 2) * (size_t)grid * cols * es);
     if (!part) return 1;
-    // partial rows are [dgamma | dbeta] side by side: when the two gradients are adjacent in memory (LayerNorm's
-    // weight and bias are consecutive parameters of the gradient arena) one column reduction finishes both
-    const int64_t part_ld = 2 * cols;
+    // partial rows are [dgamma | dbeta (| dx sums)] side by side: when the two gradients are adjacent in memory
+    // (LayerNorm's weight and bias are consecutive parameters of the gradient arena) one column reduction finishes both
+    const int64_t part_ld = (want_dxsum ? 3 : 2) * cols;
     void* pg = part;
     void* pb = (char*)part + (size_t)cols * es;
+    void* px = want_dxsum ? (char*)part + 2 * (size_t)cols * es : nullptr;
     if (fast) {
-        const size_t smem_fast = 9 * (size_t)cols * sizeof(float);   // gamma + 8 warp slots: <= 36 KB for cols <= 1024
+        // gamma + 8 warp slots (+ 8 more for the dx sums): <= 36 (68) KB for cols <= 1024
+        const size_t smem_fast = (want_dxsum ? 17 : 9) * (size_t)cols * sizeof(float);
 #define LN_B(NV_)                                                                                              \
-    ln_bwd_vec_kernel<NV_><<<grid, 256, smem_fast, stream()>>>((const float*)x, (const float*)gamma, (const float*)mean, \
-                                                          (const float*)rstd, (const float*)g, (float*)dx,     \
-                                                          (float*)pg, (float*)pb, rows, (int)cols, part_ld)
+    do {                                                                                                       \
+        static bool attr_done = false;                                                                         \
+        if (!attr_done) {                                                                                      \
+            cudaFuncSetAttribute(ln_bwd_vec_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024 * 4); \
+            attr_done = true;                                                                                  \
+        }                                                                                                      \
+        ln_bwd_vec_kernel<NV_><<<grid, 256, smem_fast, stream()>>>((const float*)x, (const float*)gamma,      \
+                                                              (const float*)mean, (const float*)rstd,          \
+                                                              (const float*)g, (float*)dx, (float*)pg,         \
+                                                              (float*)pb, (float*)px, rows, (int)cols, part_ld); \
+    } while (0)
         if (nv == 2) LN_B(2); else if (nv == 4) LN_B(4); else if (nv == 6) LN_B(6); else LN_B(8);
 #undef LN_B
     } else if (dtype == LG_F32)
@@ -815,6 +844,7 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
         rc = lg_reduce_pitched(LG_RED_SUM, dtype, pg, dgamma, 1, grid, cols, part_ld, 1.0, accumulate);
         if (!rc) rc = lg_reduce_pitched(LG_RED_SUM, dtype, pb, dbeta, 1, grid, cols, part_ld, 1.0, accumulate);
     }
+    if (!rc && want_dxsum) rc = lg_reduce_pitched(LG_RED_SUM, dtype, px, dx_colsum, 1, grid, cols, part_ld, 1.0, 0);
     tmp_free(part);      // deferred until the join while on the side stream
     if (side) lg_side_end();
     return rc;

@@ -180,12 +180,15 @@ int lg_gemm_epilogue(int mode, int dtype, const LgGemmDesc* d, const void* a, co
         rc = gemm_tc_epilogue(mode, d, a, b, c, bias, epi_op, aux, aux_ld, alpha);
     } else {
         // exact path: the product, then the activation as a strided elementwise pass over the same buffers
-        rc = gemm_simt(dtype, d, a, b, c, bias, 0);
+        rc = gemm_simt(dtype, d, a, b, c, epi_op == LG_EPI_GELU_BWD ? nullptr : bias, 0);
         const int64_t shape[2] = {d->M, d->N}, sc[2] = {d->sc_m, 1}, sx[2] = {aux_ld, 1};
         if (!rc && epi_op == LG_EPI_GELU_FWD)
             rc = lg_ew(LG_EW_GELU, dtype, 2, shape, c, sc, nullptr, nullptr, nullptr, nullptr, aux, sx, 0.0);
-        else if (!rc)
+        else if (!rc) {
             rc = lg_ew(LG_EW_GELU_BWD, dtype, 2, shape, aux, sx, c, sc, nullptr, nullptr, c, sc, 0.0);
+            // (bias names the accumulation target of the result's column sums for this epilogue, see the header)
+            if (!rc && bias) rc = lg_reduce_pitched(LG_RED_SUM, dtype, c, const_cast<void*>(bias), 1, d->M, d->N, d->sc_m, 1.0, 1);
+        }
     }
     if (g_prof_on) {
         LG_CUDA(cudaEventRecord(pr.e1, stream()));

@@ -67,6 +67,8 @@ struct TcParams {
     long long aux_ld;
     long long aux_sb0, aux_sb1;   // its batch strides (epi_op 4; same batch dims as C)
     float epi_alpha;
+    float* colsum;            // epi_op 2: colsum[n] += sum over rows of C (the bias gradient of the layer that produced
+                              // the pre-activations), accumulated by the epilogue; nullptr: not wanted
     // tail-wave split (plain one-problem GEMMs, splits == 1): the last `tiles % clusters` tiles, which would run as
     // a mostly empty extra wave, are each cut into tail_splits K-ranges whose partials meet by reduce-add
     int items_per_batch;      // work items of one problem: tail_first whole tiles + (tiles - tail_first) * tail_splits
@@ -145,7 +147,25 @@ struct EpiTile {
     int bc1, bc0;           // batch coordinates
     int reduce_out;
     bool rows_live;
+    float* colsum;          // epi_op 2: column sums of the finished chunk are added here (or nullptr)
 };
+
+// Column sums of a 32 x 32 chunk held one row per lane: five exchange steps in which every lane keeps the half of the
+// columns selected by one bit of its lane number and hands the other half to its partner -- 31 shuffles instead of
+// 32 x 5 -- after which lane j holds the sum of column j over the warp's 32 rows.
+__device__ __forceinline__ float warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float give = upper ? x[i] : x[i + s];
+            const float keep = upper ? x[i + s] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, give, s);
+        }
+    }
+    return x[0];
+}
 
 // stage one 32 x 32 chunk (thread = row) in the 128B-swizzled buffer and hand it to the TMA unit
 __device__ __forceinline__ void epi_store(const CUtensorMap* map, const uint32_t (&v)[32], uint8_t* buf, int col0,
@@ -166,6 +186,18 @@ __device__ __forceinline__ void epi_store(const CUtensorMap* map, const uint32_t
     }
 }
 
+// d(bias) of the layer whose pre-activations an op-2 epilogue multiplies with = column sums of this very result: taken
+// here, from registers, instead of by a kernel that reads the matrix back (50 MB per BERT layer for the FFN).
+// Compiled into the wide-tile kernels only (BN > 128: the shapes a GELU-backward GEMM runs at); the narrow-tile kernels
+// carry the row epilogues and have no registers to spare -- for them the host adds the column sums with lg_reduce.
+__device__ __forceinline__ void epi_colsum(const uint32_t (&v)[32], float* colsum, int col0, int N, int lane) {
+    float x[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
+    const float sum = warp_transpose_sum(x, lane);
+    if (col0 + lane < N) atomicAdd(colsum + col0 + lane, sum);
+}
+
 // v: this thread's 32 accumulator values of the chunk (as raw bits), finished and stored in place
 // this thread's 32 pre-activation values of a chunk (op 2): one 128-byte line; columns past N are never stored
 __device__ __forceinline__ void epi_load_h(const EpiTile& t, int col0, float4 (&h)[8]) {
@@ -176,6 +208,7 @@ __device__ __forceinline__ void epi_load_h(const EpiTile& t, int col0, float4 (&
                    : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+template <bool COLSUM>
 __device__ __forceinline__ void epi_emit(const EpiTile& t, uint32_t (&v)[32], float bcur, const float4 (&h)[8], int col0,
                                          uint8_t* buf, int lane) {
     if (t.bias != nullptr) {
@@ -193,6 +226,9 @@ __device__ __forceinline__ void epi_emit(const EpiTile& t, uint32_t (&v)[32], fl
         }
     }
     epi_store(t.map_c, v, buf, col0, t.row0, t.bc1, t.bc0, t.reduce_out, lane);
+    if constexpr (COLSUM) {
+        if (t.epi_op == 2 && t.colsum != nullptr) epi_colsum(v, t.colsum, col0, t.N, lane);
+    }
     if (t.epi_op == 1) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(epi_gelu(__uint_as_float(v[k])));
@@ -228,7 +264,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiTile& t, float bfirst, co
             if (t.epi_op == 2) epi_load_h(t, col0 + 64, hnext);
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        epi_emit(t, v, bcur, hcur, col0, buf, lane);
+        epi_emit<(BN > 128)>(t, v, bcur, hcur, col0, buf, lane);
     }
 }
 
@@ -573,6 +609,7 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             t.bc0 = bc0;
             t.reduce_out = p.reduce_out | item.partial;
             t.rows_live = t.row0 < p.M;
+            t.colsum = p.colsum;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
             // operands the epilogue reads from global memory, fetched before the wait for the accumulator:
             // op 2: the first chunk's pre-activations (row_aux[0]); op 4: this thread's slice of the probabilities
@@ -814,6 +851,7 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
             t.bc0 = bc0;
             t.reduce_out = p.reduce_out | item.partial;
             t.rows_live = t.row0 < p.M;
+            t.colsum = p.colsum;
             const float bfirst = bias_slice(t.bias, n0 + half * 32 + lane, p.N);
             float hfirst[32];
             {
@@ -1229,6 +1267,15 @@ int gemm_tc_grouped(int mode, const LgGemmDesc* d, int groups, const void* const
     p.aux_sb0 = d->sc_b0;      // a saved matrix of a row epilogue has C's batch layout
     p.aux_sb1 = d->sc_b1;
     p.epi_alpha = (float)alpha;
+    p.colsum = nullptr;
+    float* colsum_after = nullptr;
+    if (epi_op == 2 && p.bias[0] != nullptr) {
+        // LG_EPI_GELU_BWD has no bias to add: the pointer names where the column sums of the result are accumulated --
+        // by the epilogue of the wide-tile kernels, by a column reduction after the launch for narrow tiles
+        if (pl.bn > 128) p.colsum = const_cast<float*>(p.bias[0]);
+        else colsum_after = const_cast<float*>(p.bias[0]);
+        p.bias[0] = nullptr;
+    }
     if (epi_op == 1) {
         // second result: same geometry as C, its own row pitch
         rc = make_map(&maps.aux, aux, N, M, aux_ld, BatchDims{1, 0, 1, 0}, 32, 32);
@@ -1278,8 +1325,11 @@ int gemm_tc_grouped(int mode, const LgGemmDesc* d, int groups, const void* const
     LG_REQUIRE(items64 < 0x7fffffff, "gemm_tc: too many tiles");
     const int items = (int)items64;
     const int grid = cl * (items < max_clusters ? items : max_clusters);
-    return es == 4 ? launch_any<4>(pair_mma, pl.bn, a_mn, b_mn, maps, p, grid)
-                   : launch_any<2>(pair_mma, pl.bn, a_mn, b_mn, maps, p, grid);
+    rc = es == 4 ? launch_any<4>(pair_mma, pl.bn, a_mn, b_mn, maps, p, grid)
+                 : launch_any<2>(pair_mma, pl.bn, a_mn, b_mn, maps, p, grid);
+    if (!rc && colsum_after)
+        rc = lg_reduce_pitched(LG_RED_SUM, LG_F32, c[0], colsum_after, 1, M, N, d->sc_m, 1.0, 1);
+    return rc;
 }
 
 int gemm_tc(int mode, const LgGemmDesc* d, const void* a, const void* b, void* c, const void* bias, int accumulate) {

@@ -247,7 +247,7 @@ class FakeDevice(object):
 
     def gemm_epilogue(self, mode, dt, dref, a, b, c, bias, epi, aux, aux_ld, alpha):
         d = dref._obj
-        self.gemm(mode, dt, dref, a, b, c, bias, 0)
+        self.gemm(mode, dt, dref, a, b, c, None if epi == 2 else bias, 0)
         if dt == rt.BF16:
             dt = rt.F32
         f = NP[dt]
@@ -272,6 +272,8 @@ class FakeDevice(object):
             t = np.tanh((X * c1) * (f(1.0) + c2 * x2))
             du = c1 * (f(1.0) + f(3.0) * c2 * x2)
             Cm[...] = (f(0.5) * (f(1.0) + t) + (f(0.5) * X) * (f(1.0) - t * t) * du) * Cm
+            if bias:            # for this epilogue `bias` names where the result's column sums are accumulated
+                _arr(bias, dt, [d.N])[...] += Cm.sum(axis=0)
 
     def gemm_sm_limit(self, n): pass
 
@@ -325,7 +327,7 @@ class FakeDevice(object):
         _arr(out, dt, [b, s, h, d])[...] = o.transpose(0, 2, 1, 3)
         _arr(lse, dt, [b, h, s])[...] = (m + np.log(z))[..., 0]
 
-    def attention_bwd(self, dt, qkv, out, dout, lse, b, s, h, d, scale, dqkv):
+    def attention_bwd(self, dt, qkv, out, dout, lse, b, s, h, d, scale, dqkv, dbq, dbk, dbv):
         self.launches += 1
         X = _arr(qkv, dt, [3, b * s, h * d])
         q, k, v = (self._heads(X[i], b, s, h, d) for i in range(3))
@@ -339,6 +341,9 @@ class FakeDevice(object):
         G[0] = (ds @ k).transpose(0, 2, 1, 3)
         G[1] = (ds.transpose(0, 1, 3, 2) @ q).transpose(0, 2, 1, 3)
         G[2] = (p.transpose(0, 1, 3, 2) @ do).transpose(0, 2, 1, 3)
+        for i, db in enumerate((dbq, dbk, dbv)):
+            if db:
+                _arr(db, dt, [h * d])[...] += G[i].reshape(b * s, h * d).sum(axis=0)
 
     def prof_gemm_read(self, ms, n, fl):
         ms._obj.value, n._obj.value, fl._obj.value = 0.0, 0, 0.0
@@ -444,7 +449,7 @@ class FakeDevice(object):
         _arr(s, dt, [rows, cols])[...] = _arr(a, dt, [rows, cols]) + _arr(b, dt, [rows, cols])
         self.layernorm_fwd(dt, s, w, bias, y, mean, rstd, rows, cols, eps)
 
-    def layernorm_bwd(self, dt, x, w, mean, rstd, g, dx, dw, db, rows, cols, accumulate):
+    def layernorm_bwd(self, dt, x, w, mean, rstd, g, dx, dw, db, rows, cols, accumulate, dx_colsum=None):
         self.launches += 1
         X, G, W = _arr(x, dt, [rows, cols]), _arr(g, dt, [rows, cols]), _arr(w, dt, [cols])
         mu, rs = _arr(mean, dt, [rows])[:, None], _arr(rstd, dt, [rows])[:, None]
@@ -455,6 +460,8 @@ class FakeDevice(object):
         DW, DB = _arr(dw, dt, [cols]), _arr(db, dt, [cols])
         DW[...] = (DW if accumulate else 0) + (G * xh).sum(axis=0)
         DB[...] = (DB if accumulate else 0) + G.sum(axis=0)
+        if dx_colsum:
+            _arr(dx_colsum, dt, [cols])[...] = _arr(dx, dt, [rows, cols]).sum(axis=0)
 
     # ---- optimizers
     def sgd_step(self, p, g, d, n, lr, mom):

@@ -55,14 +55,23 @@ OPTIMIZERS = {
 }
 
 
-def _check(name, exchange='nvls'):
+def _check(name, exchange='nvls', exact=True):
+    """``exact``: bit-identical parameters (the numpy test double is deterministic).  On the device the gradients
+    themselves are not bit-reproducible from run to run (atomic scatter-adds of the embedding gradient, split-K partial
+    sums), so two runs of the PLAIN step differ in the last bits too: the comparison there is to 1e-4 / 1e-6."""
     want, t_want, loss_want = _run(OPTIMIZERS[name], None)
     for bucket_bytes in (1, 4096, 1 << 30):
         got, t_got, loss_got = _run(OPTIMIZERS[name], bucket_bytes, exchange=exchange)
         assert t_got == t_want
-        assert loss_got == loss_want
+        if exact:
+            assert loss_got == loss_want
+        else:
+            assert abs(loss_got - loss_want) <= 1e-5 * abs(loss_want)
         for a, b in zip(got, want):
-            np.testing.assert_array_equal(a, b)
+            if exact:
+                np.testing.assert_array_equal(a, b)
+            else:
+                np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize('name', sorted(OPTIMIZERS))
@@ -73,7 +82,7 @@ def test_team_of_one_exchange_equals_plain_step_host_logic(fake_device, name):
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', sorted(OPTIMIZERS))
 def test_team_of_one_exchange_equals_plain_step_on_device(cuda, name):
-    _check(name)
+    _check(name, exact=False)
 
 
 # one GPU: the optimizer as per-bucket small-footprint kernels on the collective stream, beside backward (exchange 'local')
@@ -85,7 +94,7 @@ def test_overlapped_optimizer_equals_plain_step_host_logic(fake_device, name):
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', sorted(OPTIMIZERS))
 def test_overlapped_optimizer_equals_plain_step_on_device(cuda, name):
-    _check(name, exchange='local')
+    _check(name, exchange='local', exact=False)
 
 
 @pytest.mark.gpu
@@ -106,16 +115,16 @@ def test_overlapped_optimizer_inside_a_captured_graph(cuda):
             dp.backward_and_step(loss, bucket_bytes=4096)
             return loss
         if graph:
-            sg = StepGraph(step, warmup=0)
+            sg = StepGraph(step, warmup=1)          # one eager step (shape-dependent constants), then capture = step 2
             for _ in range(3):
                 sg.replay()
             sg.destroy()
         else:
-            for _ in range(4):
+            for _ in range(5):
                 step()
         return [p.numpy() for p in model.parameters()]
     for a, b in zip(run(True), run(False)):
-        np.testing.assert_array_equal(a, b)
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.gpu
@@ -138,15 +147,15 @@ def test_exchange_step_inside_a_captured_graph(cuda):
             dp.backward_and_step(loss, bucket_bytes=4096)
             return loss
         if graph:
-            sg = StepGraph(step, warmup=0)          # capture runs the step once
+            sg = StepGraph(step, warmup=1)          # one eager step, then the capture runs the step once
             for _ in range(3):
                 sg.replay()
             sg.destroy()
         else:
-            for _ in range(4):
+            for _ in range(5):
                 step()
         out = [p.numpy() for p in model.parameters()]
         dp.close()
         return out
     for a, b in zip(run(True), run(False)):
-        np.testing.assert_array_equal(a, b)
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
