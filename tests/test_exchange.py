@@ -123,8 +123,10 @@ def test_overlapped_optimizer_inside_a_captured_graph(cuda):
             for _ in range(5):
                 step()
         return [p.numpy() for p in model.parameters()]
+    # five Adam steps: for an element whose gradient is near zero, m / sqrt(v) turns last-bit differences of the gradient
+    # (atomic scatter-adds, split-K) into a visible fraction of lr per step; measured 1.4e-6 on one element in 1024
     for a, b in zip(run(True), run(False)):
-        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.gpu
@@ -157,5 +159,7 @@ def test_exchange_step_inside_a_captured_graph(cuda):
         out = [p.numpy() for p in model.parameters()]
         dp.close()
         return out
+    # five Adam steps: for an element whose gradient is near zero, m / sqrt(v) turns last-bit differences of the gradient
+    # (atomic scatter-adds, split-K) into a visible fraction of lr per step; measured 1.4e-6 on one element in 1024
     for a, b in zip(run(True), run(False)):
-        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
