@@ -15,9 +15,14 @@ ap.add_argument('--mode', default='tf32')
 ap.add_argument('--batch', type=int, default=32)
 ap.add_argument('--warmup', type=int, default=2)
 ap.add_argument('--steps', type=int, default=1)
+ap.add_argument('--layers', type=int, default=None, help="encoder layers (default: BERT-base's 12); 1 gives one launch of "
+                "each kernel at the step's shapes for an `ncu --set full` capture")
 args = ap.parse_args()
 ops.set_matmul_mode(args.mode)
-model = bench.build_bert(CudaTensor, bert.BERT_BASE)
+cfg = dict(bert.BERT_BASE)
+if args.layers:
+    cfg['num_hidden_layers'] = args.layers
+model = bench.build_bert(CudaTensor, cfg)
 opt = light.optim.Adam(model.parameters(), lr=1e-4)
 step = bench.make_step(model, opt, None, light)
 light.Gradients.retain_intermediate = False

@@ -28,7 +28,10 @@ namespace {
 constexpr int SEQ = 128, HD = 64;
 constexpr int TILE_BYTES = SEQ * HD * 4;         // 32 KB: one (128 x 64) fp32 operand tile
 constexpr int KB_BYTES = SEQ * 128;              // 16 KB: 128 rows x one 128-byte swizzle row (32 fp32 of K)
-constexpr int ATT_THREADS = 192;                 // warp 0: TMA + MMA issue (one lane); warp 1: TMEM; warps 2..5: rows
+constexpr int ATT_THREADS = 320;                 // warp 0: TMA + MMA issue (one lane); warp 1: TMEM; warps 2..9: rows
+constexpr int ROW_THREADS = 256;                 // two warps per TMEM lane quarter, each takes half of the columns: the
+                                                 // row work is a chain of TMEM loads, ex2 and shared-memory stores whose
+                                                 // latency one warp per scheduler cannot hide
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
@@ -50,6 +53,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void row_threads_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory"); }
 
 // A (128 x 128 of K, four 16 KB k-blocks, K-major SWIZZLE_128B) times a K-major B tile of N rows
 template <int N, int KBLOCKS>
@@ -153,13 +157,14 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
     uint64_t* b_p = bars + 5;     // probabilities staged (128 arrivals)
     uint64_t* b_o = bars + 6;     // O = P V complete
     uint32_t* tmem_slot = (uint32_t*)(bars + 7);
+    float* xch = (float*)(bars + 8);   // [2][2][128]: row maxima and row sums of the two column halves
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.heads * HD;
     const int tiles = p.batch * p.heads;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(b_qk + i, 1); mbar_init(b_v + i, 1); }
-        mbar_init(b_s, 1); mbar_init(b_p, 128); mbar_init(b_o, 1);
+        mbar_init(b_s, 1); mbar_init(b_p, ROW_THREADS); mbar_init(b_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
@@ -214,8 +219,13 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
         }
     } else if (warp >= 2) {
         const int q = warp & 3;                      // TMEM lane quarter of this warp
+        const int half = (warp - 2) >> 2;            // which half of the columns (the other warp of the quarter: the rest)
         const int row = 32 * q + lane;
         const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
+        float* my_max = xch + half * SEQ + row;
+        float* my_sum = xch + 2 * SEQ + half * SEQ + row;
+        const float* their_max = xch + (half ^ 1) * SEQ + row;
+        const float* their_sum = xch + 2 * SEQ + (half ^ 1) * SEQ + row;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
@@ -223,48 +233,53 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
             uint8_t* sP = smem + (it & 1) * 3 * TILE_BYTES;
             mbar_wait(b_s, ph);
             tc_fence_after();
-            // pass 1: row maximum
+            // this warp's 64 columns of the row stay in registers between the maximum and the exponentials
+            uint32_t v0[32], v1[32];
+            tmem_ld32(v0, t_row + half * 64);
+            tmem_ld32(v1, t_row + half * 64 + 32);
+            tmem_wait_ld();
             float m = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(v, t_row + c * 32);
-                tmem_wait_ld();
 #pragma unroll
-                for (int k = 0; k < 32; ++k) m = fmaxf(m, __uint_as_float(v[k]));
-            }
-            // pass 2: exp(alpha (s - max)) as ex2 of a single fma; the unnormalised values are the A operand of P V
+            for (int k = 0; k < 32; ++k) m = fmaxf(m, fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])));
+            *my_max = m;
+            row_threads_sync();
+            m = fmaxf(m, *their_max);
+            // exp(alpha (s - max)) as ex2 of a single fma; the unnormalised values are the A operand of P V
             const float mneg = -m * p.scale_log2e;
             float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
+            {
                 float x[32];
-                tmem_ld32(v, t_row + c * 32);
-                tmem_wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    x[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2e, mneg));
+                    x[k] = ex2(fmaf(__uint_as_float(v0[k]), p.scale_log2e, mneg));
                     sum += x[k];
                 }
-                store_row_chunk(sP, c, row, x);      // Q and K tiles of this set are dead: S is complete
+                store_row_chunk(sP, 2 * half, row, x);       // Q and K tiles of this set are dead: S is complete
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    x[k] = ex2(fmaf(__uint_as_float(v1[k]), p.scale_log2e, mneg));
+                    sum += x[k];
+                }
+                store_row_chunk(sP, 2 * half + 1, row, x);
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(b_p);
-            p.lse[(size_t)tile * SEQ + row] = m * p.scale + __logf(sum);
+            *my_sum = sum;
+            row_threads_sync();
+            sum += *their_sum;                       // (a + b == b + a: both warps of the row hold the same total)
+            if (half == 0) p.lse[(size_t)tile * SEQ + row] = m * p.scale + __logf(sum);
             const float inv = 1.0f / sum;
             mbar_wait(b_o, ph);
             tc_fence_after();
-            float* orow = p.out + (size_t)(b * SEQ + row) * H + h * HD;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            float* orow = p.out + (size_t)(b * SEQ + row) * H + h * HD + half * 32;
+            {
                 uint32_t v[32];
-                tmem_ld32(v, t_row + 128 + c * 32);
+                tmem_ld32(v, t_row + 128 + half * 32);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<float4*>(orow + c * 32)[j] =
+                    reinterpret_cast<float4*>(orow)[j] =
                         make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
                                     __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
             }
@@ -295,17 +310,19 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
     uint64_t* b_ld2 = bars + 1;     // dO_mn, K_mn, Q_mn landed
     uint64_t* b_sdp = bars + 2;     // S and dP complete
     uint64_t* b_op1 = bars + 3;     // P^T and dS staged (128 arrivals)
-    uint64_t* b_dvdq = bars + 4;    // dV and dQ complete
+    uint64_t* b_dv = bars + 4;      // dV complete (P^T consumed: the row threads may overwrite it with dS^T)
+    uint64_t* b_dq = bars + 5;      // dQ complete
     uint64_t* b_op2 = bars + 6;     // dS^T staged (128 arrivals)
     uint64_t* b_dk = bars + 7;      // dK complete
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+    float* xch = (float*)(bars + 10);  // [2][128]: rowsum(dO o O) over the two column halves
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.heads * HD;
     const int tiles = p.batch * p.heads;
 
     if (warp == 0 && lane == 0) {
-        mbar_init(b_ld1, 1); mbar_init(b_ld2, 1); mbar_init(b_sdp, 1); mbar_init(b_op1, 128); mbar_init(b_dvdq, 1);
-        mbar_init(b_op2, 128); mbar_init(b_dk, 1);
+        mbar_init(b_ld1, 1); mbar_init(b_ld2, 1); mbar_init(b_sdp, 1); mbar_init(b_op1, ROW_THREADS); mbar_init(b_dv, 1); mbar_init(b_dq, 1);
+        mbar_init(b_op2, ROW_THREADS); mbar_init(b_dk, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
@@ -360,8 +377,9 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 mbar_wait(b_ld2, ph);
                 tc_fence_after();
                 mma_mn_b(tmem + 256, smem_u32(sX), smem_u32(sZ1));                             // dV = P^T dO
+                umma_commit(b_dv);
                 mma_mn_b(tmem + 320, smem_u32(sY), smem_u32(sZ2));                             // dQ = dS K
-                umma_commit(b_dvdq);
+                umma_commit(b_dq);
                 mbar_wait(b_op2, ph);
                 tc_fence_after();
                 mma_mn_b(tmem + 384, smem_u32(sX), smem_u32(sZ3));                             // dK = dS^T Q
@@ -374,6 +392,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
         }
     } else if (warp >= 2) {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;            // which half of the columns (the other warp of the quarter: the rest)
         const int row = 32 * q + lane;
         const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
         uint32_t it = 0;
@@ -384,53 +403,54 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
             // D = rowsum(dO o O) and the row's LSE, fetched while the loads and the first products are in flight
             float dsum = 0.f;
             {
-                const float4* po = reinterpret_cast<const float4*>(p.o + grow);
-                const float4* pg = reinterpret_cast<const float4*>(p.dout + grow);
+                const float4* po = reinterpret_cast<const float4*>(p.o + grow + half * 32);
+                const float4* pg = reinterpret_cast<const float4*>(p.dout + grow + half * 32);
 #pragma unroll
-                for (int j = 0; j < HD / 4; ++j) {
+                for (int j = 0; j < HD / 8; ++j) {
                     const float4 a = __ldg(po + j), g = __ldg(pg + j);
                     dsum += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
                 }
             }
             const float lneg = -p.lse[(size_t)tile * SEQ + row] * 1.4426950408889634f;
+            xch[half * SEQ + row] = dsum;
+            row_threads_sync();
+            dsum += xch[(half ^ 1) * SEQ + row];     // (a + b == b + a: both warps of the row hold the same D)
             mbar_wait(b_sdp, ph);
             tc_fence_after();
-            // pass A: P^T -> X (transposed), dS -> Y (row form)
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t s[32], g[32];
-                float pv[32], ds[32];
-                tmem_ld32(s, t_row + c * 32);
-                tmem_ld32(g, t_row + 128 + c * 32);
+            // pass A: P^T -> X (transposed), dS -> Y (row form); both chunks' TMEM loads in flight together.  dS stays in
+            // registers: its transpose goes to X once dV has consumed P^T (no second TMEM pass, no second exponential)
+            float ds0[32], ds1[32];
+            {
+                uint32_t s0[32], g0[32], s1[32], g1[32];
+                float pv[32];
+                tmem_ld32(s0, t_row + half * 64);
+                tmem_ld32(g0, t_row + 128 + half * 64);
+                tmem_ld32(s1, t_row + half * 64 + 32);
+                tmem_ld32(g1, t_row + 128 + half * 64 + 32);
                 tmem_wait_ld();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    pv[k] = ex2(fmaf(__uint_as_float(s[k]), p.scale_log2e, lneg));
-                    ds[k] = p.scale * pv[k] * (__uint_as_float(g[k]) - dsum);
+                    pv[k] = ex2(fmaf(__uint_as_float(s0[k]), p.scale_log2e, lneg));
+                    ds0[k] = p.scale * pv[k] * (__uint_as_float(g0[k]) - dsum);
                 }
-                store_col_chunk(sX, row, c * 32, pv);
-                store_row_chunk(sY, c, row, ds);
+                store_col_chunk(sX, row, half * 64, pv);
+                store_row_chunk(sY, 2 * half, row, ds0);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    pv[k] = ex2(fmaf(__uint_as_float(s1[k]), p.scale_log2e, lneg));
+                    ds1[k] = p.scale * pv[k] * (__uint_as_float(g1[k]) - dsum);
+                }
+                store_col_chunk(sX, row, half * 64 + 32, pv);
+                store_row_chunk(sY, 2 * half + 1, row, ds1);
             }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(b_op1);
-            mbar_wait(b_dvdq, ph);
+            mbar_wait(b_dv, ph);
             tc_fence_after();
-            // pass B: dS^T -> X (dV has consumed P^T)
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t s[32], g[32];
-                float ds[32];
-                tmem_ld32(s, t_row + c * 32);
-                tmem_ld32(g, t_row + 128 + c * 32);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float pk = ex2(fmaf(__uint_as_float(s[k]), p.scale_log2e, lneg));
-                    ds[k] = p.scale * pk * (__uint_as_float(g[k]) - dsum);
-                }
-                store_col_chunk(sX, row, c * 32, ds);
-            }
+            // pass B: dS^T -> X
+            store_col_chunk(sX, row, half * 64, ds0);
+            store_col_chunk(sX, row, half * 64 + 32, ds1);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(b_op2);
@@ -438,26 +458,30 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
             float* dq = p.dqkv + grow;
             float* dk = p.dqkv + (size_t)p.rows * H + grow;
             float* dv = p.dqkv + 2 * (size_t)p.rows * H + grow;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32], w[32];
+            // (the projections' bias gradients are the column sums of dQ / dK / dV: taken from the registers that hold the
+            //  rows, not by three kernels that read the matrices back)
+            {
+                const int c = half;
+                uint32_t v[32];
                 tmem_ld32(v, t_row + 256 + c * 32);
-                tmem_ld32(w, t_row + 320 + c * 32);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 8; ++j)
                     reinterpret_cast<uint4*>(dv + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    reinterpret_cast<uint4*>(dq + c * 32)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                }
-                // the projections' bias gradients are the column sums of dQ / dK / dV: taken from the registers that
-                // hold the rows, not by three kernels that read the matrices back
                 bias_grad_chunk(p.dbias[2], v, h * HD + c * 32, lane);
-                bias_grad_chunk(p.dbias[0], w, h * HD + c * 32, lane);
+                mbar_wait(b_dq, ph);
+                tc_fence_after();
+                tmem_ld32(v, t_row + 320 + c * 32);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<uint4*>(dq + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                bias_grad_chunk(p.dbias[0], v, h * HD + c * 32, lane);
             }
             mbar_wait(b_dk, ph);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            {
+                const int c = half;
                 uint32_t v[32];
                 tmem_ld32(v, t_row + 384 + c * 32);
                 tmem_wait_ld();
@@ -490,8 +514,8 @@ int make_map_2d(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, 
     return 0;
 }
 
-constexpr size_t FWD_SMEM = 6 * TILE_BYTES + 128 + 1024;
-constexpr size_t BWD_SMEM = 7 * TILE_BYTES + 128 + 1024;
+constexpr size_t FWD_SMEM = 6 * TILE_BYTES + 128 + 2048 + 1024;     // operands | barriers | row exchange | alignment
+constexpr size_t BWD_SMEM = 7 * TILE_BYTES + 128 + 1024 + 1024;
 
 int check_shape(const char* who, int dtype, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
     LG_REQUIRE(dtype == LG_F32 && seq == SEQ && head_dim == HD && batch >= 1 && heads >= 1 &&

@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, in
                                                      const T* __restrict__ gscale, T* __restrict__ dx, int64_t ld_dx,
                                                      int64_t rows, int64_t cols) {
     LG_PDL_TRIGGER();
-    const T gs = gscale[0];
-    const T inv_rows = T(rows);
+    // (p - onehot) / N * out_grad (loss.py:20-24) as one multiply by out_grad / N: the division by N moved out of the
+    // 125 M-element loop (the kernel was issue-bound on it: 214 us for 1 GB of traffic)
+    const T mul = gscale[0] / T(rows);
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const T* p = x + row * ld;
         T* q = dx + row * ld_dx;
@@ -197,21 +198,32 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, in
         int64_t nv = 0;
         if ((((uintptr_t)p | (uintptr_t)q) & 15) == 0) {
             nv = cols / V;
-            for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
-                Vec<T, V> w = reinterpret_cast<const Vec<T, V>*>(p)[j], o;
+            const int64_t lab_vec = lab / V;
+            const int lab_k = (int)(lab - lab_vec * V);
+            auto emit = [&](int64_t j, const Vec<T, V>& w) {
+                Vec<T, V> o;
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    T pr = f_exp(w.v[k] - l);
-                    if (j * V + k == lab) pr -= T(1);
-                    o.v[k] = pr / inv_rows * gs;
+                for (int k = 0; k < V; ++k) o.v[k] = f_exp(w.v[k] - l) * mul;
+                if (j == lab_vec) {
+#pragma unroll
+                    for (int k = 0; k < V; ++k)
+                        if (k == lab_k) o.v[k] = (f_exp(w.v[k] - l) - T(1)) * mul;
                 }
                 reinterpret_cast<Vec<T, V>*>(q)[j] = o;
+            };
+            int64_t j = threadIdx.x;
+            for (; j + blockDim.x < nv; j += 2 * blockDim.x) {      // two vectors per thread in flight
+                const Vec<T, V> w0 = reinterpret_cast<const Vec<T, V>*>(p)[j];
+                const Vec<T, V> w1 = reinterpret_cast<const Vec<T, V>*>(p)[j + blockDim.x];
+                emit(j, w0);
+                emit(j + blockDim.x, w1);
             }
+            for (; j < nv; j += blockDim.x) emit(j, reinterpret_cast<const Vec<T, V>*>(p)[j]);
         }
         for (int64_t j = nv * V + threadIdx.x; j < cols; j += blockDim.x) {
             T pr = f_exp(p[j] - l);
             if (j == lab) pr -= T(1);
-            q[j] = pr / inv_rows * gs;   // (p - onehot) / N * out_grad, as loss.py:20-24
+            q[j] = pr * mul;
         }
     }
 }
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ x, co
 // (gamma / beta are re-read through L1 for every row instead of living in 2 x NV x 4 registers: at 128 registers per
 //  thread only two CTAs fit on an SM -- ncu: 22 % of the warp slots active, 11.5 us for 50 MB -- with <= 80 it is three)
 template <int NV>
-__global__ void __launch_bounds__(256, (NV <= 6 ? 3 : 2)) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
+__global__ void __launch_bounds__(256, (NV <= 6 ? 4 : 2)) ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                          float* __restrict__ sum_out, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ y,
                                                          float* __restrict__ mean, float* __restrict__ rstd,
