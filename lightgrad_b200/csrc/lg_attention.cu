@@ -40,6 +40,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -138,6 +144,7 @@ struct AttnMaps {
     CUtensorMap qkv_mn;   // same memory, SWIZZLE_128B_ATOM_32B                                     (MN-major operand tiles)
     CUtensorMap do_k;     // (rows, H) gradient of the result, SWIZZLE_128B
     CUtensorMap do_mn;    // same, SWIZZLE_128B_ATOM_32B
+    CUtensorMap dqkv;     // backward result (3 * rows, H), box 32 x 128, SWIZZLE_128B: written by TMA from staged row tiles
 };
 
 // ======================================= forward =========================================================
@@ -314,20 +321,22 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
     uint64_t* b_dq = bars + 5;      // dQ complete
     uint64_t* b_op2 = bars + 6;     // dS^T staged (128 arrivals)
     uint64_t* b_dk = bars + 7;      // dK complete
+    uint64_t* b_out = bars + 8;     // the result tiles staged over dO / K / Q (MN-major) have left shared memory
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
-    float* xch = (float*)(bars + 10);  // [2][128]: rowsum(dO o O) over the two column halves
+    float* xch = (float*)(bars + 10);  // [128]: rowsum(dO o O)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.heads * HD;
     const int tiles = p.batch * p.heads;
 
     if (warp == 0 && lane == 0) {
         mbar_init(b_ld1, 1); mbar_init(b_ld2, 1); mbar_init(b_sdp, 1); mbar_init(b_op1, ROW_THREADS); mbar_init(b_dv, 1); mbar_init(b_dq, 1);
-        mbar_init(b_op2, ROW_THREADS); mbar_init(b_dk, 1);
+        mbar_init(b_op2, ROW_THREADS); mbar_init(b_dk, 1); mbar_init(b_out, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.do_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.do_mn));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.dqkv));
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
@@ -342,9 +351,9 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            // all seven operand tiles of a (batch, head) tile in one go; the next tile's loads are issued as soon as
-            // this tile's last product has consumed the shared memory, i.e. while the row threads still store results
-            auto load_tile = [&](int tile) {
+            // the K-major tiles (needed first) are requested as soon as this tile's last product has consumed the shared
+            // memory; the MN-major ones once the results staged over them have been written out
+            auto load_k = [&](int tile) {
                 const int b = tile / p.heads, h = tile - b * p.heads;
                 const int r0 = b * SEQ, c0 = h * HD;
                 mbar_expect_tx(b_ld1, 4 * TILE_BYTES);
@@ -356,6 +365,10 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 tma_load_2d(&maps.do_k, b_ld1, sY + KB_BYTES, c0 + 32, r0);
                 tma_load_2d(&maps.qkv_k, b_ld1, sY + TILE_BYTES, c0, 2 * p.rows + r0);         // V
                 tma_load_2d(&maps.qkv_k, b_ld1, sY + TILE_BYTES + KB_BYTES, c0 + 32, 2 * p.rows + r0);
+            };
+            auto load_mn = [&](int tile) {
+                const int b = tile / p.heads, h = tile - b * p.heads;
+                const int r0 = b * SEQ, c0 = h * HD;
                 mbar_expect_tx(b_ld2, 3 * TILE_BYTES);
                 tma_load_2d(&maps.do_mn, b_ld2, sZ1, c0, r0);                                  // dO, MN-major
                 tma_load_2d(&maps.do_mn, b_ld2, sZ1 + KB_BYTES, c0 + 32, r0);
@@ -364,6 +377,7 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 tma_load_2d(&maps.qkv_mn, b_ld2, sZ3, c0, r0);                                 // Q, MN-major
                 tma_load_2d(&maps.qkv_mn, b_ld2, sZ3 + KB_BYTES, c0 + 32, r0);
             };
+            auto load_tile = [&](int tile) { load_k(tile); load_mn(tile); };
             if ((int)blockIdx.x < tiles) load_tile(blockIdx.x);
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
@@ -386,7 +400,9 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 umma_commit(b_dk);
                 if (tile + (int)gridDim.x < tiles) {
                     mbar_wait(b_dk, ph);             // every operand of this tile has been consumed
-                    load_tile(tile + gridDim.x);
+                    load_k(tile + gridDim.x);
+                    mbar_wait(b_out, ph);            // dV / dQ / dK tiles have been read out of shared memory
+                    load_mn(tile + gridDim.x);
                 }
             }
         }
@@ -399,22 +415,25 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
             const int b = tile / p.heads, h = tile - b * p.heads;
-            const size_t grow = (size_t)(b * SEQ + row) * H + h * HD;
-            // D = rowsum(dO o O) and the row's LSE, fetched while the loads and the first products are in flight
-            float dsum = 0.f;
+            // D = rowsum(dO o O), fetched while the loads and the first products are in flight.  Coalesced: this warp takes
+            // 16 of its quarter's rows, two 256-byte rows per instruction (16 lanes each), and leaves the sums in shared
+            // memory for the threads that own the rows
             {
-                const float4* po = reinterpret_cast<const float4*>(p.o + grow + half * 32);
-                const float4* pg = reinterpret_cast<const float4*>(p.dout + grow + half * 32);
+                const int sub = lane >> 4, chunk = lane & 15;
+                const size_t g0 = (size_t)(b * SEQ + 32 * q + 16 * half + sub) * H + h * HD + 4 * chunk;
 #pragma unroll
-                for (int j = 0; j < HD / 8; ++j) {
-                    const float4 a = __ldg(po + j), g = __ldg(pg + j);
-                    dsum += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+                for (int i = 0; i < 8; ++i) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(p.o + g0 + (size_t)(2 * i) * H));
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.dout + g0 + (size_t)(2 * i) * H));
+                    float d = a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                    if (chunk == 0) xch[32 * q + 16 * half + 2 * i + sub] = d;
                 }
             }
             const float lneg = -p.lse[(size_t)tile * SEQ + row] * 1.4426950408889634f;
-            xch[half * SEQ + row] = dsum;
             row_threads_sync();
-            dsum += xch[(half ^ 1) * SEQ + row];     // (a + b == b + a: both warps of the row hold the same D)
+            const float dsum = xch[row];
             mbar_wait(b_sdp, ph);
             tc_fence_after();
             // pass A: P^T -> X (transposed), dS -> Y (row form); both chunks' TMEM loads in flight together.  dS stays in
@@ -454,45 +473,65 @@ attention_bwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(b_op2);
-            // dV (rows = keys) and dQ (rows = queries) while dK is being formed
-            float* dq = p.dqkv + grow;
-            float* dk = p.dqkv + (size_t)p.rows * H + grow;
-            float* dv = p.dqkv + 2 * (size_t)p.rows * H + grow;
+            // dV (rows = keys) and dQ (rows = queries) while dK is being formed.  The rows are staged in shared memory in
+            // the TMA box layout -- over dO / K / Q (MN-major), which dV / dQ / dK have consumed -- and written by TMA:
+            // a thread owns one 128-byte piece of a row, and 32 such pieces per store instruction, each in its own
+            // line, kept the load-store unit busy for longer than the rest of the tile took.
             // (the projections' bias gradients are the column sums of dQ / dK / dV: taken from the registers that hold the
             //  rows, not by three kernels that read the matrices back)
+            const int r0 = b * SEQ, c0 = h * HD;
             {
-                const int c = half;
                 uint32_t v[32];
-                tmem_ld32(v, t_row + 256 + c * 32);
+                float x[32];
+                tmem_ld32(v, t_row + 256 + half * 32);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<uint4*>(dv + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                bias_grad_chunk(p.dbias[2], v, h * HD + c * 32, lane);
+                for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
+                store_row_chunk(sZ1, half, row, x);
+                bias_grad_chunk(p.dbias[2], v, c0 + half * 32, lane);
                 mbar_wait(b_dq, ph);
                 tc_fence_after();
-                tmem_ld32(v, t_row + 320 + c * 32);
+                tmem_ld32(v, t_row + 320 + half * 32);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<uint4*>(dq + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                bias_grad_chunk(p.dbias[0], v, h * HD + c * 32, lane);
+                for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
+                store_row_chunk(sZ2, half, row, x);
+                bias_grad_chunk(p.dbias[0], v, c0 + half * 32, lane);
+            }
+            fence_async_smem();
+            row_threads_sync();
+            if (threadIdx.x == 64) {
+                tma_store_2d(&maps.dqkv, sZ1, c0, 2 * p.rows + r0);
+                tma_store_2d(&maps.dqkv, sZ1 + KB_BYTES, c0 + 32, 2 * p.rows + r0);
+                tma_store_2d(&maps.dqkv, sZ2, c0, r0);
+                tma_store_2d(&maps.dqkv, sZ2 + KB_BYTES, c0 + 32, r0);
+                tma_store_commit();
             }
             mbar_wait(b_dk, ph);
             tc_fence_after();
             {
-                const int c = half;
                 uint32_t v[32];
-                tmem_ld32(v, t_row + 384 + c * 32);
+                float x[32];
+                tmem_ld32(v, t_row + 384 + half * 32);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<uint4*>(dk + c * 32)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                bias_grad_chunk(p.dbias[1], v, h * HD + c * 32, lane);
+                for (int k = 0; k < 32; ++k) x[k] = __uint_as_float(v[k]);
+                store_row_chunk(sZ3, half, row, x);
+                bias_grad_chunk(p.dbias[1], v, c0 + half * 32, lane);
+            }
+            fence_async_smem();
+            row_threads_sync();
+            if (threadIdx.x == 64) {
+                tma_store_2d(&maps.dqkv, sZ3, c0, p.rows + r0);
+                tma_store_2d(&maps.dqkv, sZ3 + KB_BYTES, c0 + 32, p.rows + r0);
+                tma_store_commit();
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(b_out);
             }
             tc_fence_before();       // (the next tile's dV / dQ / dK products need this warp's next arrivals first)
         }
     }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -545,6 +584,7 @@ int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int
     if (make_map_2d(&maps.qkv_mn, qkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     maps.do_k = maps.qkv_k;
     maps.do_mn = maps.qkv_mn;
+    maps.dqkv = maps.qkv_k;
     AttnParams p = {};
     p.batch = (int)batch;
     p.heads = (int)heads;
@@ -579,6 +619,7 @@ int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* do
     if (make_map_2d(&maps.qkv_mn, qkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     if (make_map_2d(&maps.do_k, dout, H, rows, H, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (make_map_2d(&maps.do_mn, dout, H, rows, H, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    if (make_map_2d(&maps.dqkv, dqkv, H, 3 * rows, H, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     AttnParams p = {};
     p.batch = (int)batch;
     p.heads = (int)heads;

@@ -152,6 +152,11 @@ __device__ __forceinline__ void mc_wait(const unsigned int* local_flag, unsigned
     }
 }
 
+int stream_hint() {
+    static const int on = getenv("LG_MC_NO_STREAM_HINT") ? 0 : 1;
+    return on;
+}
+
 struct McArgs {
     const float* grad;         // LOCAL variant: this GPU's gradient arena (plain mapping)
     float* mc_grad;            // multicast mapping of the gradient arena
@@ -173,6 +178,17 @@ struct McArgs {
     unsigned long long* trace;  // LG_MC_TRACE: {entered, all ranks met, finished} of CTA 0 in globaltimer ns, or nullptr
 };
 
+// The optimizer operands are touched once per step.  Read and written with the streaming (evict-first) hint they do not
+// push the operand tiles of the GEMMs that run beside this kernel out of L2 (LG_MC_NO_STREAM_HINT=1: plain accesses,
+// for the A/B measurement).
+template <bool STREAM>
+__device__ __forceinline__ float4 ld_state(const float4* p) { return STREAM ? __ldcs(p) : *p; }
+template <bool STREAM>
+__device__ __forceinline__ void st_state(float4* p, const float4& v) {
+    if (STREAM) __stcs(p, v);
+    else *p = v;
+}
+
 // a time stamp on whatever stream it is launched on (LG_MC_TRACE: where the compute stream is while buckets run)
 __global__ void mc_mark_kernel(unsigned long long* slot) {
     LG_PDL_TRIGGER();
@@ -182,7 +198,7 @@ __global__ void mc_mark_kernel(unsigned long long* slot) {
 // LOCAL = true: the same small-footprint kernel for ONE GPU -- no switch, no flags: the gradients are read from the
 // local arena and the parameters written back to it.  What it keeps is the reason to exist: 128 threads, no shared
 // memory, <= 88 registers, so it runs beside the GEMMs of backward and the optimizer leaves the critical path.
-template <int KIND, bool LOCAL>
+template <int KIND, bool LOCAL, bool STREAM>
 __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a) {
     LG_PDL_TRIGGER();
     // ---- every rank's gradients of this bucket are final once its kernel runs (stream order on that rank):
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
         for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < v1) {
-                if (LOCAL) g[u] = __ldg(reinterpret_cast<const float4*>(a.grad) + base + i);
+                if (LOCAL) g[u] = ld_state<STREAM>(reinterpret_cast<const float4*>(a.grad) + base + i);
                 else g[u] = mc_ld_reduce(a.mc_grad + ((base + i) << 2));
             }
         }
@@ -230,17 +246,17 @@ __global__ void __launch_bounds__(MC_THREADS) mc_exchange_kernel(const McArgs a)
         for (int u = 0; u < U; ++u) {
             const int64_t i = i0 + u * stride;
             if (i >= v1) break;
-            float4 p = reinterpret_cast<const float4*>(a.param)[base + i];
+            float4 p = ld_state<STREAM>(reinterpret_cast<const float4*>(a.param) + base + i);
             float4 gi = g[u];
             gi.x *= a.inv_world; gi.y *= a.inv_world; gi.z *= a.inv_world; gi.w *= a.inv_world;
             if (KIND <= 1) {
-                float4 mm = reinterpret_cast<const float4*>(a.m)[base + i];
-                float4 vv = reinterpret_cast<const float4*>(a.v)[base + i];
+                float4 mm = ld_state<STREAM>(reinterpret_cast<const float4*>(a.m) + base + i);
+                float4 vv = ld_state<STREAM>(reinterpret_cast<const float4*>(a.v) + base + i);
                 seg = adam_segment(seg, (base + i) << 2, a.n_seg, a.seg_end);
                 adam_update4<KIND == 1>(p, gi, mm, vv, a.c1[seg], a.c2[seg], a.c1[2 * a.n_seg + seg],
                                         a.c2[2 * a.n_seg + seg], a.neg_lr, a.b1, a.b2, a.omb1, a.omb2, a.eps);
-                reinterpret_cast<float4*>(a.m)[base + i] = mm;
-                reinterpret_cast<float4*>(a.v)[base + i] = vv;
+                st_state<STREAM>(reinterpret_cast<float4*>(a.m) + base + i, mm);
+                st_state<STREAM>(reinterpret_cast<float4*>(a.v) + base + i, vv);
             } else if (KIND == 2) {
                 float4 d;
                 if (a.momentum != 0.f) {
@@ -492,12 +508,23 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
         adam_prep_kernel<<<1, 256, 0, st>>>(n_seg, t_dev, beta1, beta2, corr, corr + n_seg, seg_offset, t_advance);
         count_launch();
     }
-    switch (kind) {
-        case 0: mc_exchange_kernel<0, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
-        case 1: mc_exchange_kernel<1, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
-        case 2: mc_exchange_kernel<2, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
-        default: mc_exchange_kernel<3, false><<<rg.grid, MC_THREADS, 0, st>>>(a); break;
+#define MC_LAUNCH(K_, S_) mc_exchange_kernel<K_, false, S_><<<rg.grid, MC_THREADS, 0, st>>>(a)
+    if (stream_hint()) {
+        switch (kind) {
+            case 0: MC_LAUNCH(0, true); break;
+            case 1: MC_LAUNCH(1, true); break;
+            case 2: MC_LAUNCH(2, true); break;
+            default: MC_LAUNCH(3, true); break;
+        }
+    } else {
+        switch (kind) {
+            case 0: MC_LAUNCH(0, false); break;
+            case 1: MC_LAUNCH(1, false); break;
+            case 2: MC_LAUNCH(2, false); break;
+            default: MC_LAUNCH(3, false); break;
+        }
     }
+#undef MC_LAUNCH
     if (corr) {
         // the collective stream still reads it: hand it back once the compute stream has joined (lg_nccl_wait)
         comm_defer_free(corr);
@@ -553,11 +580,21 @@ int lg_bucket_step(int kind, void* param, const void* grad, void* m, void* v, in
     }
     static const int grid_env = getenv("LG_MC_CTAS") ? atoi(getenv("LG_MC_CTAS")) : 0;
     const int grid = grid_env > 0 ? (grid_env < MC_MAX_CTAS ? grid_env : MC_MAX_CTAS) : sm_count();
-    switch (kind) {
-        case 0: mc_exchange_kernel<0, true><<<grid, MC_THREADS, 0, st>>>(a); break;
-        case 1: mc_exchange_kernel<1, true><<<grid, MC_THREADS, 0, st>>>(a); break;
-        default: mc_exchange_kernel<2, true><<<grid, MC_THREADS, 0, st>>>(a); break;
+#define MC_LAUNCH(K_, S_) mc_exchange_kernel<K_, true, S_><<<grid, MC_THREADS, 0, st>>>(a)
+    if (stream_hint()) {
+        switch (kind) {
+            case 0: MC_LAUNCH(0, true); break;
+            case 1: MC_LAUNCH(1, true); break;
+            default: MC_LAUNCH(2, true); break;
+        }
+    } else {
+        switch (kind) {
+            case 0: MC_LAUNCH(0, false); break;
+            case 1: MC_LAUNCH(1, false); break;
+            default: MC_LAUNCH(2, false); break;
+        }
     }
+#undef MC_LAUNCH
     if (corr) comm_defer_free(corr);
     LG_CHECK_LAUNCH();
     return 0;
