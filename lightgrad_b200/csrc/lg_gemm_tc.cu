@@ -44,6 +44,7 @@ constexpr int KSTEPS = 4;             // UMMA k-steps (32 bytes of K each) per k
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, taking alternate 32-column chunks
 constexpr int NTHREADS = 32 * (2 + EPI_WARPS);
+constexpr int SCHED_SLOTS = 4;           // work items in flight between the producer thread and the other roles
 constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 32 fp32, per warp, double buffered
 
 // SMs the persistent GEMM grids may occupy (lg_gemm_sm_limit): a data-parallel step leaves a few SMs to the
@@ -75,6 +76,10 @@ struct TcParams {
     int tail_first, tail_splits, tail_kper;
     int kcat;                 // operand pairs concatenated along K into ONE result: C = sum_g A_g B_g (1-CTA kernel)
     const float* bias[LG_MAX_GROUPS];
+    // dynamic tile order (1-CTA kernel): sched[0] counts the work items claimed beyond the first one of every CTA,
+    // sched[1] the CTAs that have made their last claim (the last of them zeroes both for the next launch on this
+    // stream); nullptr: the static order w = cta, cta + grid, ...
+    unsigned int* sched;
 };
 
 // work item -> (tile, K-range); `wi` counts inside one problem of one batch
@@ -412,6 +417,12 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+    // work items reach the three roles through a small ring: the producer thread claims them (statically, or from a
+    // global counter so that CTAs which start late -- behind another stream's kernel -- or run beside one take less)
+    static_assert(CL == 1, "the work-item ring is per CTA");
+    uint64_t* sfull = bars + 2 * STAGES + 6;
+    uint64_t* sempty = sfull + SCHED_SLOTS;
+    volatile int* ring = (volatile int*)(sempty + SCHED_SLOTS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // p.tiles_m counts groups of CL vertically adjacent tiles; work items are distributed over clusters
@@ -430,6 +441,10 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], EPI_WARPS * 32);
+        }
+        for (int s = 0; s < SCHED_SLOTS; ++s) {
+            mbar_init(&sfull[s], 1);
+            mbar_init(&sempty[s], 1 + EPI_WARPS);        // the MMA thread and one lane of every epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < p.groups * p.kcat; ++g) {
@@ -457,7 +472,21 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int w = cluster_id; w < work_items; w += n_clusters) {
+            int sslot = 0;
+            uint32_t sphase = 0;
+            int w = cluster_id < work_items ? cluster_id : -1;
+            while (true) {
+                // publish the item (or the end mark) to the MMA thread and the epilogue warps
+                mbar_wait(&sempty[sslot], sphase ^ 1);
+                ring[sslot] = w;
+                mbar_arrive(&sfull[sslot]);
+                if (++sslot == SCHED_SLOTS) {
+                    sslot = 0;
+                    sphase ^= 1;
+                }
+                if (w < 0) break;
+                // claim the next one now: the atomic's round trip hides behind this item's loads
+                const int w_next = p.sched ? n_clusters + (int)atomicAdd(p.sched, 1u) : w + n_clusters;
                 const int grp = w / items_per_group, wg = w - grp * items_per_group;
                 const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
                 const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
@@ -516,6 +545,14 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                         phase ^= 1;
                     }
                 }
+                w = w_next < work_items ? w_next : -1;
+            }
+            if (p.sched) {
+                // this CTA has made its last claim; the last CTA to get here leaves the counters at zero
+                if (atomicAdd(p.sched + 1, 1u) == (unsigned)n_clusters - 1) {
+                    atomicExch(p.sched, 0u);
+                    atomicExch(p.sched + 1, 0u);
+                }
             }
         }
     } else if (warp == 1) {
@@ -526,7 +563,17 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int w = cluster_id; w < work_items; w += n_clusters) {
+            int sslot = 0;
+            uint32_t sphase = 0;
+            while (true) {
+                mbar_wait(&sfull[sslot], sphase);
+                const int w = ring[sslot];
+                mbar_arrive(&sempty[sslot]);
+                if (++sslot == SCHED_SLOTS) {
+                    sslot = 0;
+                    sphase ^= 1;
+                }
+                if (w < 0) break;
                 const TcItem item = decode_item(p, (w % items_per_group) % items_per_batch);
                 const int kb0 = item.kb0, kb1 = item.kb1;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -585,7 +632,18 @@ gemm_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         uint8_t* buf0 = epi_base + ew * EPI_BUF_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int w = cluster_id; w < work_items; w += n_clusters) {
+        int sslot = 0;
+        uint32_t sphase = 0;
+        while (true) {
+            mbar_wait(&sfull[sslot], sphase);
+            const int w = ring[sslot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sslot]);
+            if (++sslot == SCHED_SLOTS) {
+                sslot = 0;
+                sphase ^= 1;
+            }
+            if (w < 0) break;
             const int grp = w / items_per_group, wg = w - grp * items_per_group;
             const CUtensorMap* map_c = &maps.c[grp];
             const float* bias = p.bias[grp];
@@ -957,7 +1015,7 @@ constexpr int stages_for() {
 template <int BN>
 constexpr size_t smem_for() {
     return (size_t)stages_for<BN>() * (A_STAGE_BYTES + BN * 128) + EPI_WARPS * EPI_BUF_BYTES +
-           (2 * stages_for<BN>() + 4) * 8 + 16 + 1024;
+           (2 * stages_for<BN>() + 4) * 8 + 16 + SCHED_SLOTS * (8 + 8 + 4) + 1024;
 }
 
 inline bool pdl_enabled() {
@@ -1077,6 +1135,26 @@ bool mn_major(int64_t s_mn, int64_t s_k, int64_t extent_k, int q) { return s_mn 
 struct Plan {
     int bn, splits, tiles_m, tiles_n, kblocks, kper;
 };
+
+// Counters of the dynamic tile order, one pair per stream a GEMM can be launched on (compute, side, collective):
+// launches on one stream are ordered, so a pair is always back at zero when the next launch starts claiming.
+// Opt-in (LG_GEMM_DYNAMIC=1): measured on the BERT-base step, where weight-gradient GEMMs on the side stream run beside
+// the activation-gradient GEMMs, 8.122 / 8.124 ms against 8.132 / 8.144 ms with the static order -- inside the noise,
+// so the default stays the static order.
+unsigned int* sched_counters() {
+    static unsigned int* base = nullptr;
+    static const bool on = getenv("LG_GEMM_DYNAMIC") != nullptr;
+    if (!on) return nullptr;
+    if (!base) {
+        if (capturing()) return nullptr;          // (first GEMM ever inside a capture: static order for this graph)
+        unsigned int* q = nullptr;
+        if (cudaMalloc((void**)&q, 3 * 128) != cudaSuccess) return nullptr;
+        cudaMemset(q, 0, 3 * 128);
+        cudaDeviceSynchronize();
+        base = q;
+    }
+    return base + 32 * alt_stream_index();
+}
 
 Plan choose_plan(int64_t M, int64_t N, int64_t K, int64_t batches, bool allow_split, bool tail_ok, int es) {
     const int sms = gemm_sms();
@@ -1268,6 +1346,7 @@ int gemm_tc_grouped(int mode, const LgGemmDesc* d, int groups, const void* const
     p.aux_sb1 = d->sc_b1;
     p.epi_alpha = (float)alpha;
     p.colsum = nullptr;
+    p.sched = pair_mma ? nullptr : sched_counters();
     float* colsum_after = nullptr;
     if (epi_op == 2 && p.bias[0] != nullptr) {
         // LG_EPI_GELU_BWD has no bias to add: the pointer names where the column sums of the result are accumulated --

@@ -296,9 +296,10 @@ class DataParallel(object):
         parameters in reverse registration order, so buckets complete from the tail of the arena.
         The optimizer (compute stream) waits for the communication stream at the end."""
         if bucket_bytes is None:
-            # the multicast exchange pays ~20 us per bucket but leaves only the LAST bucket (the first layer's parameters
-            # and the word embeddings, whose gradients are final when backward ends) exposed: small buckets
-            bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '24' if self.exchange in ('nvls', 'local') else '64')) << 20
+            # measured at 8 GPUs (profiles/r2_bench_n8_nvls_b*.json): 24 / 48 / 96 MB buckets = 8.73 / 8.51 / 8.43 ms per
+            # step -- every bucket is two cross-GPU barriers and a kernel beside the GEMMs of backward, and only the LAST
+            # bucket (the word embeddings, final when backward ends) is exposed whatever the size
+            bucket_bytes = int(os.environ.get('LG_DP_BUCKET_MB', '96' if self.exchange in ('nvls', 'local') else '64')) << 20
         nvls_step = _step_buckets and self.exchange == 'nvls'
         local_step = _step_buckets and self.exchange == 'local'
         if (nvls_step or local_step) and os.environ.get('LG_DP_NO_OVERLAP'):
