@@ -57,8 +57,8 @@ SEQ = 128
 GEMM_FLOPS_PER_SAMPLE = 85.5e9   # fwd + both backward GEMMs, SURVEY.md 8(a)/BASELINE.md "work per unit"
 # ncu dram__bytes_read.sum + dram__bytes_write.sum over the matmul launches of one batch-32 step on 1 GPU, per mode
 NCU_GEMM_DRAM_BYTES_PER_STEP = {
-    'tf32': (13.02e9, 'profiles/r1_gemm_dram_bytes.csv: 222 matmul launches of one batch-32 step, 11.90 GB read + '
-                      '1.12 GB written (algorithmic operand + result bytes of those launches: ~16 GB; results still '
+    'tf32': (10.84e9, 'profiles/r2_gemm_dram_bytes.csv: the 150 matmul launches of one batch-32 step, 9.71 GB read + '
+                      '1.13 GB written (r1, before the fused attention kernels: 222 launches, 13.02 GB; results still '
                       'in L2 at kernel end are charged to later kernels)'),
 }
 
