@@ -158,7 +158,7 @@ def cases():
                     return (lambda i: rt.api.layernorm_fwd(rt.F32, X[i].ptr, w.ptr, b.ptr, Y[i].ptr, mean.ptr, rstd.ptr,
                                                            R, H, 1e-5)), 2.0 * R * H * 4
                 return (lambda i: rt.api.layernorm_bwd(rt.F32, X[i].ptr, w.ptr, mean.ptr, rstd.ptr, G[i].ptr, Y[i].ptr,
-                                                       wg.ptr, wg.ptr + 4 * H, R, H, 1)), 3.0 * R * H * 4
+                                                       wg.ptr, wg.ptr + 4 * H, R, H, 1, None)), 3.0 * R * H * 4
             return make
 
         def colsum(n):

@@ -734,9 +734,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
     LG_PDL_TRIGGER();
     using G = Geo<ES>;
-    const CUtensorMap& map_a = maps.a[0];
-    const CUtensorMap& map_b = maps.b[0];
-    const CUtensorMap& map_c = maps.c[0];
     constexpr int HB = BN / 2;                          // B rows staged per CTA
     constexpr int B_STAGE_BYTES = HB * 128;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -754,7 +751,10 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items_per_batch = p.items_per_batch;   // p.tiles_m counts 256-row tile pairs
-    const int work_items = items_per_batch * p.batches;
+    // grouped launch: `groups` problems of identical shape (own operand / result maps), enumerated group-major;
+    // kcat > 1: operand pairs concatenated along K into one result (both as in the independent-CTA kernel)
+    const int items_per_group = items_per_batch * p.batches;
+    const int work_items = items_per_group * p.groups;
     const int crank = (int)cluster_ctarank();
     const bool leader = crank == 0;
     const int cluster_id = (int)blockIdx.x / 2, n_clusters = (int)gridDim.x / 2;
@@ -769,9 +769,11 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
             mbar_init(&tempty[s], 2 * EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c));
+        for (int g = 0; g < p.groups * p.kcat; ++g) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[g]));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[g]));
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.c[g]));
+        }
     }
     __syncthreads();
     cluster_sync_all();
@@ -794,14 +796,19 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             for (int w = cluster_id; w < work_items; w += n_clusters) {
-                const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+                const int grp = w / items_per_group, wg = w - grp * items_per_group;
+                const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
                 const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
                 const TcItem item = decode_item(p, wi);
                 const int tile = item.tile;
                 const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM;
                 const int n0 = (tile / p.tiles_m) * BN + crank * HB;     // this CTA's half of the B tile
                 const int kb0 = item.kb0, kb1 = item.kb1;
-                for (int kb = kb0; kb < kb1; ++kb) {
+                const int kspan = kb1 - kb0;
+                for (int it = 0; it < kspan * p.kcat; ++it) {
+                    const int kc = it / kspan, kb = kb0 + (it - kc * kspan);
+                    const CUtensorMap* map_a = &maps.a[grp + kc];
+                    const CUtensorMap* map_b = &maps.b[grp + kc];
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
@@ -809,22 +816,22 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
                     if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
                     const int k0 = kb * G::BKE;
                     if (!A_MN) {
-                        tma_load_4d_2sm(&map_a, &full[stage], sa, k0, m0, bc1, bc0);
+                        tma_load_4d_2sm(map_a, &full[stage], sa, k0, m0, bc1, bc0);
                     } else if (p.a_chunked) {
-                        tma_load_5d_2sm(&map_a, &full[stage], sa, 0, k0, m0 >> G::CH_SHIFT, bc1, bc0);
+                        tma_load_5d_2sm(map_a, &full[stage], sa, 0, k0, m0 >> G::CH_SHIFT, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / G::CH; ++j)
-                            tma_load_4d_2sm(&map_a, &full[stage], sa + j * G::CHUNK_BYTES, m0 + G::CH * j, k0, bc1, bc0);
+                            tma_load_4d_2sm(map_a, &full[stage], sa + j * G::CHUNK_BYTES, m0 + G::CH * j, k0, bc1, bc0);
                     }
                     if (!B_MN) {
-                        tma_load_4d_2sm(&map_b, &full[stage], sb, k0, n0, bc1, bc0);
+                        tma_load_4d_2sm(map_b, &full[stage], sb, k0, n0, bc1, bc0);
                     } else if (p.b_chunked) {
-                        tma_load_5d_2sm(&map_b, &full[stage], sb, 0, k0, n0 >> G::CH_SHIFT, bc1, bc0);
+                        tma_load_5d_2sm(map_b, &full[stage], sb, 0, k0, n0 >> G::CH_SHIFT, bc1, bc0);
                     } else {
 #pragma unroll
                         for (int j = 0; j < HB / G::CH; ++j)
-                            tma_load_4d_2sm(&map_b, &full[stage], sb + j * G::CHUNK_BYTES, n0 + G::CH * j, k0, bc1, bc0);
+                            tma_load_4d_2sm(map_b, &full[stage], sb + j * G::CHUNK_BYTES, n0 + G::CH * j, k0, bc1, bc0);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -842,12 +849,12 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int w = cluster_id; w < work_items; w += n_clusters) {
-                const TcItem item = decode_item(p, w % items_per_batch);
-                const int kb0 = item.kb0, kb1 = item.kb1;
+                const TcItem item = decode_item(p, (w % items_per_group) % items_per_batch);
+                const int n_it = (item.kb1 - item.kb0) * p.kcat;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int it = 0; it < n_it; ++it) {
                     mbar_wait(&full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
@@ -858,7 +865,7 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
                                                  : umma_desc(sa + ks * 32, 16, 1024, 2);
                         const uint64_t db = B_MN ? umma_desc(sb + ks * G::KSTEP_MN_BYTES, G::CHUNK_BYTES, G::MN_SBO, G::MN_LAYOUT)
                                                  : umma_desc(sb + ks * 32, 16, 1024, 2);
-                        const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        const uint32_t accum = (it > 0 || ks > 0) ? 1u : 0u;
                         umma_issue<ES, 2>(d_tmem, da, db, idesc, accum);
                     }
                     asm volatile(
@@ -891,16 +898,17 @@ gemm_tc_2cta_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int w = cluster_id; w < work_items; w += n_clusters) {
-            const int bi = w / items_per_batch, wi = w - bi * items_per_batch;
+            const int grp = w / items_per_group, wg = w - grp * items_per_group;
+            const int bi = wg / items_per_batch, wi = wg - bi * items_per_batch;
             const int bc0 = bi / p.batch1, bc1 = bi - bc0 * p.batch1;
             const TcItem item = decode_item(p, wi);
             const int tile = item.tile, split = item.split;
             const int m0 = ((tile % p.tiles_m) * 2 + crank) * BM, n0 = (tile / p.tiles_m) * BN;
             EpiTile t;
-            t.map_c = &map_c;
+            t.map_c = &maps.c[grp];
             t.map_aux = &maps.aux;
             t.epi_op = p.epi_op;
-            t.bias = split == 0 ? p.bias[0] : nullptr;
+            t.bias = split == 0 ? p.bias[grp] : nullptr;
             t.row0 = m0 + 32 * q;
             t.aux = (p.epi_op == 2 && t.row0 + lane < p.M) ? p.aux + (long long)(t.row0 + lane) * p.aux_ld : nullptr;
             t.n0 = n0;
@@ -1300,13 +1308,18 @@ int gemm_tc_grouped(int mode, const LgGemmDesc* d, int groups, const void* const
     int rc;
     const BatchDims ba{d->batch1, d->sa_b1, d->batch0, d->sa_b0}, bb{d->batch1, d->sb_b1, d->batch0, d->sb_b0},
         bc{d->batch1, d->sc_b1, d->batch0, d->sc_b0};
-    // CTA pairs (cta_group::2) take 256-row tiles and split the B tile between the two SMs; needs >= 2 tile rows
-    // (measured: +5..8 % on >= 2-wave problems such as 4096^3 or the 30522-wide decoder, but slower than
-    //  independent CTAs on the one-wave BERT projections, which therefore keep cta_group::1)
+    // CTA pairs (cta_group::2) take 256-row tiles and split the B tile between the two SMs; needs >= 2 tile rows.
+    // Every SM then stages 16 KB of A + BN/2 rows of B per k-block instead of 16 KB + BN rows: at 4-byte operands the
+    // independent-CTA kernel asks L2 for 125-140 GB/s per SM at full tensor rate, the pair kernel for 85-100.
+    // r2, final kernels, every shape of the BERT step inside a graph (profiles/r2_gemm_in_graph{,_pairs}.jsonl): pairs are
+    // never slower and 3-10 % faster on the N = 768 / K = 3072 shapes (40.9 -> 37.1 us), the weight gradients
+    // (35.1 -> 31.9) and the decoder's dX (339 -> 305) -- so pairs are the default wherever the launch allows them
+    // (LG_GEMM_PAIR=0: independent CTAs; r1 used pairs only on >= 2-wave problems).
     static const int force_pair = getenv("LG_GEMM_PAIR") ? atoi(getenv("LG_GEMM_PAIR")) : -1;
-    const bool big = (int64_t)pl.tiles_m * pl.tiles_n * pl.splits >= 2 * (int64_t)gemm_sms();
-    const bool pair_mma = groups == 1 && batches == 1 && epi_op < 3 && pl.tiles_m >= 2 &&
-                          (force_pair < 0 ? big : force_pair == 1);
+    // (an MN-major B tile is staged in chunks of 128 bytes of N: each CTA's half, BN / 2 columns, must be whole chunks --
+    //  bf16 with BN = 192 or 64 is not, and keeps independent CTAs)
+    const bool halves_ok = !b_mn || ((pl.bn / 2) % (128 / es) == 0);
+    const bool pair_mma = batches == 1 && epi_op < 3 && pl.tiles_m >= 2 && halves_ok && force_pair != 0;
     const int cl = pair_mma ? 2 : 1;
     TcMaps maps;
     TcParams p;
