@@ -148,48 +148,72 @@ struct AttnMaps {
 };
 
 // ======================================= forward =========================================================
-// One persistent CTA per SM, two operand sets: while the tile in one set is being computed, TMA fills the other with
-// the next tile's Q, K, V (a (batch, head) tile is 96 KB of operands for ~3 us of dependent work: without the prefetch
-// every CTA would first wait for its share of HBM bandwidth and then compute with the memory system idle).
+// One persistent CTA per SM with TWO tiles in flight: the eight row warps form two groups of four, group g owns the
+// CTA's tiles 2n + g together with operand set g (Q | K | V, 96 KB) and its own S / O columns of tensor memory.  For one
+// tile the work is a serial chain -- loads, S = Q K^T, softmax, O = P V, store: ~5.5 us, most of it latencies of barrier
+// hand-offs, the tensor pipe and the loads (ncu: the row warps spent two thirds of their samples waiting for S or O) --
+// so while one group computes its softmax the other tile's products and loads run.  A set can only be refilled when its
+// P V product has finished (P lives over Q | K), hence no deeper pipeline at 4-byte operands.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnParams p) {
     LG_PDL_TRIGGER();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    // set s at smem + s * 96 KB: Q (32 KB; with K: the 64 KB probability operand once S is complete) | K | V (MN-major)
+    // set g at smem + g * 96 KB: Q (32 KB; with K: the 64 KB probability operand once S is complete) | K | V (MN-major)
     uint64_t* bars = (uint64_t*)(smem + 6 * TILE_BYTES);
     uint64_t* b_qk = bars;        // [2] Q, K of a set landed
     uint64_t* b_v = bars + 2;     // [2] V of a set landed
-    uint64_t* b_s = bars + 4;     // S = Q K^T complete
-    uint64_t* b_p = bars + 5;     // probabilities staged (128 arrivals)
-    uint64_t* b_o = bars + 6;     // O = P V complete
-    uint32_t* tmem_slot = (uint32_t*)(bars + 7);
-    float* xch = (float*)(bars + 8);   // [2][2][128]: row maxima and row sums of the two column halves
+    uint64_t* b_s = bars + 4;     // [2] S = Q K^T complete
+    uint64_t* b_p = bars + 6;     // [2] probabilities staged (128 arrivals)
+    uint64_t* b_o = bars + 8;     // [2] O = P V complete: the set may be refilled
+    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.heads * HD;
     const int tiles = p.batch * p.heads;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; the i-th of them belongs to group / set i & 1
+    const int my_tiles = (int)blockIdx.x < tiles ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(b_qk + i, 1); mbar_init(b_v + i, 1); }
-        mbar_init(b_s, 1); mbar_init(b_p, ROW_THREADS); mbar_init(b_o, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(b_qk + i, 1); mbar_init(b_v + i, 1); mbar_init(b_s + i, 1); mbar_init(b_p + i, 128);
+            mbar_init(b_o + i, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_k));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.qkv_mn));
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;          // S: columns 0..127, O: columns 128..191
+    const uint32_t tmem = *tmem_slot;          // group g: S at columns 256 g .. +127, O at 256 g + 128 .. +63
     LG_PDL_WAIT();
 
     if (warp == 0) {
+        // ---- TMA producer: tile i goes to set i & 1 as soon as that set's previous P V product is done
         if (lane == 0) {
-            auto load_tile = [&](int tile, int set) {
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+                const int set = i & 1, n = i >> 1;
+                if (n > 0) mbar_wait(b_o + set, (uint32_t)(n - 1) & 1);
                 const int b = tile / p.heads, h = tile - b * p.heads;
                 const int r0 = b * SEQ, c0 = h * HD;
                 uint8_t* sQ = smem + set * 3 * TILE_BYTES;
@@ -203,101 +227,111 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const __grid_constan
                 mbar_expect_tx(b_v + set, TILE_BYTES);
                 tma_load_2d(&maps.qkv_mn, b_v + set, sV, c0, 2 * p.rows + r0);
                 tma_load_2d(&maps.qkv_mn, b_v + set, sV + KB_BYTES, c0 + 32, 2 * p.rows + r0);
-            };
-            if ((int)blockIdx.x < tiles) load_tile(blockIdx.x, 0);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-                const int set = it & 1;
-                const uint32_t ph = it & 1, ph_set = (it >> 1) & 1;
-                uint8_t* sQ = smem + set * 3 * TILE_BYTES;
-                mbar_wait(b_qk + set, ph_set);
-                tc_fence_after();
-                mma_kmajor<SEQ, 2>(tmem, smem_u32(sQ), smem_u32(sQ + TILE_BYTES));
-                umma_commit(b_s);
-                // the other set was last read by the P V product of the previous tile
-                if (it > 0) mbar_wait(b_o, ph ^ 1);
-                if (tile + (int)gridDim.x < tiles) load_tile(tile + gridDim.x, set ^ 1);
-                mbar_wait(b_p, ph);
-                mbar_wait(b_v + set, ph_set);
-                tc_fence_after();
-                mma_mn_b(tmem + 128, smem_u32(sQ), smem_u32(sQ + 2 * TILE_BYTES));
-                umma_commit(b_o);
             }
         }
-    } else if (warp >= 2) {
+    } else if (warp == 1) {
+        // ---- tensor-core issue: whichever of {S of the next tile, P V of the oldest open tile} has its operands first
+        if (lane == 0) {
+            int s_next = 0, pv_next = 0;
+            while (pv_next < my_tiles) {
+                bool progressed = false;
+                // S(i) overwrites the S columns of tile i - 2: its softmax has read them once P(i - 2) was staged, i.e.
+                // once P V (i - 2) has been issued
+                if (s_next < my_tiles && s_next - pv_next < 2) {
+                    const int set = s_next & 1;
+                    if (mbar_test(b_qk + set, (uint32_t)(s_next >> 1) & 1)) {
+                        tc_fence_after();
+                        uint8_t* sQ = smem + set * 3 * TILE_BYTES;
+                        mma_kmajor<SEQ, 2>(tmem + 256 * set, smem_u32(sQ), smem_u32(sQ + TILE_BYTES));
+                        umma_commit(b_s + set);
+                        ++s_next;
+                        progressed = true;
+                    }
+                }
+                if (pv_next < s_next) {
+                    const int set = pv_next & 1;
+                    const uint32_t ph = (uint32_t)(pv_next >> 1) & 1;
+                    if (mbar_test(b_p + set, ph) && mbar_test(b_v + set, ph)) {
+                        tc_fence_after();
+                        uint8_t* sQ = smem + set * 3 * TILE_BYTES;
+                        mma_mn_b(tmem + 256 * set + 128, smem_u32(sQ), smem_u32(sQ + 2 * TILE_BYTES));
+                        umma_commit(b_o + set);
+                        ++pv_next;
+                        progressed = true;
+                    }
+                }
+                if (!progressed) __nanosleep(32);
+            }
+        }
+    } else {
+        // ---- row warps: group g = tiles g, g + 2, ... of this CTA; a thread owns one row of the tile
         const int q = warp & 3;                      // TMEM lane quarter of this warp
-        const int half = (warp - 2) >> 2;            // which half of the columns (the other warp of the quarter: the rest)
+        const int g = (warp - 2) >> 2;
         const int row = 32 * q + lane;
-        const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
-        float* my_max = xch + half * SEQ + row;
-        float* my_sum = xch + 2 * SEQ + half * SEQ + row;
-        const float* their_max = xch + (half ^ 1) * SEQ + row;
-        const float* their_sum = xch + 2 * SEQ + (half ^ 1) * SEQ + row;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-            const uint32_t ph = it & 1;
+        const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16) + 256 * g;
+        uint8_t* sP = smem + g * 3 * TILE_BYTES;
+        for (int i = g; i < my_tiles; i += 2) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1;
             const int b = tile / p.heads, h = tile - b * p.heads;
-            uint8_t* sP = smem + (it & 1) * 3 * TILE_BYTES;
-            mbar_wait(b_s, ph);
+            mbar_wait(b_s + g, ph);
             tc_fence_after();
-            // this warp's 64 columns of the row stay in registers between the maximum and the exponentials
-            uint32_t v0[32], v1[32];
-            tmem_ld32(v0, t_row + half * 64);
-            tmem_ld32(v1, t_row + half * 64 + 32);
+            // the whole row of S stays in registers between the maximum and the exponentials
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            tmem_ld32(v0, t_row);
+            tmem_ld32(v1, t_row + 32);
+            tmem_ld32(v2, t_row + 64);
+            tmem_ld32(v3, t_row + 96);
             tmem_wait_ld();
             float m = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) m = fmaxf(m, fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])));
-            *my_max = m;
-            row_threads_sync();
-            m = fmaxf(m, *their_max);
+            for (int k = 0; k < 32; ++k)
+                m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v0[k]), __uint_as_float(v1[k])),
+                                   fmaxf(__uint_as_float(v2[k]), __uint_as_float(v3[k]))));
             // exp(alpha (s - max)) as ex2 of a single fma; the unnormalised values are the A operand of P V
             const float mneg = -m * p.scale_log2e;
             float sum = 0.f;
             {
                 float x[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    x[k] = ex2(fmaf(__uint_as_float(v0[k]), p.scale_log2e, mneg));
-                    sum += x[k];
-                }
-                store_row_chunk(sP, 2 * half, row, x);       // Q and K tiles of this set are dead: S is complete
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    x[k] = ex2(fmaf(__uint_as_float(v1[k]), p.scale_log2e, mneg));
-                    sum += x[k];
-                }
-                store_row_chunk(sP, 2 * half + 1, row, x);
+#define LG_ATT_EXP_CHUNK(V_, C_)                                                       \
+    _Pragma("unroll") for (int k = 0; k < 32; ++k) {                                    \
+        x[k] = ex2(fmaf(__uint_as_float(V_[k]), p.scale_log2e, mneg));                 \
+        sum += x[k];                                                                   \
+    }                                                                                  \
+    store_row_chunk(sP, C_, row, x);      /* Q and K tiles of this set are dead: S is complete */
+                LG_ATT_EXP_CHUNK(v0, 0)
+                LG_ATT_EXP_CHUNK(v1, 1)
+                LG_ATT_EXP_CHUNK(v2, 2)
+                LG_ATT_EXP_CHUNK(v3, 3)
+#undef LG_ATT_EXP_CHUNK
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(b_p);
-            *my_sum = sum;
-            row_threads_sync();
-            sum += *their_sum;                       // (a + b == b + a: both warps of the row hold the same total)
-            if (half == 0) p.lse[(size_t)tile * SEQ + row] = m * p.scale + __logf(sum);
+            mbar_arrive(b_p + g);
+            p.lse[(size_t)tile * SEQ + row] = m * p.scale + __logf(sum);
             const float inv = 1.0f / sum;
-            mbar_wait(b_o, ph);
+            mbar_wait(b_o + g, ph);
             tc_fence_after();
-            float* orow = p.out + (size_t)(b * SEQ + row) * H + h * HD + half * 32;
-            {
+            float* orow = p.out + (size_t)(b * SEQ + row) * H + h * HD;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(v, t_row + 128 + half * 32);
+                tmem_ld32(v, t_row + 128 + c * 32);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<float4*>(orow)[j] =
+                    reinterpret_cast<float4*>(orow + c * 32)[j] =
                         make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
                                     __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
             }
-            tc_fence_before();       // the next tile's P V product overwrites these columns only after this warp's next b_p
+            tc_fence_before();       // this group's next P V product overwrites these columns only after its next b_p
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
     }
 }
 

@@ -508,7 +508,10 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
         adam_prep_kernel<<<1, 256, 0, st>>>(n_seg, t_dev, beta1, beta2, corr, corr + n_seg, seg_offset, t_advance);
         count_launch();
     }
-#define MC_LAUNCH(K_, S_) mc_exchange_kernel<K_, false, S_><<<rg.grid, MC_THREADS, 0, st>>>(a)
+    // (tried: 2 or 4 CTAs per SM for the bucket that closes the step -- the word embeddings, fully exposed -- 8.22-8.24 /
+    //  8.28 ms per step at 2 GPUs against 8.20-8.24 with one: its 218 us are the NVLink transfer, not latency)
+    const int grid = rg.grid;
+#define MC_LAUNCH(K_, S_) mc_exchange_kernel<K_, false, S_><<<grid, MC_THREADS, 0, st>>>(a)
     if (stream_hint()) {
         switch (kind) {
             case 0: MC_LAUNCH(0, true); break;
