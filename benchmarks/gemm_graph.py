@@ -216,7 +216,30 @@ def cases():
                 return (lambda i: opt.step()), 7.0 * n * 4
             return make
 
-        return [('layernorm fwd 4096x768', ln(False)), ('layernorm bwd 4096x768 (+partials reduce)', ln(True)),
+        def attention(bwd):
+            def make(sets):
+                B, S, NH, DH = 32, 128, 12, 64
+                QKV = [rand(3, R, H) for _ in range(sets)]
+                O = [CudaTensor.empty((R, H)) for _ in range(sets)]
+                DO = [rand(R, H) for _ in range(sets)]
+                DQKV = [CudaTensor.empty((3, R, H)) for _ in range(sets)]
+                lse = CudaTensor.empty((B * NH * S,))
+                db = CudaTensor.zeros((3, H))
+                scale = 1.0 / 8.0
+                for i in range(sets):
+                    rt.api.attention_fwd(rt.F32, QKV[i].ptr, B, S, NH, DH, scale, O[i].ptr, lse.ptr)
+                if not bwd:
+                    # algorithmic bytes: Q, K, V read + O written
+                    return (lambda i: rt.api.attention_fwd(rt.F32, QKV[i].ptr, B, S, NH, DH, scale, O[i].ptr,
+                                                           lse.ptr)), 4.0 * R * H * 4
+                # Q, K, V, O, dO read + dQ, dK, dV written
+                return (lambda i: rt.api.attention_bwd(rt.F32, QKV[i].ptr, O[i].ptr, DO[i].ptr, lse.ptr, B, S, NH, DH,
+                                                       scale, DQKV[i].ptr, db.ptr, db.ptr + 4 * H,
+                                                       db.ptr + 8 * H)), 8.0 * R * H * 4
+            return make
+
+        return [('attention fwd 32x12x128x64', attention(False)), ('attention bwd 32x12x128x64', attention(True)),
+                ('layernorm fwd 4096x768', ln(False)), ('layernorm bwd 4096x768 (+partials reduce)', ln(True)),
                 ('bias grad colsum 4096x768', colsum(H)), ('bias grad colsum 4096x3072', colsum(F)),
                 ('add 4096x768', ew('ADD', 2, H)), ('gelu 4096x3072', ew('GELU', 1, F)),
                 ('gelu_bwd 4096x3072', ew('GELU_BWD', 2, F)),
