@@ -327,11 +327,17 @@ class DataParallel(object):
             # a parameter's slot runs to the next parameter's (64-element aligned) offset: the zero padding travels along
             ends = list(a.offsets[1:]) + [a.total]
             self._bucket_of, self._buckets = [], []      # per param -> bucket; bucket -> [lo, hi, n_params]
+            # Backward finishes the arena from its END, so the buckets at its START are launched last and run exposed.
+            # LG_DP_RAMP_BUCKETS=n closes the first n of them at a quarter of the size (the word embeddings alone, then
+            # one encoder layer each).  Measured at 8 GPUs: 8.42 / 8.46 ms with n = 3 against 8.44 with equal buckets --
+            # no difference, so the default keeps equal buckets.
+            ramp = int(os.environ.get('LG_DP_RAMP_BUCKETS', '0')) if (nvls_step or local_step) else 0
             lo, count = 0, 0
             for i, hi in enumerate(ends):
                 self._bucket_of.append(len(self._buckets))
                 count += 1
-                if (hi - lo) * 4 >= bucket_bytes or i == len(ends) - 1:
+                limit = bucket_bytes // 4 if len(self._buckets) < ramp else bucket_bytes
+                if (hi - lo) * 4 >= limit or i == len(ends) - 1:
                     self._buckets.append([lo, hi, count])
                     lo, count = hi, 0
             self._index = {id(p): i for i, p in enumerate(params)}
