@@ -108,6 +108,7 @@ class Gradients(object):
         keep = Gradients.retain_intermediate if retain is None else retain
         hook = Gradients.leaf_hook if Gradients._walking == 0 else None
         pending = None
+        wrappers_left, deferred = 0, []
         if hook is not None:
             # number of graph nodes that still owe each leaf a contribution
             pending = {}
@@ -115,6 +116,10 @@ class Gradients(object):
                 for t in node.parent_tensors:
                     if t.ctx is None:
                         pending[id(t)] = pending.get(id(t), 0) + 1
+                # a WrapperFunction back-propagates through a private graph, which may reach leaves (parameters used by
+                # closure) that this count cannot see: no leaf is reported as finished while such a node is outstanding
+                if getattr(node, '_inner', None) is not None:
+                    wrappers_left += 1
         Gradients._depth += 1
         Gradients._walking += 1
         try:
@@ -132,13 +137,22 @@ class Gradients(object):
                     g._temp = True
                 node._backpropagate(g)
                 if pending is not None:
+                    if getattr(node, '_inner', None) is not None:
+                        wrappers_left -= 1
                     for t in node.parent_tensors:
                         k = id(t)
                         if k in pending:
                             pending[k] -= 1
                             if pending[k] == 0:
                                 del pending[k]
-                                hook(t)
+                                deferred.append(t)
+                    if wrappers_left <= 0 and deferred:
+                        for t in deferred:
+                            hook(t)
+                        deferred = []
+            if pending is not None:
+                for t in deferred:      # (a wrapper node that received no gradient was skipped above)
+                    hook(t)
         finally:
             Gradients._walking -= 1
             d = Gradients._depth - 1
