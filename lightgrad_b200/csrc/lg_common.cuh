@@ -17,6 +17,7 @@ namespace lg {
 
 // ---- error plumbing ---------------------------------------------------------------------------
 int set_error(const char* fmt, ...);
+void prefer_gemm_carveout(const void* kernel);   // this kernel runs beside GEMM CTAs: ask for their shared-memory split
 cudaStream_t stream();        // stream kernels launch on: the compute stream, or the side stream inside lg_side_begin/end
 bool on_side_stream();      // launching on the side stream or (lg_comm_compute_begin) on the collective stream
 int alt_stream_index();     // 0 compute, 1 side, 2 collective stream

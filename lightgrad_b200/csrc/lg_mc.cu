@@ -511,7 +511,11 @@ int lg_mc_exchange_step(int kind, size_t grad_offset, size_t param_offset, size_
     // (tried: 2 or 4 CTAs per SM for the bucket that closes the step -- the word embeddings, fully exposed -- 8.22-8.24 /
     //  8.28 ms per step at 2 GPUs against 8.20-8.24 with one: its 218 us are the NVLink transfer, not latency)
     const int grid = rg.grid;
-#define MC_LAUNCH(K_, S_) mc_exchange_kernel<K_, false, S_><<<grid, MC_THREADS, 0, st>>>(a)
+#define MC_LAUNCH(K_, S_)                                                                   \
+    do {                                                                                    \
+        prefer_gemm_carveout((const void*)mc_exchange_kernel<K_, false, S_>);               \
+        mc_exchange_kernel<K_, false, S_><<<grid, MC_THREADS, 0, st>>>(a);                  \
+    } while (0)
     if (stream_hint()) {
         switch (kind) {
             case 0: MC_LAUNCH(0, true); break;
@@ -583,7 +587,11 @@ int lg_bucket_step(int kind, void* param, const void* grad, void* m, void* v, in
     }
     static const int grid_env = getenv("LG_MC_CTAS") ? atoi(getenv("LG_MC_CTAS")) : 0;
     const int grid = grid_env > 0 ? (grid_env < MC_MAX_CTAS ? grid_env : MC_MAX_CTAS) : sm_count();
-#define MC_LAUNCH(K_, S_) mc_exchange_kernel<K_, true, S_><<<grid, MC_THREADS, 0, st>>>(a)
+#define MC_LAUNCH(K_, S_)                                                                   \
+    do {                                                                                    \
+        prefer_gemm_carveout((const void*)mc_exchange_kernel<K_, true, S_>);                \
+        mc_exchange_kernel<K_, true, S_><<<grid, MC_THREADS, 0, st>>>(a);                   \
+    } while (0)
     if (stream_hint()) {
         switch (kind) {
             case 0: MC_LAUNCH(0, true); break;

@@ -333,14 +333,14 @@ int reduce_impl(const T* x, T* out, int64_t outer, int64_t rlen, int64_t inner, 
     unsigned int* tickets = (S > 1 && ntiles * outer <= kTicketSlots) ? ticket_buffer() : nullptr;
     if (tickets) {
         // single launch: partials + last-CTA final pass
-        if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, scale, acc_out, out, tickets);
-        else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, scale, acc_out, out, tickets);
+        if (vec) { prefer_gemm_carveout((const void*)red_cols<R, T, VMAX>); red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, scale, acc_out, out, tickets); }
+        else { prefer_gemm_carveout((const void*)red_cols<R, T, 1>); red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, scale, acc_out, out, tickets); }
         LG_CHECK_LAUNCH();
         tmp_free(partial);
         return 0;
     }
-    if (vec) red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out, (T*)nullptr, nullptr);
-    else red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out, (T*)nullptr, nullptr);
+    if (vec) { prefer_gemm_carveout((const void*)red_cols<R, T, VMAX>); red_cols<R, T, VMAX><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out, (T*)nullptr, nullptr); }
+    else { prefer_gemm_carveout((const void*)red_cols<R, T, 1>); red_cols<R, T, 1><<<grid, 256, 0, stream()>>>(x, dst, rlen, inner, ld, chunk, (int)S, ntiles, sc, S > 1 ? 0 : acc_out, (T*)nullptr, nullptr); }
     LG_CHECK_LAUNCH();
     if (S > 1) {
         int rc = reduce_impl<R, T>(partial, out, outer, S, inner, scale, 0, acc_out);
@@ -402,6 +402,7 @@ bool colsum_acc_small(const float* x, float* out, int64_t rows, int64_t cols, in
     const int64_t rows_per = (rows + slices - 1) / slices;
     slices = (rows + rows_per - 1) / rows_per;
     const int64_t total = slices * nvec;
+    prefer_gemm_carveout((const void*)colsum_acc_small_kernel);     // runs on the side stream beside GEMM CTAs
     colsum_acc_small_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream()>>>(x, out, rows, nvec, ld, rows_per, scale);
     return true;
 }

@@ -2,6 +2,7 @@
 // Replaces what the reference's OpenCL backend gets from pyopencl: one context + one in-order
 // queue + a MemoryPool per device (opencl/device.py:51-115) and blocking enqueue_copy
 // (opencl/tensor.py:74-93).  Here copies and kernels are stream-ordered and only D2H blocks.
+#include <unordered_set>
 #include "lg_common.cuh"
 #include <mutex>
 #include <unordered_map>
@@ -40,6 +41,14 @@ int set_error(const char* fmt, ...) {
     return 1;
 }
 cudaStream_t stream() { return g_cur; }
+void prefer_gemm_carveout(const void* kernel) {
+    // opt-in (LG_GEMM_CARVEOUT=1): measured without effect, see do_init
+    static const bool on = getenv("LG_GEMM_CARVEOUT") != nullptr;
+    static std::unordered_set<const void*> done;
+    if (!on || done.count(kernel)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    done.insert(kernel);
+}
 unsigned int* error_flag() { return g_errflag_dev; }
 // after a synchronisation: report (once) what a kernel flagged since the last check
 static int check_device_error() {
@@ -201,6 +210,17 @@ static int do_init(int device) {
         return set_error("lightgrad_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
                          prop.minor);
     g_sms = prop.multiProcessorCount;
+    {
+        // Hypothesis tested in r2: the GEMM / attention CTAs need the largest shared-memory carve-out, a kernel without
+        // shared memory prefers the largest L1, and an SM can only change its split when it is empty -- so a small kernel
+        // of another stream (column sums on the side stream, the exchange kernel) might keep the next GEMM's CTAs off its
+        // SMs.  Measured (profiles/r2_bench_carveout_*.json): preferring shared memory DEVICE-WIDE (LG_PREFER_SHARED=1)
+        // costs the L1-reliant kernels 0.2-0.3 ms per step (8.28 vs 8.02 ms on one GPU; at 2 GPUs 8.58-8.62 vs 8.49-8.51);
+        // asking for the GEMM's carve-out only on the kernels that run beside GEMMs (LG_GEMM_CARVEOUT=1:
+        // prefer_gemm_carveout) changes nothing (7.96 vs 7.99 ms; 2 GPUs 8.50-8.57 vs 8.48-8.50).  Both stay off.
+        static const bool all = getenv("LG_PREFER_SHARED") != nullptr;
+        if (all) LG_CUDA(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
+    }
     LG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     {
         // the collective stream gets the highest priority: its few small CTAs (NCCL, or the multicast exchange kernel)
