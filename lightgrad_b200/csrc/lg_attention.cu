@@ -634,7 +634,7 @@ int lg_attention_fwd(int dtype, const void* qkv, int64_t batch, int64_t seq, int
     }
     const int tiles = (int)(batch * heads);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    attention_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, stream()>>>(maps, p);
+    LG_CUDA(launch_pdl(attention_fwd_kernel, dim3(grid), dim3(ATT_THREADS), FWD_SMEM, stream(), maps, p));
     LG_CHECK_LAUNCH();
     return 0;
 }
@@ -674,7 +674,7 @@ int lg_attention_bwd(int dtype, const void* qkv, const void* out, const void* do
     }
     const int tiles = (int)(batch * heads);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    attention_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, stream()>>>(maps, p);
+    LG_CUDA(launch_pdl(attention_bwd_kernel, dim3(grid), dim3(ATT_THREADS), BWD_SMEM, stream(), maps, p));
     LG_CHECK_LAUNCH();
     return 0;
 }

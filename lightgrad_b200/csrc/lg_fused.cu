@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ x, in
                                                      T* __restrict__ lse, int64_t rows, int64_t cols,
                                                      unsigned int* __restrict__ errflag) {
     LG_PDL_TRIGGER();
+    LG_PDL_WAIT();
     __shared__ T sm[8];
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const T* p = x + row * ld;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const T* __restrict__ x, in
                                                      const T* __restrict__ gscale, T* __restrict__ dx, int64_t ld_dx,
                                                      int64_t rows, int64_t cols) {
     LG_PDL_TRIGGER();
+    LG_PDL_WAIT();
     // (p - onehot) / N * out_grad (loss.py:20-24) as one multiply by out_grad / N: the division by N moved out of the
     // 125 M-element loop (the kernel was issue-bound on it: 214 us for 1 GB of traffic)
     const T mul = gscale[0] / T(rows);
@@ -346,6 +348,7 @@ __global__ void __launch_bounds__(256, (NV <= 6 ? 4 : 2)) ln_fwd_vec_kernel(cons
                                                          int64_t rows, int cols, float eps) {
     // res != nullptr: the normalised input is x + res (residual connection), written to sum_out for backward
     LG_PDL_TRIGGER();
+    LG_PDL_WAIT();
     const int lane = threadIdx.x & 31;
     int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t row_step = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -423,6 +426,7 @@ ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
     // atomic_out: the three result pointers are the final vectors and every CTA adds its sums to them (red.add: 296
     // adds per address, spread over the kernel's life) -- no partial rows in HBM and no reduction launches afterwards
     LG_PDL_TRIGGER();
+    LG_PDL_WAIT();
     // [gamma : cols floats][8 warps x cols floats][8 warps x cols floats, only with dxsum_part]: gamma is re-read from
     // here every row (keeps it out of the register file so two CTAs fit on an SM); every warp parks its register
     // partials in its slot at the end; the third region accumulates the column sums of dx, row by row (each lane owns
@@ -684,9 +688,8 @@ int softmax_bwd(const void* y, const void* g, void* dx, int64_t rows, int64_t co
 template <typename T, typename L>
 int ce_fwd(const void* x, int64_t ld, const void* labels, void* loss_rows, void* lse, int64_t rows, int64_t cols) {
     int64_t cap = (int64_t)sm_count() * 8;
-    ce_fwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>((const T*)x, ld, (const L*)labels,
-                                                                              (T*)loss_rows, (T*)lse, rows, cols,
-                                                                              error_flag());
+    LG_CUDA(launch_pdl(ce_fwd_kernel<T, L>, dim3((unsigned)(rows < cap ? rows : cap)), dim3(256), 0, stream(), (const T*)x,
+                       ld, (const L*)labels, (T*)loss_rows, (T*)lse, rows, cols, error_flag()));
     LG_CHECK_LAUNCH();
     return 0;
 }
@@ -694,8 +697,8 @@ template <typename T, typename L>
 int ce_bwd(const void* x, int64_t ld, const void* labels, const void* lse, const void* gs, void* dx, int64_t ld_dx,
            int64_t rows, int64_t cols) {
     int64_t cap = (int64_t)sm_count() * 8;
-    ce_bwd_kernel<T, L><<<(int)(rows < cap ? rows : cap), 256, 0, stream()>>>(
-        (const T*)x, ld, (const L*)labels, (const T*)lse, (const T*)gs, (T*)dx, ld_dx, rows, cols);
+    LG_CUDA(launch_pdl(ce_bwd_kernel<T, L>, dim3((unsigned)(rows < cap ? rows : cap)), dim3(256), 0, stream(), (const T*)x,
+                       ld, (const L*)labels, (const T*)lse, (const T*)gs, (T*)dx, ld_dx, rows, cols));
     LG_CHECK_LAUNCH();
     return 0;
 }
@@ -781,9 +784,9 @@ static int layernorm_fwd_impl(int dtype, const void* x, const void* res, void* s
         int64_t cap2 = (int64_t)sm_count() * 4;
         int g2 = (int)(blocks < cap2 ? blocks : cap2);
 #define LN_F(NV_)                                                                                           \
-    ln_fwd_vec_kernel<NV_><<<g2, 256, 0, stream()>>>((const float*)x, (const float*)res, (float*)sum_out,           \
-                                                     (const float*)gamma, (const float*)beta, (float*)y,            \
-                                                     (float*)mean, (float*)rstd, rows, (int)cols, (float)eps)
+    launch_pdl(ln_fwd_vec_kernel<NV_>, dim3((unsigned)g2), dim3(256), 0, stream(), (const float*)x,                \
+               (const float*)res, (float*)sum_out, (const float*)gamma, (const float*)beta, (float*)y,             \
+               (float*)mean, (float*)rstd, rows, (int)cols, (float)eps)
         if (nv == 2) LN_F(2); else if (nv == 4) LN_F(4); else if (nv == 6) LN_F(6); else LN_F(8);
 #undef LN_F
         LG_CHECK_LAUNCH();
@@ -861,11 +864,10 @@ int lg_layernorm_bwd(int dtype, const void* x, const void* gamma, const void* me
             cudaFuncSetAttribute(ln_bwd_vec_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 1024 * 4); \
             attr_done = true;                                                                                  \
         }                                                                                                      \
-        ln_bwd_vec_kernel<NV_><<<grid, 256, smem_fast, stream()>>>((const float*)x, (const float*)gamma,      \
-                                                              (const float*)mean, (const float*)rstd,          \
-                                                              (const float*)g, (float*)dx, (float*)pg,         \
-                                                              (float*)pb, (float*)px, rows, (int)cols, part_ld, \
-                                                              atomic_out ? 1 : 0);                             \
+        launch_pdl(ln_bwd_vec_kernel<NV_>, dim3((unsigned)grid), dim3(256), smem_fast, stream(),              \
+                   (const float*)x, (const float*)gamma, (const float*)mean, (const float*)rstd,              \
+                   (const float*)g, (float*)dx, (float*)pg, (float*)pb, (float*)px, rows, (int)cols, part_ld,   \
+                   atomic_out ? 1 : 0);                                                                        \
     } while (0)
         if (nv == 2) LN_B(2); else if (nv == 4) LN_B(4); else if (nv == 6) LN_B(6); else LN_B(8);
 #undef LN_B
