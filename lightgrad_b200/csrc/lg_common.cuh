@@ -49,6 +49,11 @@ void comm_defer_free(void* p);   // block from tmp_alloc that the collective str
 int side_join();
 int side_order_before(cudaStream_t other);
 cudaStream_t comm_stream();   // collective stream
+// lg_nccl.cu: 0 = no communicator or no error; 1 = NCCL reported an asynchronous error (message set, communicator
+// aborted).  nccl_abort(): abort the communicator so that its kernels leave the GPU (a peer died / timed out).
+int nccl_async_check();
+void nccl_abort(const char* why);
+bool nccl_active();
 int sm_count();
 void count_launch(int n = 1);
 int ensure_init();

@@ -19,6 +19,9 @@ struct Api {
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    // optional (fail-fast on rank death): absent symbols only disable the check
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
 } api;
 
 ncclComm_t g_comm_nccl = nullptr;
@@ -44,6 +47,8 @@ int load_api() {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+    *(void**)(&api.CommGetAsyncError) = dlsym(api.h, "ncclCommGetAsyncError");
+    *(void**)(&api.CommAbort) = dlsym(api.h, "ncclCommAbort");
     return 0;
 }
 
@@ -54,6 +59,31 @@ int load_api() {
     } while (0)
 
 }  // namespace
+
+namespace lg {
+
+bool nccl_active() { return g_comm_nccl != nullptr; }
+
+void nccl_abort(const char* why) {
+    if (!g_comm_nccl) return;
+    // ncclCommAbort raises the communicator's abort flag: collective kernels still spinning for a peer leave the GPU
+    if (api.CommAbort) api.CommAbort(g_comm_nccl);
+    g_comm_nccl = nullptr;
+    (void)why;
+}
+
+int nccl_async_check() {
+    if (!g_comm_nccl || !api.CommGetAsyncError) return 0;
+    ncclResult_t state = ncclSuccess;
+    if (api.CommGetAsyncError(g_comm_nccl, &state) != ncclSuccess || state == ncclSuccess || state == ncclInProgress)
+        return 0;
+    set_error("NCCL reported an asynchronous error (%s): a peer rank died or a link failed; the communicator was aborted",
+              api.GetErrorString ? api.GetErrorString(state) : "?");
+    nccl_abort("async error");
+    return 1;
+}
+
+}  // namespace lg
 
 static int ensure_events() {
     if (!g_ev_fork) LG_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));

@@ -3,6 +3,8 @@
 // queue + a MemoryPool per device (opencl/device.py:51-115) and blocking enqueue_copy
 // (opencl/tensor.py:74-93).  Here copies and kernels are stream-ordered and only D2H blocks.
 #include <unordered_set>
+#include <chrono>
+#include <unistd.h>
 #include "lg_common.cuh"
 #include <mutex>
 #include <unordered_map>
@@ -303,12 +305,42 @@ int lg_device_props(int* sm_count_, int* cc_major, int* cc_minor, size_t* total_
     return 0;
 }
 
+// Synchronise a stream.  With a NCCL communicator alive the wait is watched: a collective whose peer has died spins on
+// the GPU for ever, so the stream is polled, NCCL's asynchronous error state is checked, and after LG_SYNC_TIMEOUT_S
+// (default 120; 0 = wait for ever) the communicator is aborted -- its kernels leave the GPU -- and the call fails instead
+// of hanging the rank (fail fast on rank death).  The multicast exchange kernels bound their own
+// waits (20 s, then trap).  Single-GPU processes take the plain cudaStreamSynchronize.
+static int watched_sync(cudaStream_t st) {
+    if (!nccl_active()) {
+        LG_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    static const double limit = getenv("LG_SYNC_TIMEOUT_S") ? atof(getenv("LG_SYNC_TIMEOUT_S")) : 120.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned long spins = 0;; ++spins) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) return 0;
+        if (q != cudaErrorNotReady) return set_error("cudaStreamQuery failed: %s", cudaGetErrorString(q));
+        if ((spins & 1023) == 1023) {
+            if (nccl_async_check()) return 1;
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (limit > 0 && waited > limit) {
+                nccl_abort("timeout");
+                cudaStreamSynchronize(st);       // the aborted collective's kernels exit
+                return set_error("synchronisation did not finish within %.0f s (LG_SYNC_TIMEOUT_S): a peer rank is gone "
+                                 "or stuck; the NCCL communicator was aborted", limit);
+            }
+            if (waited > 0.05) usleep(200);       // long waits: stop burning the core
+        }
+    }
+}
+
 int lg_sync(void) {
     LG_INIT();
     LG_REQUIRE(!g_capturing, "lg_sync: cannot synchronise while a step is being captured into a CUDA graph");
     if (side_join()) return 1;
-    LG_CUDA(cudaStreamSynchronize(g_stream));
-    LG_CUDA(cudaStreamSynchronize(g_comm));
+    if (watched_sync(g_stream)) return 1;
+    if (watched_sync(g_comm)) return 1;
     return check_device_error();
 }
 
@@ -409,7 +441,7 @@ int lg_memcpy_d2h(void* dst, const void* src, size_t nbytes) {
                              "being captured into a CUDA graph");
     if (side_join()) return 1;
     if (nbytes) LG_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, g_stream));
-    LG_CUDA(cudaStreamSynchronize(g_stream));
+    if (watched_sync(g_stream)) return 1;
     return check_device_error();
 }
 

@@ -57,3 +57,32 @@ def test_two_gpu_gradients_equal_single_gpu(tmp_path, mode, tol, exchange):
     assert res['param_rel_err_after_3_steps'] <= 0.05, res
     assert res['replica_checksum_spread'] == 0.0, res
     assert abs(res['local_losses'][0] - res['global_losses'][0]) < 0.05
+
+
+def test_stuck_peer_fails_fast(tmp_path):
+    """A collective whose peer never arrives must not hang the rank: the watched synchronisation
+    aborts the communicator after LG_SYNC_TIMEOUT_S and raises; the process stays usable."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = tmp_path / 'stuck.json'
+    port = 29300 + (os.getpid() % 300)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port), LG_SYNC_TIMEOUT_S='4')
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'sync_timeout_worker.py'), str(out)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    logs = []
+    for p in procs:
+        try:
+            logs.append(p.communicate(timeout=120)[0].decode())
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    res = json.load(open(out))
+    assert res['raised'], res
+    assert 'peer rank' in res['message'] and 'LG_SYNC_TIMEOUT_S' in res['message'], res
+    assert 3.5 <= res['seconds'] <= 10.0, res
+    assert res['after'] == 56.0
