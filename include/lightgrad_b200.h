@@ -103,6 +103,9 @@ int lg_init(int device);                 /* idempotent; binds the process to one
 int lg_device(int* device);
 int lg_device_props(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 int lg_sync(void);                        /* drain compute + comm streams                   */
+/* (with a NCCL communicator alive, lg_sync and lg_memcpy_d2h watch their wait: an asynchronous NCCL error, or no
+ *  completion within LG_SYNC_TIMEOUT_S seconds -- default 120, 0 = wait for ever -- aborts the communicator and fails
+ *  the call instead of hanging the rank on a collective whose peer is gone) */
 int lg_alloc(size_t nbytes, void** ptr);  /* caching, stream-ordered; 256-byte aligned      */
 int lg_free(void* ptr);                   /* returns the block to the cache                 */
 int lg_empty_cache(void);
