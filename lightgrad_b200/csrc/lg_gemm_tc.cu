@@ -122,24 +122,26 @@ __device__ __forceinline__ float bias_slice(const float* bias, int col, int N) {
     return (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
 }
 
-// GELU in the epilogue: only 4 warps per SM do this work, so tanh is formed as 1 - 2 / (exp(2u) + 1) from
-// ex2.approx and rcp.approx (abs. error ~2e-7, well inside the tf32 result's own rounding) instead of tanhf
-__device__ __forceinline__ float epi_tanh(float u) {
+// GELU in the epilogue.  With u = sqrt(2/pi) (x + 0.044715 x^3):  0.5 (1 + tanh u) = sigma(2u) = 1 / (1 + exp(-2u)), so
+//   gelu(x)  = x s,                                   s = 1 / (1 + 2^(x (k1 + k2 x^2))),  k1 = -2 log2(e) sqrt(2/pi)
+//   gelu'(x) = s + x s (1 - s) 2 u',                  2u' = 2 sqrt(2/pi) (1 + 3 * 0.044715 x^2)
+// -- one ex2.approx and one rcp.approx per element (abs. error ~2e-7, well inside the tf32 result's own rounding) and
+// 7 / 13 instructions instead of the 12 / 20 of the tanh form: the eight epilogue warps share their schedulers with
+// the TMA and MMA threads, and the last tile's epilogue of a launch is not hidden behind a main loop.
+__device__ __forceinline__ float epi_sigmoid2u(float x, float x2) {
+    constexpr float k1 = -2.0f * 1.4426950408889634f * 0.7978845608f, k2 = k1 * 0.044715f;
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * 2.885390081777927f));   // exp(2u) = 2^(2u log2 e)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * fmaf(k2, x2, k1)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return fmaf(-2.0f, r, 1.0f);
+    return r;
 }
-__device__ __forceinline__ float epi_gelu(float x) {
-    const float inner = (x * 0.7978845608f) * (1.0f + (0.044715f * x) * x);
-    return (0.5f * x) * (1.0f + epi_tanh(inner));
-}
+__device__ __forceinline__ float epi_gelu(float x) { return x * epi_sigmoid2u(x, x * x); }
 __device__ __forceinline__ float epi_gelu_bwd(float x, float g) {
-    const float c1 = 0.7978845608f, c2 = 0.044715f;
+    constexpr float c1 = 0.7978845608f, c2 = 0.044715f;
     const float x2 = x * x;
-    const float t = epi_tanh((x * c1) * (1.0f + c2 * x2));
-    const float du = c1 * (1.0f + 3.0f * c2 * x2);
-    return (0.5f * (1.0f + t) + (0.5f * x) * (1.0f - t * t) * du) * g;
+    const float s = epi_sigmoid2u(x, x2);
+    const float du2 = fmaf(6.0f * c1 * c2, x2, 2.0f * c1);
+    return fmaf((x * s) * (1.0f - s), du2, s) * g;
 }
 
 struct EpiTile {
