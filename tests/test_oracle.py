@@ -63,3 +63,30 @@ def test_leaf_hook_fires_after_last_contribution():
     for is_a, g in seen:
         want = (1 + np.e + 1) if is_a else 1.0
         np.testing.assert_allclose(g, want, rtol=1e-6)      # complete at the time the hook ran
+
+
+def test_leaf_hook_waits_for_wrapper_nodes_that_reach_the_leaf_by_closure():
+    # a WrapperFunction back-propagates through a private graph; a parameter it uses by closure receives a contribution
+    # the outer walk cannot count, so no leaf is reported as finished while such a node is still outstanding
+    from lightgrad_b200.autograd import Gradients, WrapperFunction
+    w = CpuTensor.from_numpy(np.full((3,), 2.0, dtype=np.float32))
+    x = CpuTensor.from_numpy(np.arange(3, dtype=np.float32))
+
+    @WrapperFunction.from_function
+    def scaled(t):
+        return t * w                       # w reached by closure, not as a parent of the wrapper node
+
+    seen = {}
+
+    def hook(t):
+        seen[id(t)] = t.grad.numpy().copy()
+    y = (scaled(x).sum() + (w * 3.0).sum())          # w is ALSO a direct parent of an outer node (processed first)
+    w.zero_grad(), x.zero_grad()
+    Gradients.leaf_hook = hook
+    try:
+        y.backward()
+    finally:
+        Gradients.leaf_hook = None
+    # at hook time w already held both contributions: 3 (direct) + x (through the wrapper's private graph)
+    np.testing.assert_allclose(seen[id(w)], 3.0 + np.arange(3), rtol=1e-6)
+    np.testing.assert_allclose(w.grad.numpy(), 3.0 + np.arange(3), rtol=1e-6)
