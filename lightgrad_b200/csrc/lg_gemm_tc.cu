@@ -15,6 +15,8 @@
 //   warps 2..9    epilogue (two per TMEM lane quarter, alternate 32-column chunks): tcgen05.ld 32x32b.x32 -> (+bias) -> swizzled smem -> TMA store
 //                 (cp.reduce.async.bulk.tensor .add when the K range is split across CTAs)
 //   two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// Most launches of a training step run the CTA-PAIR variant further down (cta_group::2, 256 x BN tile over two SMs, each
+// staging half of B): at 4-byte operands it is the L2 -> SM operand traffic, not the tensor pipe, that bounds a CTA.
 // BF16 mode (LG_GEMM_BF16_TC): the same kernels instantiated with 2-byte operands (ES = 2).  The byte geometry
 // of a stage is identical -- a k-block is still one 128-byte swizzle row (64 bf16 instead of 32 fp32), a UMMA
 // k-step still 32 bytes -- only the MN-major layout differs: 16-bit operands use the plain SWIZZLE_128B atoms
